@@ -1,0 +1,193 @@
+/*
+ * smcdet_b200.h -- C ABI of libsmcdet_b200.so, the B200 (sm_100a) implementation of the
+ * per-tile sequential Monte Carlo hot path of timwhite0/smcdet.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own: its seam is duck typing
+ * between SMCsampler, the Prior, the ImageModel and the MutationKernel.
+ * Each entry point below replaces the tensor program behind one of those methods; the
+ * citation on each is the reference interface it stands in for (file:line in the
+ * reference tree).  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors in practice);
+ *     the library never allocates persistent memory and never frees caller memory
+ *   - all tensors are contiguous, float32 unless stated, in the reference's layouts with
+ *     the [numH, numW] tile axes flattened to T:
+ *         tiles [T,h,w]   locs [T,N,D,2] (row, col)   fluxes [T,N,D]   counts [T,N]
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and re-entrant given distinct streams and buffers
+ *   - return value: 0 = ok, <0 = invalid argument (SMCDET_E_*), >0 = a cudaError_t;
+ *     smcdet_last_error_string() describes the last failure on the calling thread
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ */
+#ifndef SMCDET_B200_H
+#define SMCDET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCDET_ABI_VERSION 1
+
+enum {
+    SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
+    SMCDET_E_UNSUPPORTED = -2, /* shape outside what the kernels are instantiated for      */
+    SMCDET_E_TOO_LARGE = -3    /* D, tile or N beyond the compiled limits                  */
+};
+
+enum { SMCDET_MODEL_GAUSS_POISSON = 0, SMCDET_MODEL_M71_NORMAL = 1 };
+enum { SMCDET_COUNT_DISCRETE_UNIFORM = 0, SMCDET_COUNT_POISSON = 1 };
+enum { SMCDET_FLUX_PARETO = 0, SMCDET_FLUX_TRUNCATED_PARETO = 1, SMCDET_FLUX_NORMAL = 2 };
+enum { SMCDET_RESAMPLE_MULTINOMIAL = 0, SMCDET_RESAMPLE_SYSTEMATIC = 1 };
+
+/* status bits written (OR-ed) into the optional device status word of smcdet_mh_mutate */
+enum {
+    SMCDET_STATUS_OUT_OF_BOX = 1 /* a location or flux lies outside the proposal box on entry: the
+                                    reference would fail `assert (value >= lb).all() and (value <= ub).all()`
+                                    (smcdet/distributions.py:51) */
+};
+
+/* ImageModel / M71ImageModel constructor state: smcdet/images.py:7-23, :106-135 */
+typedef struct smcdet_model_params {
+    int32_t model_kind;
+    int32_t psf_radius;
+    float psf_stdev;               /* Gaussian PSF model (images.py:17)                      */
+    float sigma1, sigma2, sigmap;  /* M71 PSF (images.py:120); enter the formula un-squared  */
+    float beta, b, p0;
+    float psf_norm;                /* M71 normalising constant Z (images.py:122-135)          */
+    float background;
+    float adu_per_nmgy;            /* M71 only                                                */
+    float noise_additive;
+    float noise_multiplicative;
+    float normal_switch_rate;      /* Poisson -> Normal switch, 50000 (images.py:91)          */
+} smcdet_model_params;
+
+/* PointProcessPrior family: smcdet/prior.py:8-24, :78-101, :157-162, :192-199 */
+typedef struct smcdet_prior_params {
+    int32_t count_kind;
+    int32_t flux_kind;
+    int32_t min_objects, max_objects;
+    float count_rate;              /* Poisson mean: counts_rate*(H+2pad)*(W+2pad) (prior.py:93-97) */
+    float loc_low[2], loc_high[2]; /* Uniform location prior (prior.py:20-23)                 */
+    float flux_alpha;
+    float flux_lower;              /* Pareto scale / truncated-Pareto lower bound             */
+    float flux_upper;
+    float flux_logpdf_const;       /* truncated Pareto: distributions.py:69-74                */
+    float flux_mean, flux_stdev;   /* StarPrior (Normal flux)                                 */
+} smcdet_prior_params;
+
+/* SingleComponentMH constructor state + the box SMCsampler installs:
+ * smcdet/kernel.py:8-24, smcdet/sampler.py:36-37 */
+typedef struct smcdet_mh_params {
+    int32_t num_iters;
+    float locs_stdev;
+    float fluxes_stdev;
+    float fluxes_min, fluxes_max;
+    float locs_min[2], locs_max[2];
+} smcdet_mh_params;
+
+/* Injected draws for smcdet_mh_mutate (parity testing).  Entries are the draws the
+ * reference actually consumes per iteration (kernel.py:44, :47-61, :115):
+ * the chosen component and the uniforms of that component.  NULL tape => Philox. */
+typedef struct smcdet_draw_tape {
+    const int32_t *comp;  /* [iters,T,N]   */
+    const float *u_loc;   /* [iters,T,N,2] */
+    const float *u_flux;  /* [iters,T,N]   */
+    const float *u_acc;   /* [iters,T,N]   */
+} smcdet_draw_tape;
+
+/* Optional per-iteration traces of smcdet_mh_mutate; any member may be NULL. */
+typedef struct smcdet_mh_trace {
+    float *log_alpha;   /* [iters,T,N] log acceptance ratio before the clamp */
+    float *target_prop; /* [iters,T,N] log target of the proposal (log_num_target, kernel.py:64-70) */
+    int8_t *accept;     /* [iters,T,N] */
+} smcdet_mh_trace;
+
+int smcdet_version(void);
+const char *smcdet_last_error_string(void);
+
+/* ImageModel.loglikelihood / M71ImageModel.loglikelihood
+ * (smcdet/images.py:85-102, :159-175): fused render + per-pixel log-density + reduction.
+ * loglik [T,N]. */
+int smcdet_loglik(const smcdet_model_params *model, const float *tiles, const float *locs,
+                  const float *fluxes, float *loglik, int T, int N, int D, int h, int w,
+                  void *stream);
+
+/* ImageModel.psf (smcdet/images.py:28-76): dense PSF stack psf [T,h,w,N,D]. */
+int smcdet_psf(const smcdet_model_params *model, const float *locs, float *psf, int T, int N,
+               int D, int h, int w, void *stream);
+
+/* rate image of ImageModel.sample / loglikelihood (smcdet/images.py:78-89, :147-167):
+ * rate [T,h,w,N] = sum_d psf_d * flux_d (* adu_per_nmgy) + background. */
+int smcdet_render(const smcdet_model_params *model, const float *locs, const float *fluxes,
+                  float *rate, int T, int N, int D, int h, int w, void *stream);
+
+/* Prior.log_prob (smcdet/prior.py:67-75, :183-189, :220-226).  out [T,N]. */
+int smcdet_prior_logprob(const smcdet_prior_params *prior, const float *counts,
+                         const float *locs, const float *fluxes, float *out, int T, int N, int D,
+                         void *stream);
+
+/* Prior.sample, stratified branch (smcdet/prior.py:47-64, :201-217; distributions.py:76-85).
+ * M = (max_objects-min_objects+1)*num_per_count particles per tile.  u_locs [T,M,D,2] and
+ * u_fluxes [T,M,D] are injected uniforms; if NULL, Philox4x32-10 keyed by
+ * (seed, tile_ids[t] or t, particle) is used. */
+int smcdet_prior_sample(const smcdet_prior_params *prior, const float *u_locs,
+                        const float *u_fluxes, uint64_t seed, const int64_t *tile_ids,
+                        float *counts, float *locs, float *fluxes, int T, int num_per_count,
+                        int D, void *stream);
+
+/* SMCsampler.temper + SMCsampler.update_weights (smcdet/sampler.py:93-125, :181-196).
+ * Per tile: if do_temper, solve ESS(delta) = ess_threshold on [0, 1-tau] with Brent's method
+ * (same algorithm and tolerances as scipy.optimize.brentq(xtol=1e-6, rtol=1e-6)), or take
+ * delta = 1-tau if ESS(1-tau) >= ess_threshold; tau_prev <- tau, tau <- tau + delta.  Then
+ * weights = softmax((tau-tau_prev)*loglik), ess = 1/sum w^2, logz += max + log(mean exp).
+ * With do_temper = 0 the given tau / tau_prev are used as they are.
+ * tau, tau_prev, ess, logz [T]; wlog, weights [T,N]; funcalls [T] (nullable) counts objective
+ * evaluations. */
+int smcdet_temper_update(const float *loglik, float *tau, float *tau_prev, float ess_threshold,
+                         int do_temper, float *wlog, float *weights, float *ess, float *logz,
+                         int32_t *funcalls, int T, int N, void *stream);
+
+/* SMCsampler.resample, index part (smcdet/sampler.py:127-149): inclusive CDF of the weights in
+ * double precision, then for every draw the first k with cdf[k] >= u, clamped to [0,N-1].
+ *   multinomial: u [T,N] iid uniforms (double), searched against u*cdf[N-1]
+ *   systematic : u [T], draw i uses (i+u)/N
+ * u == NULL => Philox keyed by (seed, tile_ids[t] or t).  cdf_scratch [T,N] double. */
+int smcdet_resample(int method, const float *weights, const double *u, uint64_t seed,
+                    const int64_t *tile_ids, int64_t *index, double *cdf_scratch, int T, int N,
+                    void *stream);
+
+/* SMCsampler.resample, gather part (smcdet/sampler.py:150-168). */
+int smcdet_gather(const int64_t *index, const float *counts_in, const float *locs_in,
+                  const float *fluxes_in, float *counts_out, float *locs_out, float *fluxes_out,
+                  int T, int N, int D, void *stream);
+
+/* SingleComponentMH.run with log_target = SMCsampler.log_target
+ * (smcdet/kernel.py:26-130, smcdet/sampler.py:87-91): num_iters single-site random-walk MH
+ * sweeps, fused with the prior, the likelihood re-evaluation and accept/reject.
+ * locs/fluxes are updated in place; loglik_out [T,N] (nullable) receives the log-likelihood of
+ * the final state (what SMCsampler.temper recomputes at sampler.py:100-102); acc_rate [T] is
+ * the acceptance rate of the LAST iteration (kernel.py:130).  tape/trace/status/tile_ids are
+ * nullable; active [T] (nullable) skips tiles whose entry is 0. */
+int smcdet_mh_mutate(const smcdet_model_params *model, const smcdet_prior_params *prior,
+                     const smcdet_mh_params *mh, const float *tiles, const float *counts,
+                     float *locs, float *fluxes, const float *tau, float *loglik_out,
+                     float *acc_rate, const smcdet_draw_tape *tape, const smcdet_mh_trace *trace,
+                     uint64_t seed, uint64_t offset, const int64_t *tile_ids,
+                     const int32_t *active, int32_t *status, int T, int N, int D, int h, int w,
+                     void *stream);
+
+/* SMCsampler.prune (smcdet/sampler.py:198-219): keep stars strictly inside the tile with
+ * flux above the detection threshold, compacted to the front in their original order.
+ * counts_out [T,N] int64. */
+int smcdet_prune(const float *locs, const float *fluxes, float tile_h, float tile_w,
+                 float flux_threshold, int64_t *counts_out, float *locs_out, float *fluxes_out,
+                 int T, int N, int D, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCDET_B200_H */

@@ -1,0 +1,994 @@
+// smcdet_kernels.cu -- sm_100a kernels and C ABI of libsmcdet_b200.so.
+//
+// Hot path of timwhite0/smcdet (per-tile likelihood-tempered SMC):
+//   loglik_kernel         fused render + per-pixel log density + reduction (images.py:85-102, :159-175)
+//   mh_kernel             all num_iters single-site MH sweeps in one launch, likelihood updated
+//                         incrementally from a resident rate image (kernel.py:26-130, sampler.py:87-91)
+//   temper_update_kernel  on-device Brent solve of ESS(delta)=rho*N + softmax weights / ESS / logZ
+//                         (sampler.py:93-125, :181-196)
+//   resample_kernel       float64 CDF scan + binary search (sampler.py:127-149); gather_kernel (:150-168)
+//   prior_*, prune, psf, render: the small pieces around them
+//
+// Work decomposition of the two heavy kernels: a particle is owned by TPP consecutive lanes of a
+// warp (TPP = 1..32, a template parameter); each lane owns RPT = H/TPP rows of the tile and keeps
+// its RPT*W expected counts in registers.  TPP = 1 (one thread per particle, no shuffles, no
+// redundant scalar work) is used when there are enough particles to fill the 148 SMs; larger TPP
+// spreads a small problem over more threads and handles 16x16 / 32x32 tiles.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#ifdef SMC_HOSTSIM
+// unit tests compile this very file with g++ against tests/hostsim/cuda_shim.h (CPU emulation of
+// the CUDA execution model) to check the kernels' logic without a GPU; never part of the product
+#include "cuda_shim.h"
+#else
+#include <cuda_runtime.h>
+#define SMC_SHARED __shared__
+#define SMC_DYN_SHARED(type, name) extern __shared__ type name[]
+#define SMC_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include <cstdio>
+#include <cstring>
+
+#include "smcdet_math.cuh"
+
+using namespace smc;
+
+namespace {
+
+thread_local char g_err[256] = "ok";
+
+int fail(int code, const char* what) {
+    if (code > 0) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString((cudaError_t)code));
+    else snprintf(g_err, sizeof(g_err), "%s (code %d)", what, code);
+    return code;
+}
+
+#define SMC_REQUIRE(cond, code, msg) \
+    do { if (!(cond)) return fail((code), (msg)); } while (0)
+
+int launch_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, what);
+    return 0;
+}
+
+constexpr int kBT = 128;        // threads per block of the particle kernels
+constexpr int kMaxStars = 64;   // D limit (shared-memory staging)
+
+int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_num_sms = n;
+        else
+            g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+template <int TPP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// stage the tile and the block's particle catalogs (AoS in global memory, coalesced reads) into
+// shared memory as s_star[(d*3 + c) * PB + particle], c = 0 row, 1 col, 2 flux
+template <int MODEL, int HW, int PB>
+__device__ __forceinline__ void stage_block(const float* __restrict__ tile, const float* __restrict__ locs,
+                                            const float* __restrict__ fluxes, int n_here, int D,
+                                            float* s_tile, float* s_lgam, float* s_star) {
+    for (int i = threadIdx.x; i < HW; i += kBT) {
+        const float x = tile[i];
+        s_tile[i] = x;
+        s_lgam[i] = (MODEL == SMCDET_MODEL_GAUSS_POISSON) ? lgammaf(x + 1.0f) : 0.0f;
+    }
+    const int nl = n_here * 2 * D;
+    for (int i = threadIdx.x; i < nl; i += kBT) {
+        const int pi = i / (2 * D), r = i - pi * 2 * D;
+        s_star[((r >> 1) * 3 + (r & 1)) * PB + pi] = locs[i];
+    }
+    const int nf = n_here * D;
+    for (int i = threadIdx.x; i < nf; i += kBT) {
+        const int pi = i / D, d = i - pi * D;
+        s_star[(d * 3 + 2) * PB + pi] = fluxes[i];
+    }
+    // particles past the end of the tile: inert catalogs
+    for (int i = threadIdx.x; i < (PB - n_here) * 3 * D; i += kBT) {
+        const int pi = n_here + i / (3 * D), r = i % (3 * D);
+        s_star[r * PB + pi] = 0.0f;
+    }
+}
+
+template <int PB>
+__device__ __forceinline__ void unstage_block(float* __restrict__ locs, float* __restrict__ fluxes, int n_here,
+                                              int D, const float* s_star) {
+    const int nl = n_here * 2 * D;
+    for (int i = threadIdx.x; i < nl; i += kBT) {
+        const int pi = i / (2 * D), r = i - pi * 2 * D;
+        locs[i] = s_star[((r >> 1) * 3 + (r & 1)) * PB + pi];
+    }
+    const int nf = n_here * D;
+    for (int i = threadIdx.x; i < nf; i += kBT) {
+        const int pi = i / D, d = i - pi * D;
+        fluxes[i] = s_star[(d * 3 + 2) * PB + pi];
+    }
+}
+
+// full render of the lane's pixels from the staged catalog (without the background)
+template <int MODEL, int RPT, int W, int PB>
+__device__ __forceinline__ void render_rows(const ModelK& m, const float* s_star, int pi, int D, int row0,
+                                            float (&acc)[RPT * W]) {
+#pragma unroll
+    for (int p = 0; p < RPT * W; ++p) acc[p] = 0.0f;
+    for (int d = 0; d < D; ++d) {
+        const float f = s_star[(d * 3 + 2) * PB + pi];
+        if (f != 0.0f) {  // empty slots contribute exactly zero (prior.py:61-62 zero-fills them)
+            const float l0 = s_star[(d * 3 + 0) * PB + pi];
+            const float l1 = s_star[(d * 3 + 1) * PB + pi];
+            star_accumulate<MODEL, RPT, W>(m, l0, l1, m.c0 * f, row0, acc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: fused render + log-likelihood
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int H, int W, int TPP>
+__global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float* __restrict__ tiles,
+                                                     const float* __restrict__ locs,
+                                                     const float* __restrict__ fluxes, float* __restrict__ out,
+                                                     int N, int D, int blocks_per_tile) {
+    constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
+    SMC_DYN_SHARED(float, smem);
+    float* s_tile = smem;
+    float* s_lgam = s_tile + HW;
+    float* s_star = s_lgam + HW;
+
+    const int t = blockIdx.x / blocks_per_tile;
+    const int n0 = (blockIdx.x - t * blocks_per_tile) * PB;
+    const int n_here = min(PB, N - n0);
+    const size_t pbase = (size_t)t * N + n0;
+    stage_block<MODEL, HW, PB>(tiles + (size_t)t * HW, locs + pbase * 2 * D, fluxes + pbase * D, n_here, D, s_tile,
+                               s_lgam, s_star);
+    __syncthreads();
+
+    const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
+    float acc[PPT];
+    render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
+    const float part = pixel_loglik_sum<MODEL, PPT>(m, s_tile + row0 * W, s_lgam + row0 * W,
+                                                    [&](int p) { return acc[p] + m.bg; });
+    const float ll = group_sum<TPP>(part);
+    if (sub == 0 && pi < n_here) out[pbase + pi] = ll;
+}
+
+// any tile shape: one warp per particle, lanes stride over pixels, direct PSF evaluation
+__global__ void __launch_bounds__(kBT) loglik_generic_kernel(const ModelK m, const float* __restrict__ tiles,
+                                                             const float* __restrict__ locs,
+                                                             const float* __restrict__ fluxes,
+                                                             float* __restrict__ out, int T, int N, int D, int h,
+                                                             int w) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (size_t)blockIdx.x * (kBT / 32) + (threadIdx.x >> 5);
+    if (warp >= (size_t)T * N) return;
+    const int t = (int)(warp / N);
+    const float* tile = tiles + (size_t)t * h * w;
+    const float* l = locs + warp * 2 * D;
+    const float* f = fluxes + warp * D;
+    float acc = 0.0f;
+    for (int p = lane; p < h * w; p += 32) {
+        const int i = p / w, j = p - i * w;
+        float rate = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            const float fd = f[d];
+            if (fd != 0.0f) rate = fmaf(m.c0 * fd, psf_direct(m, l[2 * d], l[2 * d + 1], i, j), rate);
+        }
+        rate += m.bg;
+        const float x = tile[p];
+        if (m.kind == SMCDET_MODEL_M71_NORMAL) {
+            const float var = fmaf(m.nm, rate, m.na), dd = x - rate;
+            acc += fmaf(-0.5f * dd * dd, rcp_fast(var), fmaf(-0.5f * kLn2, lg2_fast(var), -kLogSqrt2Pi));
+        } else {
+            const float lg = lg2_fast(rate) * kLn2;
+            if (rate > m.nswitch) {
+                const float dd = x - rate;
+                acc += fmaf(-0.5f * dd * dd, rcp_fast(rate), fmaf(-0.5f, lg, -kLogSqrt2Pi));
+            } else {
+                acc += ((x == 0.0f) ? 0.0f : x * lg) - rate - lgammaf(x + 1.0f);
+            }
+        }
+    }
+    acc = group_sum<32>(acc);
+    if (lane == 0) out[warp] = acc;
+}
+
+// dense PSF stack [T,h,w,N,D] (images.py:28-76) and rate image [T,h,w,N] (images.py:87-89)
+__global__ void psf_kernel(const ModelK m, float norm, const float* __restrict__ locs, float* __restrict__ out,
+                           int T, int N, int D, int h, int w) {
+    const size_t total = (size_t)T * h * w * N * D;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        size_t r = e;
+        const int d = (int)(r % D); r /= D;
+        const int n = (int)(r % N); r /= N;
+        const int j = (int)(r % w); r /= w;
+        const int i = (int)(r % h); r /= h;
+        const int t = (int)r;
+        const float* l = locs + (((size_t)t * N + n) * D + d) * 2;
+        out[e] = norm * psf_direct(m, l[0], l[1], i, j);
+    }
+}
+
+__global__ void render_kernel(const ModelK m, const float* __restrict__ locs, const float* __restrict__ fluxes,
+                              float* __restrict__ out, int T, int N, int D, int h, int w) {
+    const size_t total = (size_t)T * h * w * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        size_t r = e;
+        const int n = (int)(r % N); r /= N;
+        const int j = (int)(r % w); r /= w;
+        const int i = (int)(r % h); r /= h;
+        const int t = (int)r;
+        const size_t pn = (size_t)t * N + n;
+        float rate = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            const float fd = fluxes[pn * D + d];
+            if (fd != 0.0f)
+                rate = fmaf(m.c0 * fd, psf_direct(m, locs[(pn * D + d) * 2], locs[(pn * D + d) * 2 + 1], i, j), rate);
+        }
+        out[e] = rate + m.bg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prior
+// ---------------------------------------------------------------------------------------------
+__global__ void prior_logprob_kernel(const smcdet_prior_params p, const float* __restrict__ counts,
+                                     const float* __restrict__ locs, const float* __restrict__ fluxes,
+                                     float* __restrict__ out, size_t TN, int D) {
+    const size_t pn = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pn >= TN) return;
+    const float* l = locs + pn * 2 * D;
+    const float* f = fluxes + pn * D;
+    out[pn] = prior_logprob_catalog(p, counts[pn], D, [&](int d, float& l0, float& l1, float& fv) {
+        l0 = l[2 * d]; l1 = l[2 * d + 1]; fv = f[d];
+    });
+}
+
+__global__ void prior_sample_kernel(const smcdet_prior_params p, const float* __restrict__ u_locs,
+                                    const float* __restrict__ u_fluxes, uint64_t seed,
+                                    const int64_t* __restrict__ tile_ids, float* __restrict__ counts,
+                                    float* __restrict__ locs, float* __restrict__ fluxes, int T, int M,
+                                    int num_per_count, int D) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per star slot
+    if (e >= (size_t)T * M * D) return;
+    const int d = (int)(e % D);
+    const size_t pn = e / D;
+    const int n = (int)(pn % M), t = (int)(pn / M);
+    const float c = (float)(p.min_objects + n / num_per_count);
+    if (d == 0) counts[pn] = c;
+    float u0, u1, uf;
+    if (u_locs != nullptr) {
+        u0 = u_locs[2 * e]; u1 = u_locs[2 * e + 1]; uf = u_fluxes[e];
+    } else {
+        const uint64_t tid = tile_ids ? (uint64_t)tile_ids[t] : (uint64_t)t;
+        const Philox4 r = philox4x32_10((uint32_t)n, (uint32_t)tid, (uint32_t)d, kStreamPriorLocs, (uint32_t)seed,
+                                        (uint32_t)(seed >> 32));
+        u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]);
+    }
+    const float mask = ((float)d < c) ? 1.0f : 0.0f;
+    // torch Uniform.rsample: low + rand*(high-low) (prior.py:59)
+    locs[2 * e] = (p.loc_low[0] + u0 * (p.loc_high[0] - p.loc_low[0])) * mask;
+    locs[2 * e + 1] = (p.loc_low[1] + u1 * (p.loc_high[1] - p.loc_low[1])) * mask;
+    float fl;
+    if (p.flux_kind == SMCDET_FLUX_TRUNCATED_PARETO) {
+        // distributions.py:76-85
+        const float Ua = powf(p.flux_upper, p.flux_alpha), La = powf(p.flux_lower, p.flux_alpha);
+        const float num = Ua - uf * Ua + uf * La;
+        fl = powf(num / (La * Ua), -1.0f / p.flux_alpha);
+    } else if (p.flux_kind == SMCDET_FLUX_PARETO) {
+        // inverse-cdf form of torch Pareto.sample (Exponential(alpha) -> exp -> * scale)
+        fl = p.flux_lower * expf(-log1pf(-uf) / p.flux_alpha);
+    } else {
+        const float q = clamp_f(uf, 1e-7f, 1.0f - 1e-7f);
+        fl = p.flux_mean + p.flux_stdev * kSqrt2 * erfinv_f(2.0f * q - 1.0f);
+    }
+    fluxes[e] = fl * mask;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: adaptive tempering + weight update, one block per tile
+// ---------------------------------------------------------------------------------------------
+constexpr int kTB = 256;
+
+__device__ __forceinline__ double block_sum2(double a, double& b_inout, double* s_red) {
+    // reduces (a, b) over the block; every thread returns the totals (a as return, b by reference)
+    double b = b_inout;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();  // protect s_red from the previous use
+    if (lane == 0) { s_red[2 * wid] = a; s_red[2 * wid + 1] = b; }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int i = 0; i < kTB / 32; ++i) { ta += s_red[2 * i]; tb += s_red[2 * i + 1]; }
+    b_inout = tb;
+    return ta;
+}
+
+__device__ __forceinline__ float block_max(float v, float* s_redf) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_redf[wid] = v;
+    __syncthreads();
+    float t = s_redf[0];
+#pragma unroll
+    for (int i = 1; i < kTB / 32; ++i) t = fmaxf(t, s_redf[i]);
+    return t;
+}
+
+// ESS(delta) - threshold with ESS = (sum e)^2 / sum e^2, e_i = exp(delta*(l_i - max l))
+// (sampler.py:93-97; exp(2 delta l) = e^2 so one exponential per particle serves both sums)
+__device__ __forceinline__ double ess_objective(const float* __restrict__ ll, int N, float mx, double delta,
+                                                double thr, double* s_red) {
+    const float dl2e = (float)delta * kLog2e;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < N; i += kTB) {
+        const float l = ll[i];
+        float e = 0.0f;
+        if (fabsf(l) <= 3.4028234663852886e38f) e = (dl2e == 0.0f) ? 1.0f : ex2_fast(dl2e * (l - mx));
+        s1 += (double)e;
+        s2 += (double)e * (double)e;
+    }
+    s1 = block_sum2(s1, s2, s_red);
+    return s1 * s1 / s2 - thr;
+}
+
+__global__ void __launch_bounds__(kTB) temper_update_kernel(const float* __restrict__ loglik, float* __restrict__ tau,
+                                                            float* __restrict__ tau_prev, float ess_threshold,
+                                                            int do_temper, float* __restrict__ wlog,
+                                                            float* __restrict__ weights, float* __restrict__ ess,
+                                                            float* __restrict__ logz, int32_t* __restrict__ funcalls,
+                                                            int N) {
+    SMC_SHARED double s_red[2 * (kTB / 32)];
+    SMC_SHARED float s_redf[kTB / 32];
+    const int t = blockIdx.x;
+    const float* ll = loglik + (size_t)t * N;
+
+    float tau_old, tau_new;
+    if (do_temper) {
+        float mx = -INFINITY;
+        for (int i = threadIdx.x; i < N; i += kTB) {
+            const float l = ll[i];
+            if (fabsf(l) <= 3.4028234663852886e38f) mx = fmaxf(mx, l);
+        }
+        mx = block_max(mx, s_redf);
+        if (mx == -INFINITY) mx = 0.0f;
+        tau_old = tau[t];
+        const double thr = (double)ess_threshold;
+        const double hi = 1.0 - (double)tau_old;
+        int calls = 1;
+        double delta = hi;
+        const double f_hi = ess_objective(ll, N, mx, hi, thr, s_red);
+        if (f_hi < 0.0) {
+            // scipy evaluates both ends again before iterating
+            const double f_lo = ess_objective(ll, N, mx, 0.0, thr, s_red);
+            calls += 2;
+            Brent b;
+            b.start(0.0, hi, f_lo, f_hi, 1e-6, 1e-6);
+            while (!b.done) {  // uniform across the block: every thread holds the same state
+                const double f = ess_objective(ll, N, mx, b.x, thr, s_red);
+                ++calls;
+                b.step(f);
+            }
+            delta = b.x;
+        }
+        tau_new = tau_old + (float)delta;
+        if (threadIdx.x == 0) {
+            tau_prev[t] = tau_old;
+            tau[t] = tau_new;
+            if (funcalls) funcalls[t] = calls;
+        }
+    } else {
+        tau_old = tau_prev[t];
+        tau_new = tau[t];
+    }
+
+    // update_weights (sampler.py:181-196)
+    const float dt = tau_new - tau_old;
+    float* wl = wlog + (size_t)t * N;
+    float* wt = weights + (size_t)t * N;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += kTB) {
+        float v = dt * ll[i];
+        // torch.nan_to_num(x, -inf): nan -> -inf, +-inf -> +-FLT_MAX
+        if (v != v) v = -INFINITY;
+        else if (v == INFINITY) v = 3.4028234663852886e38f;
+        else if (v == -INFINITY) v = -3.4028234663852886e38f;
+        wl[i] = v;
+        m = fmaxf(m, v);
+    }
+    m = block_max(m, s_redf);
+    double s = 0.0, unused = 0.0;
+    for (int i = threadIdx.x; i < N; i += kTB) s += (double)expf(wl[i] - m);
+    s = block_sum2(s, unused, s_red);
+    double s2 = 0.0;
+    unused = 0.0;
+    const float sf = (float)s;
+    for (int i = threadIdx.x; i < N; i += kTB) {
+        const float wv = expf(wl[i] - m) / sf;
+        wt[i] = wv;
+        s2 += (double)wv * (double)wv;
+    }
+    s2 = block_sum2(s2, unused, s_red);
+    if (threadIdx.x == 0) {
+        ess[t] = (float)(1.0 / s2);
+        logz[t] = logz[t] + m + logf(sf / (float)N);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 3: resampling -- float64 inclusive CDF (per-thread chunks + warp-shuffle scan of the chunk
+// totals) and one binary search per draw; one block per tile
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTB) resample_kernel(int method, const float* __restrict__ weights,
+                                                       const double* __restrict__ u, uint64_t seed,
+                                                       const int64_t* __restrict__ tile_ids,
+                                                       int64_t* __restrict__ index, double* __restrict__ cdf_all,
+                                                       int N) {
+    SMC_SHARED double s_warp[kTB / 32];
+    const int t = blockIdx.x;
+    const float* w = weights + (size_t)t * N;
+    double* cdf = cdf_all + (size_t)t * N;
+    const int chunk = (N + kTB - 1) / kTB;
+    const int lo = min(N, (int)threadIdx.x * chunk), hi = min(N, lo + chunk);
+    double local = 0.0;
+    for (int i = lo; i < hi; ++i) local += (double)w[i];
+    // inclusive scan of the chunk totals across the block
+    double incl = local;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    double base = 0.0;
+    for (int i = 0; i < wid; ++i) base += s_warp[i];
+    double run = base + (incl - local);
+    for (int i = lo; i < hi; ++i) {
+        run += (double)w[i];
+        cdf[i] = run;
+    }
+    __syncthreads();
+    const double total = cdf[N - 1];
+    const uint64_t tid = tile_ids ? (uint64_t)tile_ids[t] : (uint64_t)t;
+    double u_sys = 0.0;
+    if (method == SMCDET_RESAMPLE_SYSTEMATIC) {
+        if (u != nullptr) u_sys = u[t];
+        else {
+            const Philox4 r = philox4x32_10(0u, (uint32_t)tid, (uint32_t)(tid >> 32), kStreamResample ^ 1u,
+                                            (uint32_t)seed, (uint32_t)(seed >> 32));
+            u_sys = u01_d(r.v[0], r.v[1]);
+        }
+    }
+    for (int i = threadIdx.x; i < N; i += kTB) {
+        double ui;
+        if (method == SMCDET_RESAMPLE_SYSTEMATIC) {
+            ui = ((double)i + u_sys) / (double)N;
+        } else {
+            double uu;
+            if (u != nullptr) uu = u[(size_t)t * N + i];
+            else {
+                const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)tid, (uint32_t)(tid >> 32), kStreamResample,
+                                                (uint32_t)seed, (uint32_t)(seed >> 32));
+                uu = u01_d(r.v[0], r.v[1]);
+            }
+            ui = uu * total;
+        }
+        int a = 0, b = N;  // first k with cdf[k] >= ui (torch.bucketize, right=False)
+        while (a < b) {
+            const int mid = a + ((b - a) >> 1);
+            if (cdf[mid] >= ui) b = mid; else a = mid + 1;
+        }
+        index[(size_t)t * N + i] = (int64_t)min(max(a, 0), N - 1);
+    }
+}
+
+__global__ void gather_kernel(const int64_t* __restrict__ index, const float* __restrict__ counts_in,
+                              const float* __restrict__ locs_in, const float* __restrict__ fluxes_in,
+                              float* __restrict__ counts_out, float* __restrict__ locs_out,
+                              float* __restrict__ fluxes_out, int T, int N, int D) {
+    const int row = 3 * D + 1;
+    const size_t total = (size_t)T * N * row;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t pn = e / row;
+        const int c = (int)(e - pn * row);
+        const size_t t = pn / N;
+        const size_t src = t * N + (size_t)index[pn];
+        if (c < 2 * D) locs_out[pn * 2 * D + c] = locs_in[src * 2 * D + c];
+        else if (c < 3 * D) fluxes_out[pn * D + (c - 2 * D)] = fluxes_in[src * D + (c - 2 * D)];
+        else counts_out[pn] = counts_in[src];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 4: fused single-component MH
+// ---------------------------------------------------------------------------------------------
+struct MHArgs {
+    ModelK m;
+    smcdet_prior_params prior;
+    smcdet_mh_params mh;
+    const float* tiles;
+    const float* counts;
+    float* locs;
+    float* fluxes;
+    const float* tau;
+    float* loglik_out;
+    float* acc_count;
+    const int32_t* tape_comp;
+    const float* tape_u_loc;
+    const float* tape_u_flux;
+    const float* tape_u_acc;
+    float* tr_log_alpha;
+    float* tr_target_prop;
+    int8_t* tr_accept;
+    uint64_t seed, offset;
+    const int64_t* tile_ids;
+    const int32_t* active;
+    int32_t* status;
+    int T, N, D, blocks_per_tile;
+};
+
+template <int MODEL, int H, int W, int TPP>
+__global__ void __launch_bounds__(kBT) mh_kernel(const MHArgs a) {
+    constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
+    SMC_DYN_SHARED(float, smem);
+    float* s_tile = smem;
+    float* s_lgam = s_tile + HW;
+    float* s_star = s_lgam + HW;              // [3*D][PB]
+    float* s_rate = s_star + 3 * a.D * PB;    // [PPT][kBT]
+
+    const int t = blockIdx.x / a.blocks_per_tile;
+    if (a.active != nullptr && a.active[t] == 0) return;
+    const int N = a.N, D = a.D;
+    const int n0 = (blockIdx.x - t * a.blocks_per_tile) * PB;
+    const int n_here = min(PB, N - n0);
+    const size_t pbase = (size_t)t * N + n0;
+    stage_block<MODEL, HW, PB>(a.tiles + (size_t)t * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
+                               s_tile, s_lgam, s_star);
+    __syncthreads();
+
+    const ModelK& m = a.m;
+    const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
+    const bool valid = pi < n_here;
+    const size_t pn = pbase + pi;
+    const float* xs = s_tile + row0 * W;
+    const float* lg = s_lgam + row0 * W;
+    float* my_rate = s_rate + threadIdx.x;
+    const float* my_star = s_star + pi;
+
+    // ---- state on entry: rate image, log-likelihood, log prior, cached log target (kernel.py:88-96)
+    float acc[PPT];
+    render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) my_rate[p * kBT] = acc[p] + m.bg;
+    float ll = group_sum<TPP>(pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int p) { return acc[p] + m.bg; }));
+    const float count = valid ? a.counts[pn] : (float)D;
+    const float tau = a.tau[t];
+    const float prior0 = prior_logprob_catalog(a.prior, count, D, [&](int d, float& l0, float& l1, float& f) {
+        l0 = my_star[(d * 3 + 0) * PB]; l1 = my_star[(d * 3 + 1) * PB]; f = my_star[(d * 3 + 2) * PB];
+    });
+    float cached = prior0 + tau * ll;
+
+    if (a.status != nullptr && valid && sub == 0) {
+        bool oob = false;
+        for (int d = 0; d < D; ++d) {
+            const float l0 = my_star[(d * 3 + 0) * PB], l1 = my_star[(d * 3 + 1) * PB], f = my_star[(d * 3 + 2) * PB];
+            oob |= !(l0 >= a.mh.locs_min[0] && l0 <= a.mh.locs_max[0] && l1 >= a.mh.locs_min[1] &&
+                     l1 <= a.mh.locs_max[1] && f >= a.mh.fluxes_min && f <= a.mh.fluxes_max);
+        }
+        if (oob) atomicOr(a.status, SMCDET_STATUS_OUT_OF_BOX);
+    }
+
+    const uint64_t tile_key = a.tile_ids ? (uint64_t)a.tile_ids[t] : (uint64_t)t;
+    const uint32_t pidx = (uint32_t)(n0 + pi);
+    const float sl = a.mh.locs_stdev, sf = a.mh.fluxes_stdev;
+    int last_acc = 0;
+
+    for (int it = 0; it < a.mh.num_iters; ++it) {
+        // ---- draws: component, 2 location uniforms, flux uniform, accept uniform
+        int k = 0;
+        float u0 = 0.5f, u1 = 0.5f, uf = 0.5f, ua = 0.5f;
+        const size_t e = ((size_t)it * a.T + t) * N + (n0 + pi);
+        if (a.tape_comp != nullptr) {
+            if (valid) {
+                k = a.tape_comp[e];
+                u0 = a.tape_u_loc[2 * e]; u1 = a.tape_u_loc[2 * e + 1];
+                uf = a.tape_u_flux[e]; ua = a.tape_u_acc[e];
+            }
+        } else {
+            const uint32_t c2 = (uint32_t)(a.offset << 16) ^ (uint32_t)it;
+            const Philox4 r = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHDraws, (uint32_t)a.seed,
+                                            (uint32_t)(a.seed >> 32));
+            const Philox4 rc = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHComp, (uint32_t)a.seed,
+                                             (uint32_t)(a.seed >> 32));
+            u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]); ua = u01_f(r.v[3]);
+            k = (int)(((uint64_t)rc.v[0] * (uint64_t)D) >> 32);
+        }
+
+        // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
+        const float l0 = my_star[(k * 3 + 0) * PB], l1 = my_star[(k * 3 + 1) * PB], f = my_star[(k * 3 + 2) * PB];
+        const TruncNormal q0 = truncnormal_make(l0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
+        const TruncNormal q1 = truncnormal_make(l1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
+        const TruncNormal qf = truncnormal_make(f, sf, a.mh.fluxes_min, a.mh.fluxes_max);
+        const float pl0 = truncnormal_draw(q0, l0, sl, a.mh.locs_min[0], a.mh.locs_max[0], u0);
+        const float pl1 = truncnormal_draw(q1, l1, sl, a.mh.locs_min[1], a.mh.locs_max[1], u1);
+        const float pf = truncnormal_draw(qf, f, sf, a.mh.fluxes_min, a.mh.fluxes_max, uf);
+        const TruncNormal r0 = truncnormal_make(pl0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
+        const TruncNormal r1 = truncnormal_make(pl1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
+        const TruncNormal rf = truncnormal_make(pf, sf, a.mh.fluxes_min, a.mh.fluxes_max);
+        // log q(prev|prop) - log q(prop|prev): the Gaussian parts are identical and cancel, leaving the
+        // box masses (kernel.py:71-85, :97-111)
+        const float lq = ((q0.log_mass + q1.log_mass) + qf.log_mass) - ((r0.log_mass + r1.log_mass) + rf.log_mass);
+
+        // ---- likelihood of the proposal: rate' = rate - old star + new star on the lane's pixels
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) acc[p] = 0.0f;
+        if (f != 0.0f) star_accumulate<MODEL, RPT, W>(m, l0, l1, -(m.c0 * f), row0, acc);
+        if (pf != 0.0f) star_accumulate<MODEL, RPT, W>(m, pl0, pl1, m.c0 * pf, row0, acc);
+        const float llp = group_sum<TPP>(
+            pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int p) { return my_rate[p * kBT] + acc[p]; }));
+
+        // ---- prior of the proposal and the MH ratio (sampler.py:87-91, kernel.py:114-116)
+        const float priorp = prior_logprob_catalog(a.prior, count, D, [&](int d, float& x0, float& x1, float& xf) {
+            if (d == k) { x0 = pl0; x1 = pl1; xf = pf; }
+            else { x0 = my_star[(d * 3 + 0) * PB]; x1 = my_star[(d * 3 + 1) * PB]; xf = my_star[(d * 3 + 2) * PB]; }
+        });
+        const float target_p = priorp + tau * llp;
+        const float log_alpha = (target_p - cached) + lq;
+        float alpha = expf(log_alpha);
+        if (alpha > 1.0f) alpha = 1.0f;  // clamp(max=1) keeps nan
+        const bool accept = (ua <= alpha);
+
+        __syncwarp();  // every lane of the particle has read the old star
+        if (accept) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) my_rate[p * kBT] += acc[p];
+            ll = llp;
+            if (sub == 0) {
+                s_star[(k * 3 + 0) * PB + pi] = pl0;
+                s_star[(k * 3 + 1) * PB + pi] = pl1;
+                s_star[(k * 3 + 2) * PB + pi] = pf;
+            }
+        }
+        // arithmetic blend with the bool as in kernel.py:125 (-inf * 0 = nan poisons the cache)
+        cached = target_p * (accept ? 1.0f : 0.0f) + cached * (accept ? 0.0f : 1.0f);
+        last_acc = accept ? 1 : 0;
+        __syncwarp();
+        if (valid && sub == 0) {
+            if (a.tr_log_alpha) a.tr_log_alpha[e] = log_alpha;
+            if (a.tr_target_prop) a.tr_target_prop[e] = target_p;
+            if (a.tr_accept) a.tr_accept[e] = (int8_t)last_acc;
+        }
+    }
+
+    // ---- log-likelihood of the final state from a fresh render (what sampler.py:100-102 recomputes)
+    if (a.loglik_out != nullptr) {
+        render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
+        ll = group_sum<TPP>(pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int p) { return acc[p] + m.bg; }));
+        if (valid && sub == 0) a.loglik_out[pn] = ll;
+    }
+    const unsigned votes = __ballot_sync(0xffffffffu, valid && sub == 0 && last_acc);
+    if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(a.acc_count + t, (float)__popc(votes));
+    __syncthreads();
+    unstage_block<PB>(a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D, s_star);
+}
+
+__global__ void divide_kernel(float* v, const int32_t* active, float denom, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T && (active == nullptr || active[t] != 0)) v[t] = v[t] / denom;  // accept.float().mean(-1)
+}
+
+__global__ void zero_active_kernel(float* v, const int32_t* active, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T && (active == nullptr || active[t] != 0)) v[t] = 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prune (sampler.py:198-219): order-preserving compaction, one thread per particle
+// ---------------------------------------------------------------------------------------------
+__global__ void prune_kernel(const float* __restrict__ locs, const float* __restrict__ fluxes, float tile_h,
+                             float tile_w, float thr, int64_t* __restrict__ counts, float* __restrict__ locs_out,
+                             float* __restrict__ fluxes_out, size_t TN, int D) {
+    const size_t pn = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pn >= TN) return;
+    const float* l = locs + pn * 2 * D;
+    const float* f = fluxes + pn * D;
+    float* lo = locs_out + pn * 2 * D;
+    float* fo = fluxes_out + pn * D;
+    int k = 0;
+    for (int d = 0; d < D; ++d) {
+        const float l0 = l[2 * d], l1 = l[2 * d + 1], fv = f[d];
+        const bool keep = (l0 > 0.0f && l0 < tile_h) && (l1 > 0.0f && l1 < tile_w) && (fv > thr);
+        if (keep) { lo[2 * k] = l0; lo[2 * k + 1] = l1; fo[k] = fv; ++k; }
+    }
+    counts[pn] = k;
+    for (; k < D; ++k) { lo[2 * k] = 0.0f; lo[2 * k + 1] = 0.0f; fo[k] = 0.0f; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch over (model, tile, threads-per-particle)
+// ---------------------------------------------------------------------------------------------
+// smallest TPP whose grid fills the machine, within what is instantiated for the tile size
+int choose_tpp(int side, long long particles) {
+    const int min_tpp = side == 8 ? 1 : (side == 16 ? 4 : 16);
+    const int max_tpp = side == 8 ? 8 : (side == 16 ? 16 : 32);
+    const long long want = (long long)num_sms() * 768;  // threads that keep every SM busy
+    int tpp = min_tpp;
+    while (tpp < max_tpp && particles * tpp < want) tpp *= 2;
+    return tpp;
+}
+
+int g_force_tpp = 0;  // test hook (smcdet_debug_force_tpp)
+
+template <int MODEL, int H, int TPP>
+int launch_loglik_t(const ModelK& m, const float* tiles, const float* locs, const float* fluxes, float* out, int T,
+                    int N, int D, cudaStream_t st) {
+    constexpr int PB = kBT / TPP;
+    const int bpt = (N + PB - 1) / PB;
+    const size_t smem = sizeof(float) * (2 * H * H + 3 * (size_t)D * PB);
+    auto kern = loglik_kernel<MODEL, H, H, TPP>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(loglik)");
+    }
+    SMC_LAUNCH(kern, (unsigned)((size_t)T * bpt), kBT, smem, st, m, tiles, locs, fluxes, out, N, D, bpt);
+    return launch_status("loglik_kernel");
+}
+
+template <int MODEL, int H, int TPP>
+int launch_mh_t(MHArgs& a, cudaStream_t st) {
+    constexpr int PB = kBT / TPP, PPT = (H / TPP) * H;
+    a.blocks_per_tile = (a.N + PB - 1) / PB;
+    const size_t smem = sizeof(float) * (2 * H * H + 3 * (size_t)a.D * PB + (size_t)PPT * kBT);
+    auto kern = mh_kernel<MODEL, H, H, TPP>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mh)");
+    }
+    SMC_LAUNCH(kern, (unsigned)((size_t)a.T * a.blocks_per_tile), kBT, smem, st, a);
+    return launch_status("mh_kernel");
+}
+
+#define SMC_DISPATCH_TPP(FN, MODEL, H, tpp, ...)                         \
+    switch (tpp) {                                                       \
+        case 1: if constexpr (H == 8) return FN<MODEL, H, 1>(__VA_ARGS__); break;   \
+        case 2: if constexpr (H == 8) return FN<MODEL, H, 2>(__VA_ARGS__); break;   \
+        case 4: if constexpr (H <= 16) return FN<MODEL, H, 4>(__VA_ARGS__); break;  \
+        case 8: if constexpr (H <= 16) return FN<MODEL, H, 8>(__VA_ARGS__); break;  \
+        case 16: if constexpr (H >= 16) return FN<MODEL, H, 16>(__VA_ARGS__); break; \
+        case 32: if constexpr (H == 32) return FN<MODEL, H, 32>(__VA_ARGS__); break; \
+        default: break;                                                  \
+    }                                                                    \
+    return fail(SMCDET_E_UNSUPPORTED, "threads-per-particle not instantiated for this tile size");
+
+template <int MODEL, int H>
+int dispatch_loglik_tpp(int tpp, const ModelK& m, const float* tiles, const float* locs, const float* fluxes,
+                        float* out, int T, int N, int D, cudaStream_t st) {
+    SMC_DISPATCH_TPP(launch_loglik_t, MODEL, H, tpp, m, tiles, locs, fluxes, out, T, N, D, st)
+}
+
+template <int MODEL, int H>
+int dispatch_mh_tpp(int tpp, MHArgs& a, cudaStream_t st) {
+    SMC_DISPATCH_TPP(launch_mh_t, MODEL, H, tpp, a, st)
+}
+
+template <int MODEL>
+int dispatch_loglik_side(int side, int tpp, const ModelK& m, const float* tiles, const float* locs,
+                         const float* fluxes, float* out, int T, int N, int D, cudaStream_t st) {
+    if (side == 8) return dispatch_loglik_tpp<MODEL, 8>(tpp, m, tiles, locs, fluxes, out, T, N, D, st);
+    if (side == 16) return dispatch_loglik_tpp<MODEL, 16>(tpp, m, tiles, locs, fluxes, out, T, N, D, st);
+    return dispatch_loglik_tpp<MODEL, 32>(tpp, m, tiles, locs, fluxes, out, T, N, D, st);
+}
+
+template <int MODEL>
+int dispatch_mh_side(int side, int tpp, MHArgs& a, cudaStream_t st) {
+    if (side == 8) return dispatch_mh_tpp<MODEL, 8>(tpp, a, st);
+    if (side == 16) return dispatch_mh_tpp<MODEL, 16>(tpp, a, st);
+    return dispatch_mh_tpp<MODEL, 32>(tpp, a, st);
+}
+
+bool model_ok(const smcdet_model_params* p) {
+    return p != nullptr &&
+           (p->model_kind == SMCDET_MODEL_GAUSS_POISSON || p->model_kind == SMCDET_MODEL_M71_NORMAL) &&
+           p->psf_radius >= 0;
+}
+
+unsigned grid_for(size_t total, int block) {
+    const size_t want = (total + block - 1) / block;
+    const size_t cap = (size_t)num_sms() * 32;
+    return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int smcdet_version(void) { return SMCDET_ABI_VERSION; }
+
+const char* smcdet_last_error_string(void) { return g_err; }
+
+// test hook: force the threads-per-particle choice of the next loglik / mh launches (0 = automatic)
+int smcdet_debug_force_tpp(int tpp) {
+    g_force_tpp = tpp;
+    return 0;
+}
+
+int smcdet_loglik(const smcdet_model_params* model, const float* tiles, const float* locs, const float* fluxes,
+                  float* loglik, int T, int N, int D, int h, int w, void* stream) {
+    SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_loglik: bad model parameters");
+    SMC_REQUIRE(tiles && locs && fluxes && loglik, SMCDET_E_INVALID, "smcdet_loglik: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0 && h > 0 && w > 0, SMCDET_E_INVALID, "smcdet_loglik: non-positive size");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ModelK m = make_model_k(*model);
+    const bool fast = (h == w) && (h == 8 || h == 16 || h == 32) && D <= kMaxStars;
+    if (fast) {
+        const int tpp = g_force_tpp ? g_force_tpp : choose_tpp(h, (long long)T * N);
+        if (model->model_kind == SMCDET_MODEL_M71_NORMAL)
+            return dispatch_loglik_side<SMCDET_MODEL_M71_NORMAL>(h, tpp, m, tiles, locs, fluxes, loglik, T, N, D, st);
+        return dispatch_loglik_side<SMCDET_MODEL_GAUSS_POISSON>(h, tpp, m, tiles, locs, fluxes, loglik, T, N, D, st);
+    }
+    const size_t warps = (size_t)T * N;
+    const size_t blocks = (warps + (kBT / 32) - 1) / (kBT / 32);
+    SMC_REQUIRE(blocks < 0x7fffffffull, SMCDET_E_TOO_LARGE, "smcdet_loglik: too many particles for one launch");
+    SMC_LAUNCH(loglik_generic_kernel, (unsigned)blocks, kBT, 0, st, m, tiles, locs, fluxes, loglik, T, N, D, h, w);
+    return launch_status("loglik_generic_kernel");
+}
+
+int smcdet_psf(const smcdet_model_params* model, const float* locs, float* psf, int T, int N, int D, int h, int w,
+               void* stream) {
+    SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_psf: bad model parameters");
+    SMC_REQUIRE(locs && psf, SMCDET_E_INVALID, "smcdet_psf: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0 && h > 0 && w > 0, SMCDET_E_INVALID, "smcdet_psf: non-positive size");
+    const ModelK m = make_model_k(*model);
+    const float norm = m.cn;
+    const size_t total = (size_t)T * h * w * N * D;
+    SMC_LAUNCH(psf_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, m, norm, locs, psf, T, N, D, h, w);
+    return launch_status("psf_kernel");
+}
+
+int smcdet_render(const smcdet_model_params* model, const float* locs, const float* fluxes, float* rate, int T,
+                  int N, int D, int h, int w, void* stream) {
+    SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_render: bad model parameters");
+    SMC_REQUIRE(locs && fluxes && rate, SMCDET_E_INVALID, "smcdet_render: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0 && h > 0 && w > 0, SMCDET_E_INVALID, "smcdet_render: non-positive size");
+    const ModelK m = make_model_k(*model);
+    const size_t total = (size_t)T * h * w * N;
+    SMC_LAUNCH(render_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, m, locs, fluxes, rate, T, N, D, h, w);
+    return launch_status("render_kernel");
+}
+
+int smcdet_prior_logprob(const smcdet_prior_params* prior, const float* counts, const float* locs,
+                         const float* fluxes, float* out, int T, int N, int D, void* stream) {
+    SMC_REQUIRE(prior && counts && locs && fluxes && out, SMCDET_E_INVALID, "smcdet_prior_logprob: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_prior_logprob: non-positive size");
+    const size_t TN = (size_t)T * N;
+    SMC_LAUNCH(prior_logprob_kernel, (unsigned)((TN + 255) / 256), 256, 0, (cudaStream_t)stream, *prior, counts, locs, fluxes,
+                                                                                          out, TN, D);
+    return launch_status("prior_logprob_kernel");
+}
+
+int smcdet_prior_sample(const smcdet_prior_params* prior, const float* u_locs, const float* u_fluxes, uint64_t seed,
+                        const int64_t* tile_ids, float* counts, float* locs, float* fluxes, int T,
+                        int num_per_count, int D, void* stream) {
+    SMC_REQUIRE(prior && counts && locs && fluxes, SMCDET_E_INVALID, "smcdet_prior_sample: null pointer");
+    SMC_REQUIRE((u_locs == nullptr) == (u_fluxes == nullptr), SMCDET_E_INVALID,
+                "smcdet_prior_sample: give both uniform tapes or neither");
+    SMC_REQUIRE(T > 0 && num_per_count > 0 && D > 0 && prior->max_objects >= prior->min_objects, SMCDET_E_INVALID,
+                "smcdet_prior_sample: bad sizes");
+    const int M = (prior->max_objects - prior->min_objects + 1) * num_per_count;
+    const size_t total = (size_t)T * M * D;
+    SMC_LAUNCH(prior_sample_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream,
+        *prior, u_locs, u_fluxes, seed, tile_ids, counts, locs, fluxes, T, M, num_per_count, D);
+    return launch_status("prior_sample_kernel");
+}
+
+int smcdet_temper_update(const float* loglik, float* tau, float* tau_prev, float ess_threshold, int do_temper,
+                         float* wlog, float* weights, float* ess, float* logz, int32_t* funcalls, int T, int N,
+                         void* stream) {
+    SMC_REQUIRE(loglik && tau && tau_prev && wlog && weights && ess && logz, SMCDET_E_INVALID,
+                "smcdet_temper_update: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0, SMCDET_E_INVALID, "smcdet_temper_update: non-positive size");
+    SMC_LAUNCH(temper_update_kernel, T, kTB, 0, (cudaStream_t)stream, loglik, tau, tau_prev, ess_threshold, do_temper, wlog,
+                                                              weights, ess, logz, funcalls, N);
+    return launch_status("temper_update_kernel");
+}
+
+int smcdet_resample(int method, const float* weights, const double* u, uint64_t seed, const int64_t* tile_ids,
+                    int64_t* index, double* cdf_scratch, int T, int N, void* stream) {
+    SMC_REQUIRE(method == SMCDET_RESAMPLE_MULTINOMIAL || method == SMCDET_RESAMPLE_SYSTEMATIC, SMCDET_E_INVALID,
+                "smcdet_resample: unknown method");
+    SMC_REQUIRE(weights && index && cdf_scratch, SMCDET_E_INVALID, "smcdet_resample: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0, SMCDET_E_INVALID, "smcdet_resample: non-positive size");
+    SMC_LAUNCH(resample_kernel, T, kTB, 0, (cudaStream_t)stream, method, weights, u, seed, tile_ids, index, cdf_scratch, N);
+    return launch_status("resample_kernel");
+}
+
+int smcdet_gather(const int64_t* index, const float* counts_in, const float* locs_in, const float* fluxes_in,
+                  float* counts_out, float* locs_out, float* fluxes_out, int T, int N, int D, void* stream) {
+    SMC_REQUIRE(index && counts_in && locs_in && fluxes_in && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID,
+                "smcdet_gather: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_gather: non-positive size");
+    SMC_REQUIRE(counts_in != counts_out && locs_in != locs_out && fluxes_in != fluxes_out, SMCDET_E_INVALID,
+                "smcdet_gather: in-place gather is not supported");
+    const size_t total = (size_t)T * N * (3 * D + 1);
+    SMC_LAUNCH(gather_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, index, counts_in, locs_in, fluxes_in,
+                                                                          counts_out, locs_out, fluxes_out, T, N, D);
+    return launch_status("gather_kernel");
+}
+
+int smcdet_mh_mutate(const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
+                     const float* tiles, const float* counts, float* locs, float* fluxes, const float* tau,
+                     float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
+                     uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
+                     int T, int N, int D, int h, int w, void* stream) {
+    SMC_REQUIRE(model_ok(model) && prior && mh, SMCDET_E_INVALID, "smcdet_mh_mutate: bad parameters");
+    SMC_REQUIRE(tiles && counts && locs && fluxes && tau && acc_rate, SMCDET_E_INVALID,
+                "smcdet_mh_mutate: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0 && mh->num_iters >= 0, SMCDET_E_INVALID, "smcdet_mh_mutate: bad sizes");
+    SMC_REQUIRE(h == w && (h == 8 || h == 16 || h == 32), SMCDET_E_UNSUPPORTED,
+                "smcdet_mh_mutate: tile must be 8x8, 16x16 or 32x32");
+    SMC_REQUIRE(D <= kMaxStars, SMCDET_E_TOO_LARGE, "smcdet_mh_mutate: too many stars per catalog");
+    if (tape != nullptr)
+        SMC_REQUIRE(tape->comp && tape->u_loc && tape->u_flux && tape->u_acc, SMCDET_E_INVALID,
+                    "smcdet_mh_mutate: incomplete draw tape");
+    cudaStream_t st = (cudaStream_t)stream;
+    MHArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = make_model_k(*model);
+    a.prior = *prior;
+    a.mh = *mh;
+    a.tiles = tiles; a.counts = counts; a.locs = locs; a.fluxes = fluxes; a.tau = tau;
+    a.loglik_out = loglik_out; a.acc_count = acc_rate;
+    if (tape) { a.tape_comp = tape->comp; a.tape_u_loc = tape->u_loc; a.tape_u_flux = tape->u_flux; a.tape_u_acc = tape->u_acc; }
+    if (trace) { a.tr_log_alpha = trace->log_alpha; a.tr_target_prop = trace->target_prop; a.tr_accept = trace->accept; }
+    a.seed = seed; a.offset = offset; a.tile_ids = tile_ids; a.active = active; a.status = status;
+    a.T = T; a.N = N; a.D = D;
+    SMC_LAUNCH(zero_active_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, T);
+    const int tpp = g_force_tpp ? g_force_tpp : choose_tpp(h, (long long)T * N);
+    int rc;
+    if (model->model_kind == SMCDET_MODEL_M71_NORMAL) rc = dispatch_mh_side<SMCDET_MODEL_M71_NORMAL>(h, tpp, a, st);
+    else rc = dispatch_mh_side<SMCDET_MODEL_GAUSS_POISSON>(h, tpp, a, st);
+    if (rc != 0) return rc;
+    SMC_LAUNCH(divide_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, (float)N, T);
+    return launch_status("divide_kernel");
+}
+
+int smcdet_prune(const float* locs, const float* fluxes, float tile_h, float tile_w, float flux_threshold,
+                 int64_t* counts_out, float* locs_out, float* fluxes_out, int T, int N, int D, void* stream) {
+    SMC_REQUIRE(locs && fluxes && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID, "smcdet_prune: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_prune: non-positive size");
+    const size_t TN = (size_t)T * N;
+    SMC_LAUNCH(prune_kernel, (unsigned)((TN + 255) / 256), 256, 0, (cudaStream_t)stream, locs, fluxes, tile_h, tile_w,
+                                                                                  flux_threshold, counts_out, locs_out,
+                                                                                  fluxes_out, TN, D);
+    return launch_status("prune_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,458 @@
+// smcdet_math.cuh -- per-thread arithmetic of the smcdet hot path for sm_100a.
+//
+// Everything here is a __host__ __device__ inline function over plain values and pointers, so
+// the kernels in smcdet_kernels.cu are thin loops around it and tests/hostsim can compile the
+// very same code with g++ to check the index logic against the CPU oracle without a GPU
+// (that host build is test infrastructure; the product library has no CPU path).
+//
+// Reference semantics are cited as file:line in the reference tree (timwhite0/smcdet).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/smcdet_b200.h"
+
+#if defined(__CUDACC__)
+#define SMC_HD __host__ __device__ __forceinline__
+#else
+#define SMC_HD inline
+#endif
+
+namespace smc {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kLogSqrt2Pi = 0.9189385332046727f;
+constexpr float kSqrt2 = 1.4142135623730951f;
+constexpr float kInvSqrt2 = 0.7071067811865476f;
+
+// ---------------------------------------------------------------------------------------------
+// MUFU wrappers: one SFU instruction each on the device
+// ---------------------------------------------------------------------------------------------
+SMC_HD float ex2_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+
+SMC_HD float lg2_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return log2f(x);
+#endif
+}
+
+SMC_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+
+SMC_HD float erfinv_f(float y) {
+#if defined(__CUDA_ARCH__)
+    return erfinvf(y);
+#else
+    // host build (tests only): Giles' approximation + Newton steps in double
+    if (!(y > -1.0f && y < 1.0f)) return (y == 1.0f) ? INFINITY : ((y == -1.0f) ? -INFINITY : NAN);
+    double yd = y, w = -log((1.0 - yd) * (1.0 + yd)), x;
+    if (w < 5.0) {
+        w -= 2.5;
+        x = 2.81022636e-08; x = 3.43273939e-07 + x * w; x = -3.5233877e-06 + x * w;
+        x = -4.39150654e-06 + x * w; x = 0.00021858087 + x * w; x = -0.00125372503 + x * w;
+        x = -0.00417768164 + x * w; x = 0.246640727 + x * w; x = 1.50140941 + x * w;
+    } else {
+        w = sqrt(w) - 3.0;
+        x = -0.000200214257; x = 0.000100950558 + x * w; x = 0.00134934322 + x * w;
+        x = -0.00367342844 + x * w; x = 0.00573950773 + x * w; x = -0.0076224613 + x * w;
+        x = 0.00943887047 + x * w; x = 1.00167406 + x * w; x = 2.83297682 + x * w;
+    }
+    x *= yd;
+    for (int i = 0; i < 3; ++i) x -= (erf(x) - yd) / (1.1283791670955126 * exp(-x * x));
+    return (float)x;
+#endif
+}
+
+// torch.nan_to_num with default arguments (smcdet/distributions.py:35)
+SMC_HD float nan_to_num_f(float x) {
+    if (x != x) return 0.0f;
+    if (x == INFINITY) return 3.4028234663852886e38f;
+    if (x == -INFINITY) return -3.4028234663852886e38f;
+    return x;
+}
+
+// torch.clamp propagates NaN
+SMC_HD float clamp_f(float x, float lo, float hi) {
+    if (x != x) return x;
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Image model constants folded once per launch (smcdet/images.py:17, :25-26, :137-145, :162-167)
+// ---------------------------------------------------------------------------------------------
+struct ModelK {
+    int kind;
+    float radius;   // psf_radius as float
+    float k1, k2;   // exp(-r^2/(2 s)) = ex2(-k r^2)
+    float cpl;      // power-law wing: t = 1 + cpl r^2
+    float hb;       // -beta/2
+    float b, p0;
+    float cn;       // PSF normalisation: M71 1/((1+b+p0) Z); Gaussian 1/(stdev sqrt(2pi))
+    float c0;       // flux -> weight: cn * adu_per_nmgy (M71), cn (Gaussian)
+    float bg, na, nm, nswitch;
+};
+
+inline ModelK make_model_k(const smcdet_model_params& p) {
+    ModelK m;
+    m.kind = p.model_kind;
+    m.radius = (float)p.psf_radius;
+    m.bg = p.background;
+    m.nswitch = p.normal_switch_rate;
+    if (p.model_kind == SMCDET_MODEL_M71_NORMAL) {
+        m.k1 = (float)(1.4426950408889634 / (2.0 * (double)p.sigma1));
+        m.k2 = (float)(1.4426950408889634 / (2.0 * (double)p.sigma2));
+        m.cpl = (float)(1.0 / ((double)p.beta * (double)p.sigmap));
+        m.hb = (float)(-0.5 * (double)p.beta);
+        m.b = p.b;
+        m.p0 = p.p0;
+        m.cn = (float)(1.0 / ((1.0 + (double)p.b + (double)p.p0) * (double)p.psf_norm));
+        m.c0 = (float)((double)p.adu_per_nmgy / ((1.0 + (double)p.b + (double)p.p0) * (double)p.psf_norm));
+        m.na = p.noise_additive;
+        m.nm = p.noise_multiplicative;
+    } else {
+        double s = (double)p.psf_stdev;
+        m.k1 = (float)(1.4426950408889634 / (2.0 * s * s));
+        m.k2 = 0.f; m.cpl = 0.f; m.hb = 0.f; m.b = 0.f; m.p0 = 0.f;
+        m.cn = (float)(1.0 / (s * 2.5066282746310002));
+        m.c0 = m.cn;
+        m.na = 0.f; m.nm = 1.f;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Separable PSF evaluation.
+//
+// A thread owns RPT consecutive rows [row0, row0+RPT) and all W columns of its particle's tile.
+// For one star (l0 = row coordinate, l1 = column coordinate, signed weight wgt = c0*flux):
+//   Gaussian terms:  exp(-k (dy^2+dx^2)) = exp(-k dy^2) * exp(-k dx^2)   -> RPT+W ex2 per term
+//   power-law wing:  p0 (1 + cpl r^2)^(-beta/2) = ex2(hb*lg2(ay+bx) + lg2(|wgt| p0))
+// The (2R+1)^2 patch anchored at floor(loc) (smcdet/images.py:33-43) is separable as well:
+// rows/columns outside it get zero Gaussian factors and an infinite wing argument.
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int W>
+struct ColFactors {
+    float e1[W];
+    float e2[MODEL == SMCDET_MODEL_M71_NORMAL ? W : 1];
+    float bx[MODEL == SMCDET_MODEL_M71_NORMAL ? W : 1];
+};
+
+template <int MODEL, int W>
+SMC_HD void col_factors(const ModelK& m, float l1, ColFactors<MODEL, W>& c) {
+    const float fl = floorf(l1);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float dj = (float)j - fl;
+        const bool in = (dj >= -m.radius) && (dj <= m.radius);
+        const float dx = ((float)j + 0.5f) - l1;
+        const float d2 = dx * dx;
+        c.e1[j] = in ? ex2_fast(-m.k1 * d2) : 0.0f;
+        if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+            c.e2[j] = in ? ex2_fast(-m.k2 * d2) : 0.0f;
+            c.bx[j] = in ? m.cpl * d2 : INFINITY;
+        }
+    }
+}
+
+// acc[r*W + j] += wgt * psf(star, pixel (row0+r, j)) for the thread's RPT x W pixels.
+template <int MODEL, int RPT, int W>
+SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int row0, float (&acc)[RPT * W]) {
+    ColFactors<MODEL, W> c;
+    col_factors<MODEL, W>(m, l1, c);
+    const float fl = floorf(l0);
+    float lw = 0.f, sgn = 1.f;
+    if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+        lw = lg2_fast(fabsf(wgt) * m.p0);
+        sgn = (wgt < 0.f) ? -1.f : 1.f;
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const float fi = (float)(row0 + r);
+        const float di = fi - fl;
+        const bool in = (di >= -m.radius) && (di <= m.radius);
+        const float dy = (fi + 0.5f) - l0;
+        const float d2 = dy * dy;
+        const float g1 = in ? wgt * ex2_fast(-m.k1 * d2) : 0.0f;
+        if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+            const float g2 = in ? (wgt * m.b) * ex2_fast(-m.k2 * d2) : 0.0f;
+            const float ay = in ? fmaf(m.cpl, d2, 1.0f) : INFINITY;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const float t = ay + c.bx[j];
+                const float pw = ex2_fast(fmaf(m.hb, lg2_fast(t), lw));
+                const float g = fmaf(g2, c.e2[j], g1 * c.e1[j]);
+                acc[r * W + j] = fmaf(sgn, pw, acc[r * W + j] + g);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j) acc[r * W + j] = fmaf(g1, c.e1[j], acc[r * W + j]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-pixel log density, summed over the thread's NPIX pixels.
+//   M71 (images.py:169-175): Normal(rate, sqrt(na + nm rate)).log_prob(x); pixels are paired so
+//     that two of them share one rcp and one lg2.
+//   Gaussian-PSF model (images.py:91-102): Poisson(rate).log_prob(x), Normal(rate, sqrt(rate))
+//     where rate > 50000.  lgam[p] = lgamma(x[p]+1).
+// rate_at(p) returns the expected count of the thread's p-th pixel.
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int NPIX, class RateAt>
+SMC_HD float pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam, RateAt rate_at) {
+    if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+        float q0 = 0.f, q1 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int p = 0; p < NPIX; p += 2) {
+            const float ra = rate_at(p), rb = rate_at(p + 1);
+            const float va = fmaf(m.nm, ra, m.na), vb = fmaf(m.nm, rb, m.na);
+            const float da = x[p] - ra, db = x[p + 1] - rb;
+            const float den = va * vb;
+            const float num = fmaf(da * da, vb, (db * db) * va);
+            const float q = num * rcp_fast(den);
+            const float l = lg2_fast(den);
+            if ((p >> 1) & 1) { q1 += q; s1 += l; } else { q0 += q; s0 += l; }
+        }
+        return fmaf(-0.5f, q0 + q1, fmaf(-0.5f * kLn2, s0 + s1, -(float)NPIX * kLogSqrt2Pi));
+    } else {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int p = 0; p < NPIX; ++p) {
+            const float r = rate_at(p);
+            const float xv = x[p];
+            const float lg = lg2_fast(r) * kLn2;
+            float term;
+            if (r > m.nswitch) {
+                const float d = xv - r;
+                term = fmaf(-0.5f * (d * d), rcp_fast(r), fmaf(-0.5f, lg, -kLogSqrt2Pi));
+            } else {
+                const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
+                term = (xl - r) - lgam[p];
+            }
+            if (p & 1) a1 += term; else a0 += term;
+        }
+        return a0 + a1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direct (non-separable) PSF value for the generic kernels (psf / render / arbitrary tile size)
+// ---------------------------------------------------------------------------------------------
+SMC_HD float psf_direct(const ModelK& m, float l0, float l1, int i, int j) {
+    const float di = (float)i - floorf(l0), dj = (float)j - floorf(l1);
+    if (!(di >= -m.radius && di <= m.radius && dj >= -m.radius && dj <= m.radius)) return 0.0f;
+    const float dy = ((float)i + 0.5f) - l0, dx = ((float)j + 0.5f) - l1;
+    const float r2 = fmaf(dy, dy, dx * dx);
+    if (m.kind == SMCDET_MODEL_M71_NORMAL) {
+        const float t = fmaf(m.cpl, r2, 1.0f);
+        const float v = ex2_fast(-m.k1 * r2) + m.b * ex2_fast(-m.k2 * r2) + m.p0 * ex2_fast(m.hb * lg2_fast(t));
+        return v;  // un-normalised by c0/A: caller scales
+    }
+    return ex2_fast(-m.k1 * r2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Truncated normal proposal (smcdet/distributions.py:22-52 over torch.distributions.Normal)
+// ---------------------------------------------------------------------------------------------
+SMC_HD float normal_cdf_f(float x, float mu, float sigma) {
+    return 0.5f * (1.0f + erff((x - mu) * (1.0f / sigma) * kInvSqrt2));
+}
+
+struct TruncNormal {
+    float cdf_lb;
+    float log_mass;  // nan_to_num(log(cdf(ub)-cdf(lb)))
+};
+
+SMC_HD TruncNormal truncnormal_make(float mu, float sigma, float lb, float ub) {
+    TruncNormal d;
+    d.cdf_lb = normal_cdf_f(lb, mu, sigma);
+    d.log_mass = nan_to_num_f(logf(normal_cdf_f(ub, mu, sigma) - d.cdf_lb));
+    return d;
+}
+
+SMC_HD float truncnormal_draw(const TruncNormal& d, float mu, float sigma, float lb, float ub, float u) {
+    const float lo = 1e-6f, hi = (float)(1.0 - 1e-6);
+    const float p = clamp_f(u, lo, hi);
+    const float pt = d.cdf_lb + p * expf(d.log_mass);
+    const float q = clamp_f(pt, lo, hi);
+    const float x = mu + sigma * erfinv_f(2.0f * q - 1.0f) * kSqrt2;
+    return clamp_f(x, lb, ub);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prior log density of one catalog (smcdet/prior.py:67-75, :183-189, :220-226).
+// star(d, l0, l1, f) yields the d-th star.
+// ---------------------------------------------------------------------------------------------
+SMC_HD float count_logpmf(const smcdet_prior_params& p, float c) {
+    if (p.count_kind == SMCDET_COUNT_POISSON) {
+        const float xl = (c == 0.0f) ? 0.0f : c * logf(p.count_rate);
+        return xl - p.count_rate - lgammaf(c + 1.0f);
+    }
+    if (c >= (float)p.min_objects && c <= (float)p.max_objects)
+        return logf(1.0f / (float)(p.max_objects - p.min_objects + 1));
+    return -INFINITY;
+}
+
+SMC_HD float flux_logpdf(const smcdet_prior_params& p, float f) {
+    if (p.flux_kind == SMCDET_FLUX_TRUNCATED_PARETO) {
+        const float v = (f == 0.0f) ? p.flux_lower : f;
+        return p.flux_logpdf_const - (p.flux_alpha + 1.0f) * logf(v);
+    }
+    if (p.flux_kind == SMCDET_FLUX_PARETO) {
+        const float v = (f == 0.0f) ? p.flux_lower : f;
+        const float x = logf(v / p.flux_lower);
+        return (logf(p.flux_alpha) - p.flux_alpha * x) - x - logf(p.flux_lower);
+    }
+    const float d = f - p.flux_mean;
+    return -(d * d) / (2.0f * p.flux_stdev * p.flux_stdev) - logf(p.flux_stdev) - kLogSqrt2Pi;
+}
+
+SMC_HD float loc_logpdf(const smcdet_prior_params& p, float l0, float l1) {
+    // torch Uniform.log_prob: log(1[low <= x] * 1[x < high]) - log(high - low), summed over 2 coords
+    const float in0 = (p.loc_low[0] <= l0 && p.loc_high[0] > l0) ? 0.0f : -INFINITY;
+    const float in1 = (p.loc_low[1] <= l1 && p.loc_high[1] > l1) ? 0.0f : -INFINITY;
+    return (in0 - logf(p.loc_high[0] - p.loc_low[0])) + (in1 - logf(p.loc_high[1] - p.loc_low[1]));
+}
+
+template <class StarAt>
+SMC_HD float prior_logprob_catalog(const smcdet_prior_params& p, float count, int D, StarAt star) {
+    float loc_acc = 0.f, flux_acc = 0.f;
+    for (int d = 0; d < D; ++d) {
+        float l0, l1, f;
+        star(d, l0, l1, f);
+        const float mask = ((float)d < count) ? 1.0f : 0.0f;
+        loc_acc += loc_logpdf(p, l0, l1) * mask;  // -inf * 0 = nan, as in the reference
+        flux_acc += flux_logpdf(p, f) * mask;
+    }
+    return (count_logpmf(p, count) + loc_acc) + flux_acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011)
+// ---------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t v[4];
+};
+
+SMC_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+SMC_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o;
+    o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+    return o;
+}
+
+// 24-bit uniform in [0,1), the resolution of torch.rand for float32
+SMC_HD float u01_f(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+// 53-bit uniform in [0,1)
+SMC_HD double u01_d(uint32_t hi, uint32_t lo) {
+    const uint64_t v = (((uint64_t)hi << 32) | (uint64_t)lo) >> 11;
+    return (double)v * 1.1102230246251565e-16;
+}
+
+// domain-separation constants for the Philox counter's 4th word
+enum : uint32_t {
+    kStreamPriorLocs = 0x50524c4fu, kStreamPriorFlux = 0x5052464cu, kStreamResample = 0x52455341u,
+    kStreamMHDraws = 0x4d484452u, kStreamMHComp = 0x4d48434fu
+};
+
+// ---------------------------------------------------------------------------------------------
+// Brent's root finder as an explicit state machine, so that a whole thread block can evaluate
+// the objective cooperatively between steps.  Same algorithm, tolerances and tie-breaking as
+// scipy.optimize.brentq (scipy/optimize/Zeros/brentq.c), the solver the reference calls at
+// smcdet/sampler.py:114-120.
+//   Brent b; b.start(xa, xb, fa, fb, xtol, rtol);  while (!b.done) { f = F(b.x); b.step(f); }
+// ---------------------------------------------------------------------------------------------
+struct Brent {
+    double x_prev, x_cur, x_blk, f_prev, f_cur, f_blk, s_prev, s_cur, xtol, rtol;
+    double x;  // next abscissa to evaluate, or the root once done
+    int done, iters;
+
+    SMC_HD void start(double xa, double xb, double fa, double fb, double xtol_, double rtol_) {
+        x_prev = xa; x_cur = xb; f_prev = fa; f_cur = fb;
+        x_blk = 0.0; f_blk = 0.0; s_prev = 0.0; s_cur = 0.0;
+        xtol = xtol_; rtol = rtol_; done = 0; iters = 0; x = xb;
+        if (f_prev == 0.0) { x = x_prev; done = 1; return; }
+        if (f_cur == 0.0) { x = x_cur; done = 1; return; }
+        if (signbit(f_prev) == signbit(f_cur)) { x = 0.0; done = 2; return; }
+        advance();
+    }
+
+    SMC_HD void step(double f_new) {
+        f_cur = f_new;
+        advance();
+    }
+
+    SMC_HD void advance() {
+        if (iters >= 100) { x = x_cur; done = 3; return; }
+        ++iters;
+        if (f_prev != 0.0 && f_cur != 0.0 && (signbit(f_prev) != signbit(f_cur))) {
+            x_blk = x_prev; f_blk = f_prev;
+            s_prev = s_cur = x_cur - x_prev;
+        }
+        if (fabs(f_blk) < fabs(f_cur)) {
+            x_prev = x_cur; x_cur = x_blk; x_blk = x_prev;
+            f_prev = f_cur; f_cur = f_blk; f_blk = f_prev;
+        }
+        const double tol = (xtol + rtol * fabs(x_cur)) / 2;
+        const double s_bis = (x_blk - x_cur) / 2;
+        if (f_cur == 0.0 || fabs(s_bis) < tol) { x = x_cur; done = 1; return; }
+        if (fabs(s_prev) > tol && fabs(f_cur) < fabs(f_prev)) {
+            double s_try;
+            if (x_prev == x_blk) {
+                s_try = -f_cur * (x_cur - x_prev) / (f_cur - f_prev);
+            } else {
+                const double d_prev = (f_prev - f_cur) / (x_prev - x_cur);
+                const double d_blk = (f_blk - f_cur) / (x_blk - x_cur);
+                s_try = -f_cur * (f_blk * d_blk - f_prev * d_prev) / (d_blk * d_prev * (f_blk - f_prev));
+            }
+            const double lim = fmin(fabs(s_prev), 3 * fabs(s_bis) - tol);
+            if (2 * fabs(s_try) < lim) { s_prev = s_cur; s_cur = s_try; }
+            else { s_prev = s_bis; s_cur = s_bis; }
+        } else {
+            s_prev = s_bis; s_cur = s_bis;
+        }
+        x_prev = x_cur; f_prev = f_cur;
+        if (fabs(s_cur) > tol) x_cur += s_cur;
+        else x_cur += (s_bis > 0 ? tol : -tol);
+        x = x_cur;
+    }
+};
+
+}  // namespace smc

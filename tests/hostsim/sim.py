@@ -1,0 +1,175 @@
+"""numpy front end of tests/hostsim/libsmcdet_hostsim.so -- the CUDA library's own source compiled
+for the CPU under a CUDA-semantics emulator (cuda_shim.h).  TEST INFRASTRUCTURE ONLY: lets the
+CPU-only test tier run the kernels' logic against the oracle before any GPU time is spent."""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from smcdet_b200 import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libsmcdet_hostsim.so")
+_SRC = [os.path.join(_HERE, "hostsim_lib.cpp"), os.path.join(_HERE, "cuda_shim.h"),
+        os.path.join(_HERE, "..", "..", "smcdet_b200", "csrc", "smcdet_kernels.cu"),
+        os.path.join(_HERE, "..", "..", "smcdet_b200", "csrc", "smcdet_math.cuh"),
+        os.path.join(_HERE, "..", "..", "include", "smcdet_b200.h")]
+
+
+def build(force=False):
+    if (not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in _SRC)):
+        return _LIB
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-I", _HERE, "-x", "c++",
+                    os.path.join(_HERE, "hostsim_lib.cpp"), "-o", _LIB], check=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = A.bind(C.CDLL(_LIB))
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"hostsim ABI call failed ({rc}): {lib().smcdet_last_error_string().decode()}")
+
+
+def force_tpp(tpp):
+    lib().smcdet_debug_force_tpp(int(tpp))
+
+
+def loglik(model, tiles, locs, fluxes):
+    tiles, locs, fluxes = _f(tiles), _f(locs), _f(fluxes)
+    T, h, w = tiles.shape
+    _, N, D, _ = locs.shape
+    out = np.zeros((T, N), np.float32)
+    check(lib().smcdet_loglik(C.byref(model), _p(tiles), _p(locs), _p(fluxes), _p(out), T, N, D, h, w, None))
+    return out
+
+
+def psf(model, locs, h, w):
+    locs = _f(locs)
+    T, N, D, _ = locs.shape
+    out = np.zeros((T, h, w, N, D), np.float32)
+    check(lib().smcdet_psf(C.byref(model), _p(locs), _p(out), T, N, D, h, w, None))
+    return out
+
+
+def render(model, locs, fluxes, h, w):
+    locs, fluxes = _f(locs), _f(fluxes)
+    T, N, D, _ = locs.shape
+    out = np.zeros((T, h, w, N), np.float32)
+    check(lib().smcdet_render(C.byref(model), _p(locs), _p(fluxes), _p(out), T, N, D, h, w, None))
+    return out
+
+
+def prior_logprob(prior, counts, locs, fluxes):
+    counts, locs, fluxes = _f(counts), _f(locs), _f(fluxes)
+    T, N, D, _ = locs.shape
+    out = np.zeros((T, N), np.float32)
+    check(lib().smcdet_prior_logprob(C.byref(prior), _p(counts), _p(locs), _p(fluxes), _p(out), T, N, D, None))
+    return out
+
+
+def prior_sample(prior, T, num_per_count, D, u_locs=None, u_fluxes=None, seed=0, tile_ids=None):
+    M = (prior.max_objects - prior.min_objects + 1) * num_per_count
+    counts = np.zeros((T, M), np.float32)
+    locs = np.zeros((T, M, D, 2), np.float32)
+    fluxes = np.zeros((T, M, D), np.float32)
+    ul = _f(u_locs) if u_locs is not None else None
+    uf = _f(u_fluxes) if u_fluxes is not None else None
+    ti = np.ascontiguousarray(tile_ids, np.int64) if tile_ids is not None else None
+    check(lib().smcdet_prior_sample(C.byref(prior), _p(ul), _p(uf), seed, _p(ti), _p(counts), _p(locs), _p(fluxes),
+                                    T, num_per_count, D, None))
+    return counts, locs, fluxes
+
+
+def temper_update(loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True):
+    ll = _f(loglik_)
+    T, N = ll.shape
+    tau, tau_prev, logz = _f(tau).reshape(-1).copy(), _f(tau_prev).reshape(-1).copy(), _f(logz).reshape(-1).copy()
+    wlog, weights = np.zeros((T, N), np.float32), np.zeros((T, N), np.float32)
+    ess = np.zeros(T, np.float32)
+    calls = np.zeros(T, np.int32)
+    check(lib().smcdet_temper_update(_p(ll), _p(tau), _p(tau_prev), ess_threshold, int(do_temper), _p(wlog), _p(weights),
+                                     _p(ess), _p(logz), _p(calls), T, N, None))
+    return dict(tau=tau, tau_prev=tau_prev, wlog=wlog, weights=weights, ess=ess, logz=logz, funcalls=calls)
+
+
+def resample(method, weights, u=None, seed=0):
+    w = _f(weights)
+    T, N = w.shape
+    idx = np.zeros((T, N), np.int64)
+    cdf = np.zeros((T, N), np.float64)
+    uu = np.ascontiguousarray(u, np.float64) if u is not None else None
+    check(lib().smcdet_resample(int(method), _p(w), _p(uu), seed, None, _p(idx), _p(cdf), T, N, None))
+    return idx, cdf
+
+
+def gather(idx, counts, locs, fluxes):
+    idx = np.ascontiguousarray(idx, np.int64)
+    counts, locs, fluxes = _f(counts), _f(locs), _f(fluxes)
+    T, N, D, _ = locs.shape
+    co, lo, fo = np.zeros_like(counts), np.zeros_like(locs), np.zeros_like(fluxes)
+    check(lib().smcdet_gather(_p(idx), _p(counts), _p(locs), _p(fluxes), _p(co), _p(lo), _p(fo), T, N, D, None))
+    return co, lo, fo
+
+
+def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
+              active=None):
+    tiles, counts = _f(tiles), _f(counts)
+    locs, fluxes = _f(locs).copy(), _f(fluxes).copy()
+    tau = _f(tau).reshape(-1)
+    T, h, w = tiles.shape
+    _, N, D, _ = locs.shape
+    iters = mh.num_iters
+    ll = np.zeros((T, N), np.float32)
+    acc = np.full(T, -1.0, np.float32)
+    status = np.zeros(1, np.int32)
+    keep = []
+    tp = None
+    if tape is not None:
+        comp = np.ascontiguousarray(tape["comp"], np.int32).reshape(iters, T, N)
+        ul, uf, ua = _f(tape["u_loc"]).reshape(iters, T, N, 2), _f(tape["u_flux"]).reshape(iters, T, N), _f(tape["u_acc"]).reshape(iters, T, N)
+        keep += [comp, ul, uf, ua]
+        tp = A.DrawTape(_p(comp).value, _p(ul).value, _p(uf).value, _p(ua).value)
+    tr = None
+    out = {}
+    if traces:
+        la, tg = np.zeros((iters, T, N), np.float32), np.zeros((iters, T, N), np.float32)
+        ac = np.zeros((iters, T, N), np.int8)
+        tr = A.MHTrace(_p(la).value, _p(tg).value, _p(ac).value)
+        out.update(log_alpha=la, target_prop=tg, accept=ac)
+    act = np.ascontiguousarray(active, np.int32) if active is not None else None
+    check(lib().smcdet_mh_mutate(C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes),
+                                 _p(tau), _p(ll), _p(acc), C.byref(tp) if tp is not None else None,
+                                 C.byref(tr) if tr is not None else None, seed, offset, None, _p(act), _p(status),
+                                 T, N, D, h, w, None))
+    out.update(locs=locs, fluxes=fluxes, loglik=ll, acc_rate=acc, status=int(status[0]))
+    return out
+
+
+def prune(locs, fluxes, tile_h, tile_w, thr):
+    locs, fluxes = _f(locs), _f(fluxes)
+    T, N, D, _ = locs.shape
+    counts = np.zeros((T, N), np.int64)
+    lo, fo = np.zeros_like(locs), np.zeros_like(fluxes)
+    check(lib().smcdet_prune(_p(locs), _p(fluxes), tile_h, tile_w, thr, _p(counts), _p(lo), _p(fo), T, N, D, None))
+    return counts, lo, fo

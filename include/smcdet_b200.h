@@ -39,7 +39,8 @@ enum {
 };
 
 enum { SMCDET_MODEL_GAUSS_POISSON = 0, SMCDET_MODEL_M71_NORMAL = 1 };
-enum { SMCDET_COUNT_DISCRETE_UNIFORM = 0, SMCDET_COUNT_POISSON = 1 };
+enum { SMCDET_COUNT_DISCRETE_UNIFORM = 0, SMCDET_COUNT_POISSON = 1,
+       SMCDET_COUNT_NONE = 2 /* count term left to the caller (e.g. GeometricProcessPrior) */ };
 enum { SMCDET_FLUX_PARETO = 0, SMCDET_FLUX_TRUNCATED_PARETO = 1, SMCDET_FLUX_NORMAL = 2 };
 enum { SMCDET_RESAMPLE_MULTINOMIAL = 0, SMCDET_RESAMPLE_SYSTEMATIC = 1 };
 

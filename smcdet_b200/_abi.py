@@ -5,7 +5,7 @@ import ctypes as C
 ABI_VERSION = 1
 
 MODEL_GAUSS_POISSON, MODEL_M71_NORMAL = 0, 1
-COUNT_DISCRETE_UNIFORM, COUNT_POISSON = 0, 1
+COUNT_DISCRETE_UNIFORM, COUNT_POISSON, COUNT_NONE = 0, 1, 2
 FLUX_PARETO, FLUX_TRUNCATED_PARETO, FLUX_NORMAL = 0, 1, 2
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 STATUS_OUT_OF_BOX = 1

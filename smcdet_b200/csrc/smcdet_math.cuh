@@ -309,6 +309,7 @@ SMC_HD float count_logpmf(const smcdet_prior_params& p, float c) {
         const float xl = (c == 0.0f) ? 0.0f : c * logf(p.count_rate);
         return xl - p.count_rate - lgammaf(c + 1.0f);
     }
+    if (p.count_kind == SMCDET_COUNT_NONE) return 0.0f;
     if (c >= (float)p.min_objects && c <= (float)p.max_objects)
         return logf(1.0f / (float)(p.max_objects - p.min_objects + 1));
     return -INFINITY;

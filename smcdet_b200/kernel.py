@@ -1,0 +1,129 @@
+"""Mutation kernels with the reference's interface (smcdet/kernel.py).
+
+``SingleComponentMH.run`` executes all ``num_iters`` single-site random-walk Metropolis-Hastings
+sweeps (reference kernel.py:26-130) in ONE launch of the fused CUDA kernel ``smcdet_mh_mutate``:
+proposal, prior, incremental likelihood update from a resident rate image, accept/reject.
+"""
+
+import ctypes as C
+
+import torch
+
+from . import _abi as A
+from . import _lib as L
+
+
+class SingleComponentMH(object):
+    def __init__(self, num_iters, locs_stdev, fluxes_stdev, fluxes_min, fluxes_max):
+        self.num_iters = num_iters
+        self.locs_stdev = float(locs_stdev)
+        self.locs_min = None  # defined automatically within SMCsampler
+        self.locs_max = None  # defined automatically within SMCsampler
+        self.fluxes_stdev = float(fluxes_stdev)
+        self.fluxes_min = float(fluxes_min)
+        self.fluxes_max = float(fluxes_max)
+        self.last_loglik = None  # log-likelihood of the state returned by the last run()
+        self.last_trace = None
+
+    def _params(self):
+        if self.locs_min is None or self.locs_max is None:
+            raise ValueError("locs_min / locs_max are not set (SMCsampler installs the prior's box)")
+        k = A.MHParams()
+        k.num_iters = int(self.num_iters)
+        k.locs_stdev, k.fluxes_stdev = self.locs_stdev, self.fluxes_stdev
+        k.fluxes_min, k.fluxes_max = self.fluxes_min, self.fluxes_max
+        lo = torch.as_tensor(self.locs_min).tolist()
+        hi = torch.as_tensor(self.locs_max).tolist()
+        k.locs_min[0], k.locs_min[1] = lo
+        k.locs_max[0], k.locs_max[1] = hi
+        return k
+
+    @staticmethod
+    def _resolve_target(log_target):
+        """The fused kernel needs the Prior and ImageModel behind ``log_target``.  The reference passes
+        ``SMCsampler.log_target`` (sampler.py:171-179); any bound method of an object exposing
+        ``.Prior`` and ``.ImageModel`` from this package is accepted."""
+        owner = getattr(log_target, "__self__", None)
+        prior, model = getattr(owner, "Prior", None), getattr(owner, "ImageModel", None)
+        if prior is None or model is None or not hasattr(prior, "_params") or not hasattr(model, "_params"):
+            raise NotImplementedError(
+                "SingleComponentMH.run is fused with log prior + tempered log-likelihood on the GPU: pass the "
+                "log_target bound method of an object with smcdet_b200 .Prior and .ImageModel (e.g. "
+                "SMCsampler.log_target); arbitrary Python callbacks are not supported")
+        return prior, model
+
+    def run(self, data, counts, locs, fluxes, temperature, log_target, *, tape=None, trace=False, seed=None,
+            offset=0, tile_ids=None, active=None, inplace=False):
+        """Returns [locs, fluxes, acceptance rate of the last iteration [numH, numW]] (reference
+        kernel.py:26-130).  Keyword-only extras (not in the reference):
+          tape   dict(comp[iters,numH,numW,n] int32, u_loc[...,2], u_flux, u_acc) of injected draws
+          trace  keep per-iteration log_alpha / target_prop / accept in ``self.last_trace``
+          seed, offset, tile_ids   Philox stream selection when no tape is given
+          active [numH, numW] int32 mask of tiles to mutate; inplace  update locs/fluxes in place
+        """
+        prior, model = self._resolve_target(log_target)
+        numH, numW, n, d, _ = locs.shape
+        T = numH * numW
+        h, w = model.image_height, model.image_width
+        lf = L.f32(locs)
+        dev = lf.device
+        ff = L.f32(fluxes, dev)
+        if not inplace:  # the reference returns new tensors and leaves its arguments untouched
+            if lf.data_ptr() == locs.data_ptr():
+                lf = lf.clone()
+            if ff.data_ptr() == fluxes.data_ptr():
+                ff = ff.clone()
+        tiles = L.f32(data, dev).reshape(T, h, w)
+        cf = L.f32(counts, dev).reshape(T, n)
+        tau = L.f32(temperature, dev).reshape(T)
+        loglik = torch.empty(T, n, device=dev, dtype=torch.float32)
+        acc = torch.empty(T, device=dev, dtype=torch.float32)
+        status = torch.zeros(1, device=dev, dtype=torch.int32)
+
+        iters = int(self.num_iters)
+        keep = []
+        tp = None
+        if tape is not None:
+            comp = tape["comp"].to(device=dev, dtype=torch.int32).reshape(iters, T, n).contiguous()
+            ul = L.f32(tape["u_loc"], dev).reshape(iters, T, n, 2)
+            uf = L.f32(tape["u_flux"], dev).reshape(iters, T, n)
+            ua = L.f32(tape["u_acc"], dev).reshape(iters, T, n)
+            keep += [comp, ul, uf, ua]
+            tp = A.DrawTape(comp.data_ptr(), ul.data_ptr(), uf.data_ptr(), ua.data_ptr())
+        tr = None
+        self.last_trace = None
+        if trace:
+            la = torch.empty(iters, T, n, device=dev, dtype=torch.float32)
+            tg = torch.empty(iters, T, n, device=dev, dtype=torch.float32)
+            ac = torch.empty(iters, T, n, device=dev, dtype=torch.int8)
+            tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr())
+            self.last_trace = dict(log_alpha=la.view(iters, numH, numW, n), target_prop=tg.view(iters, numH, numW, n),
+                                   accept=ac.view(iters, numH, numW, n))
+        act = None if active is None else active.to(device=dev, dtype=torch.int32).reshape(T).contiguous()
+        tids = None if tile_ids is None else tile_ids.to(device=dev, dtype=torch.int64).reshape(T).contiguous()
+
+        mp, pp, kp = model._params(), prior._params(), self._params()
+        L.check(L.lib().smcdet_mh_mutate(
+            C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), L.ptr(cf), L.ptr(lf), L.ptr(ff), L.ptr(tau),
+            L.ptr(loglik), L.ptr(acc), C.byref(tp) if tp is not None else None, C.byref(tr) if tr is not None else None,
+            L.fresh_seed() if seed is None else int(seed), int(offset), L.ptr(tids, torch.int64),
+            L.ptr(act, torch.int32), L.ptr(status, torch.int32), T, n, d, h, w, L.stream_for(lf)))
+        self._status = status
+        self.last_loglik = loglik.view(numH, numW, n)
+        return [lf.view(numH, numW, n, d, 2), ff.view(numH, numW, n, d), acc.view(numH, numW)]
+
+    def check_status(self):
+        """Raise the reference's AssertionError (distributions.py:51) if the last run() saw a location
+        or flux outside the proposal box.  Synchronises with the device."""
+        st = getattr(self, "_status", None)
+        if st is not None and int(st.item()) & A.STATUS_OUT_OF_BOX:
+            raise AssertionError("value outside [lb, ub] of the truncated-normal proposal "
+                                 "(reference smcdet/distributions.py:51)")
+
+
+class SingleComponentMALA(object):
+    """Reference kernel.py:133-275 (gradient-based proposals).  Out of scope of the B200 hot path
+    (SURVEY.md section 8f, item 3): only the deprecated jsm2024 scripts use it."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("SingleComponentMALA is not part of the B200 hot path (SURVEY.md 8f)")

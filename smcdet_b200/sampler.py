@@ -1,0 +1,291 @@
+"""Likelihood-tempered SMC sampler with the reference's interface (smcdet/sampler.py:9-298).
+
+One iteration is ``resample -> mutate (MH) -> temper -> update_weights`` (reference sampler.py:244-247);
+every stage is a launch of the CUDA library on the whole [numH, numW] grid of tiles:
+
+  resample        smcdet_resample (float64 CDF + search) + smcdet_gather
+  mutate          smcdet_mh_mutate (all MH sweeps fused; also yields the new log-likelihood)
+  temper          smcdet_temper_update(do_temper=1): on-device Brent solve of ESS(delta) = rho N
+  update_weights  smcdet_temper_update(do_temper=0): softmax weights, ESS, log normalising constant
+
+State attributes keep the reference's names and shapes ([numH, numW, ...]).
+"""
+
+import ctypes as C
+
+import torch
+
+from . import _abi as A
+from . import _lib as L
+
+
+class SMCsampler(object):
+    def __init__(self, image, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
+                 resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, tile_ids=None,
+                 freeze_finished=False, verbose=True):
+        """``image``: square 2-D tensor (reference sampler.py:25-31), or -- an extension used by the
+        tile-sharding layer -- an already tiled [numH, numW, tile_dim, tile_dim] tensor.
+        Keyword-only extras: ``tile_ids`` [numH, numW] global tile ids keying the Philox streams
+        (results then do not depend on how tiles are sharded), ``freeze_finished`` stops mutating
+        tiles that reached temperature 1 (the reference keeps mutating them, sampler.py:230),
+        ``verbose`` silences the progress prints."""
+        dev = image.device if (isinstance(image, torch.Tensor) and image.is_cuda) else L.device()
+        self.image = image
+        self.tile_dim = tile_dim
+        if image.dim() == 2:
+            self.image_dim = image.shape[0]
+            self.num_tiles_per_side = self.image_dim // self.tile_dim
+            self.numH = self.numW = self.num_tiles_per_side
+            img = L.f32(image, dev)
+            self.tiled_image = img.unfold(0, self.tile_dim, self.tile_dim).unfold(1, self.tile_dim, self.tile_dim)
+        elif image.dim() == 4:
+            self.numH, self.numW = image.shape[0], image.shape[1]
+            self.num_tiles_per_side = self.numH
+            self.image_dim = self.numH * self.tile_dim
+            self.tiled_image = L.f32(image, dev)
+        else:
+            raise ValueError("image must be a square 2-D tensor or a [numH, numW, h, w] tensor of tiles")
+        self._tiles = self.tiled_image.contiguous().view(self.numH * self.numW, self.tile_dim, self.tile_dim)
+        self._device = dev
+
+        self.Prior = Prior
+        self.ImageModel = ImageModel
+        self.MutationKernel = MutationKernel
+        self.MutationKernel.locs_min = self.Prior.loc_prior.low
+        self.MutationKernel.locs_max = self.Prior.loc_prior.high
+
+        self.num_catalogs = num_catalogs
+        self.ess_threshold = ess_threshold_prop * num_catalogs
+
+        if resample_method not in {"multinomial", "systematic"}:
+            raise ValueError("resample_method must be either multinomial or systematic.")
+        self.resample_method = resample_method
+
+        self.flux_detection_threshold = flux_detection_threshold
+        self.max_smc_iters = max_smc_iters
+        self.print_every = print_every
+        self.has_run = False
+
+        self.tile_ids = None if tile_ids is None else tile_ids.to(device=dev, dtype=torch.int64).contiguous()
+        self.freeze_finished = freeze_finished
+        self.verbose = verbose
+        self._loglik_key = None
+        self.iter = 0
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def _T(self):
+        return self.numH * self.numW
+
+    def _state_key(self):
+        """Identity + in-place version of the particle tensors the cached log-likelihood belongs to."""
+        return (self.locs.data_ptr(), self.locs._version, self.fluxes.data_ptr(), self.fluxes._version)
+
+    def _print(self, *a):
+        if self.verbose:
+            print(*a)
+
+    def initialize(self, *, tape=None):
+        """Prior draws, first likelihood, uniform weights (reference sampler.py:57-85).
+        ``tape`` = (u_locs, u_fluxes) injects the uniforms of the prior draw."""
+        self.counts, self.locs, self.fluxes = self.Prior._sample_grid(
+            self.numH, self.numW, None, True, self.num_catalogs, tape=tape, tile_ids=self.tile_ids)
+        dev = self._device
+        self.temperature_prev = torch.zeros(self.numH, self.numW, device=dev)
+        self.temperature = torch.zeros(self.numH, self.numW, device=dev)
+        self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)
+        self._loglik_key = self._state_key()
+        self.weights_log_unnorm = torch.zeros(self.numH, self.numW, self.num_catalogs, device=dev)
+        self.weights = torch.full((self.numH, self.numW, self.num_catalogs), 1.0 / self.num_catalogs, device=dev)
+        self.log_normalizing_constant = torch.zeros(self.numH, self.numW, device=dev)
+        self.ess = torch.full((self.numH, self.numW), float(self.num_catalogs), device=dev)
+        self.mutation_acc_rates = torch.zeros(self.numH, self.numW, device=dev)
+
+    def log_target(self, data, counts, locs, fluxes, temperature):
+        """log prior + temperature * log-likelihood (reference sampler.py:87-91)."""
+        logprior = self.Prior.log_prob(counts, locs, fluxes)
+        loglik = self.ImageModel.loglikelihood(data, locs, fluxes)
+        return logprior + temperature.unsqueeze(-1) * loglik
+
+    def tempering_objective(self, loglikelihood, delta):
+        """ESS(delta) - threshold for one tile (reference sampler.py:93-97); the solve itself runs
+        on the device inside ``temper``."""
+        log_numerator = 2 * ((delta * loglikelihood).logsumexp(0))
+        log_denominator = (2 * delta * loglikelihood).logsumexp(0)
+        return (log_numerator - log_denominator).exp() - self.ess_threshold
+
+    def _temper_update(self, do_temper, logz, tau, tau_prev):
+        T, n = self._T, self.num_catalogs
+        ll = L.f32(self.loglik, self._device).view(T, n)
+        wlog = torch.empty(T, n, device=self._device)
+        weights = torch.empty(T, n, device=self._device)
+        ess = torch.empty(T, device=self._device)
+        calls = torch.zeros(T, device=self._device, dtype=torch.int32)
+        L.check(L.lib().smcdet_temper_update(L.ptr(ll), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold),
+                                             int(do_temper), L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz),
+                                             L.ptr(calls, torch.int32), T, n, L.stream_for(ll)))
+        return wlog, weights, ess, calls
+
+    def temper(self):
+        """Adaptive temperature step (reference sampler.py:99-125).  The reference recomputes the
+        likelihood first; here it is reused when ``mutate``/``initialize`` just produced it."""
+        if self._loglik_key is None or self._loglik_key != self._state_key():
+            self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)
+            self._loglik_key = self._state_key()
+        tau = L.f32(self.temperature, self._device).reshape(self._T).clone()
+        tau_prev = torch.empty_like(tau)
+        scratch_logz = torch.zeros(self._T, device=self._device)
+        _, _, _, calls = self._temper_update(1, scratch_logz, tau, tau_prev)
+        self.tempering_funcalls = calls.view(self.numH, self.numW)
+        self.temperature_prev = tau_prev.view(self.numH, self.numW)
+        self.temperature = tau.view(self.numH, self.numW)
+
+    def update_weights(self):
+        """weights, ESS and log normalising constant (reference sampler.py:181-196)."""
+        tau = L.f32(self.temperature, self._device).reshape(self._T).clone()
+        tau_prev = L.f32(self.temperature_prev, self._device).reshape(self._T).clone()
+        logz = L.f32(self.log_normalizing_constant, self._device).reshape(self._T).clone()
+        wlog, weights, ess, _ = self._temper_update(0, logz, tau, tau_prev)
+        n = self.num_catalogs
+        self.weights_log_unnorm = wlog.view(self.numH, self.numW, n)
+        self.weights = weights.view(self.numH, self.numW, n)
+        self.ess = ess.view(self.numH, self.numW)
+        self.log_normalizing_constant = logz.view(self.numH, self.numW)
+
+    def resample(self, *, u=None):
+        """Multinomial or systematic resampling (reference sampler.py:127-169) with the CDF in float64.
+        ``u`` injects the uniforms: float64 [numH, numW, n] (multinomial) or [numH, numW] (systematic)."""
+        T, n = self._T, self.num_catalogs
+        dev = self._device
+        method = A.RESAMPLE_MULTINOMIAL if self.resample_method == "multinomial" else A.RESAMPLE_SYSTEMATIC
+        w = L.f32(self.weights, dev).view(T, n)
+        idx = torch.empty(T, n, device=dev, dtype=torch.int64)
+        cdf = torch.empty(T, n, device=dev, dtype=torch.float64)
+        uu = None if u is None else u.to(device=dev, dtype=torch.float64).contiguous()
+        L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(),
+                                        L.ptr(self.tile_ids, torch.int64), L.ptr(idx, torch.int64),
+                                        L.ptr(cdf, torch.float64), T, n, L.stream_for(w)))
+        active = self._active_mask()
+        if active is not None:  # frozen tiles keep their particles (identity index)
+            ident = torch.arange(n, device=dev, dtype=torch.int64).expand(T, n)
+            idx = torch.where(active.view(T, 1), idx, ident).contiguous()
+        d = self.fluxes.shape[-1]
+        cin = L.f32(self.counts, dev).view(T, n)
+        lin = L.f32(self.locs, dev).view(T, n, d, 2)
+        fin = L.f32(self.fluxes, dev).view(T, n, d)
+        cout, lout, fout = torch.empty_like(cin), torch.empty_like(lin), torch.empty_like(fin)
+        L.check(L.lib().smcdet_gather(L.ptr(idx, torch.int64), L.ptr(cin), L.ptr(lin), L.ptr(fin), L.ptr(cout),
+                                      L.ptr(lout), L.ptr(fout), T, n, d, L.stream_for(w)))
+        self.resampled_index = idx.view(self.numH, self.numW, n)
+        self.counts = cout.view(self.numH, self.numW, n)
+        self.locs = lout.view(self.numH, self.numW, n, d, 2)
+        self.fluxes = fout.view(self.numH, self.numW, n, d)
+        uniform = torch.full((self.numH, self.numW, n), 1.0 / n, device=dev)
+        self.weights = uniform if active is None else torch.where(active.unsqueeze(-1), uniform, self.weights)
+        self._loglik_key = None
+
+    def _active_mask(self):
+        """With ``freeze_finished``: tiles whose particles have not yet been resampled and mutated at
+        temperature 1 ([numH, numW] bool); None in the reference's lock-step mode."""
+        if not self.freeze_finished:
+            return None
+        return self.temperature_prev < 1
+
+    def mutate(self, **kw):
+        """MH mutation of every particle (reference sampler.py:171-179)."""
+        if self.freeze_finished and "active" not in kw:
+            kw["active"] = self._active_mask().to(torch.int32)
+        kw.setdefault("inplace", True)  # resample() just produced fresh buffers
+        kw.setdefault("tile_ids", self.tile_ids)
+        kw.setdefault("offset", self.iter)
+        self.locs, self.fluxes, acc = self.MutationKernel.run(
+            self.tiled_image, self.counts, self.locs, self.fluxes, self.temperature, self.log_target, **kw)
+        if kw.get("active") is not None:
+            act = kw["active"].to(acc.device).bool().view_as(acc)
+            acc = torch.where(act, acc, self.mutation_acc_rates.to(acc.device))
+            ll_new = getattr(self.MutationKernel, "last_loglik", None)
+            if ll_new is not None and hasattr(self, "loglik"):
+                ll_new = torch.where(act.unsqueeze(-1), ll_new, self.loglik)
+                self.MutationKernel.last_loglik = ll_new
+        self.mutation_acc_rates = acc
+        ll = getattr(self.MutationKernel, "last_loglik", None)
+        if ll is not None:
+            self.loglik = ll
+            self._loglik_key = self._state_key()
+        else:
+            self._loglik_key = None
+
+    def prune(self, locs, fluxes):
+        """Detectable stars inside the tile, compacted to the front (reference sampler.py:198-219)."""
+        numH, numW, n, d, _ = locs.shape
+        lf = L.f32(locs, self._device).view(numH * numW, n, d, 2)
+        ff = L.f32(fluxes, self._device).view(numH * numW, n, d)
+        counts = torch.empty(numH * numW, n, device=self._device, dtype=torch.int64)
+        lo, fo = torch.empty_like(lf), torch.empty_like(ff)
+        L.check(L.lib().smcdet_prune(L.ptr(lf), L.ptr(ff), float(self.tile_dim), float(self.tile_dim),
+                                     float(self.flux_detection_threshold), L.ptr(counts, torch.int64), L.ptr(lo),
+                                     L.ptr(fo), numH * numW, n, d, L.stream_for(lf)))
+        return counts.view(numH, numW, n), lo.view(numH, numW, n, d, 2), fo.view(numH, numW, n, d)
+
+    def run(self):
+        """reference sampler.py:221-256"""
+        self.iter = 0
+        self._print("starting...")
+
+        self.initialize()
+        self.temper()
+        self.update_weights()
+
+        while torch.any(self.temperature < 1) and self.iter <= self.max_smc_iters:
+            self.iter += 1
+            if self.iter % self.print_every == 0:
+                self._print(
+                    f"iteration {self.iter}: "
+                    f"temperature in [{round(self.temperature.min().item(), 2)}, "
+                    f"{round(self.temperature.max().item(), 2)}], "
+                    f"acceptance rate in [{round(self.mutation_acc_rates.min().item(), 2)}, "
+                    f"{round(self.mutation_acc_rates.max().item(), 2)}]"
+                )
+            self.resample()
+            self.mutate()
+            self.temper()
+            self.update_weights()
+
+        self.resample()
+        self.pruned_counts, self.pruned_locs, self.pruned_fluxes = self.prune(self.locs, self.fluxes)
+        if hasattr(self.MutationKernel, "check_status"):
+            self.MutationKernel.check_status()
+        self.has_run = True
+        self._print("done!\n")
+
+    # ---- posterior summaries (reference sampler.py:258-298) -----------------------------------
+    def posterior_mean_count(self, counts):
+        return (self.weights * counts).sum(-1)
+
+    def posterior_mean_total_flux(self, fluxes):
+        return (self.weights * fluxes.sum(-1)).sum(-1)
+
+    @property
+    def posterior_predictive_total_observed_flux(self):
+        return self.ImageModel.sample(self.locs, self.fluxes).sum([-2, -3]).squeeze()
+
+    def summarize(self):
+        if self.has_run is False:
+            raise ValueError("Sampler hasn't been run yet.")
+        values, freq = self.pruned_counts.unique(return_counts=True)
+        print("posterior distribution of number of detectable stars within image boundary:")
+        print(values.cpu())
+        print((freq / self.pruned_counts.shape[-1]).round(decimals=3).cpu(), "\n")
+        print("posterior mean total intrinsic flux (including undetectable and/or in padding) =",
+              f"{self.posterior_mean_total_flux(self.fluxes).item()}\n")
+        print("posterior mean total intrinsic flux of detectable stars within image boundary =",
+              f"{self.posterior_mean_total_flux(self.pruned_fluxes).item()}\n")
+        print(f"number of unique catalogs = {self.fluxes[0, 0].sum(-1).unique(dim=0).shape[0]}")
+
+
+class MHsampler(object):
+    """Reference sampler.py:301-576: a single long MH chain per tile.  Sequential by construction and
+    outside the data-parallel hot path."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("MHsampler is outside the B200 hot path (SURVEY.md section 2, item 7)")

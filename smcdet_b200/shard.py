@@ -1,0 +1,95 @@
+"""Tile sharding across the GPUs of one box (absent in the reference).
+
+Tiles never interact inside ``SMCsampler`` (every reduction is over the particle axis, reference
+sampler.py:81-85, :187-196), so the field is partitioned by tile with NO data-path collective:
+rank r of G owns the tiles t = r (mod G) -- round-robin, so crowded regions spread evenly -- and
+runs the whole SMC loop on them locally.  Philox streams are keyed by the GLOBAL tile id, so a
+tile's posterior does not depend on G when ``freeze_finished=True``.  The only communication is
+the final ``all_gather`` of posterior catalogs and per-tile summaries (NCCL over NVLink on GPUs,
+gloo in the CPU tests of the host logic) into the ``Aggregate`` sink.
+"""
+
+import torch
+import torch.distributed as dist
+
+
+def shard_tile_ids(num_tiles, world_size, rank):
+    """Global ids of the tiles owned by ``rank``: t = rank (mod world_size)."""
+    return torch.tensor(list(range(rank, num_tiles, world_size)), dtype=torch.int64)
+
+
+def shard_sizes(num_tiles, world_size):
+    return [len(range(r, num_tiles, world_size)) for r in range(world_size)]
+
+
+def gather_tiles(local, num_tiles, group=None):
+    """All-gather a per-tile tensor ``local`` [T_r, ...] (this rank's round-robin shard) into the
+    full [num_tiles, ...] tensor in global tile order, on every rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        if local.shape[0] != num_tiles:
+            raise ValueError("without a process group the local shard must be the whole field")
+        return local
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(num_tiles, world)
+    if local.shape[0] != sizes[dist.get_rank(group)]:
+        raise ValueError(f"local shard has {local.shape[0]} tiles, expected {sizes[dist.get_rank(group)]}")
+    tmax = max(sizes)
+    pad = torch.zeros((tmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad.contiguous(), group=group)
+    full = torch.empty((num_tiles,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        full[r::world] = parts[r][: sizes[r]]
+    return full
+
+
+class ShardedSMC(object):
+    """Runs ``SMCsampler`` on this rank's round-robin shard of a field of tiles and gathers the
+    posterior into per-field tensors.
+
+    ``tiles`` is the whole field [T, h, w] (identical on every rank; only the local shard is moved
+    to the GPU).  Remaining arguments are those of ``SMCsampler``.
+    """
+
+    def __init__(self, tiles, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
+                 resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, group=None,
+                 freeze_finished=True, verbose=False, device=None):
+        from .sampler import SMCsampler
+
+        self.group = group
+        self.num_tiles = tiles.shape[0]
+        if dist.is_available() and dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+        self.local_ids = shard_tile_ids(self.num_tiles, self.world, self.rank)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        local = tiles[self.local_ids].to(dev).unsqueeze(1)  # [T_r, 1, h, w]
+        self.sampler = SMCsampler(local, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs,
+                                  ess_threshold_prop, resample_method, flux_detection_threshold, max_smc_iters,
+                                  print_every, tile_ids=self.local_ids.to(dev).unsqueeze(1),
+                                  freeze_finished=freeze_finished, verbose=verbose)
+
+    def run(self):
+        self.sampler.run()
+        return self
+
+    def local_results(self):
+        s = self.sampler
+        sq = lambda t: t.squeeze(1)  # noqa: E731  [T_r, 1, ...] -> [T_r, ...]
+        summaries = torch.stack([
+            sq(s.log_normalizing_constant), sq(s.ess), sq(s.temperature), sq(s.mutation_acc_rates),
+            sq(s.posterior_mean_count(s.pruned_counts.float())), sq(s.posterior_mean_total_flux(s.pruned_fluxes)),
+        ], dim=-1)
+        return dict(counts=sq(s.counts), locs=sq(s.locs), fluxes=sq(s.fluxes), weights=sq(s.weights),
+                    pruned_counts=sq(s.pruned_counts), pruned_locs=sq(s.pruned_locs), pruned_fluxes=sq(s.pruned_fluxes),
+                    summaries=summaries)
+
+    SUMMARY_COLUMNS = ("log_normalizing_constant", "ess", "temperature", "acceptance_rate",
+                       "posterior_mean_count", "posterior_mean_detected_flux")
+
+    def gather(self, keys=("pruned_counts", "pruned_locs", "pruned_fluxes", "summaries")):
+        """All-gather the named per-tile results into global tile order ([T, ...] on every rank)."""
+        local = self.local_results()
+        return {k: gather_tiles(local[k].contiguous(), self.num_tiles, self.group) for k in keys}

@@ -1,0 +1,190 @@
+"""Two ways of reaching the C ABI of include/smcdet_b200.h from numpy arrays, with one interface:
+
+  ``gpu``      the product library libsmcdet_b200.so on cuda:0 (device buffers are torch tensors)
+  ``hostsim``  the same CUDA source compiled for the CPU under tests/hostsim/cuda_shim.h
+
+The parity tests are written once against this interface; the hostsim variant runs in the CPU-only
+tier, the gpu variant is marked ``gpu``.
+"""
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "hostsim"))
+
+from smcdet_b200 import _abi as A  # noqa: E402
+
+
+def hostsim_backend():
+    import sim
+
+    sim.lib()
+    return sim
+
+
+class GpuBackend:
+    """numpy in / numpy out through libsmcdet_b200.so on cuda:0."""
+
+    def __init__(self):
+        import torch
+
+        from smcdet_b200 import _lib as L
+
+        self.torch, self.L = torch, L
+        self.dev = torch.device("cuda", 0)
+        self.lib = L.lib()
+
+    # -- helpers
+    def _d(self, a, dtype=np.float32):
+        if a is None:
+            return None
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self.dev)
+
+    def _z(self, shape, dtype):
+        return self.torch.zeros(shape, device=self.dev, dtype=dtype)
+
+    def _p(self, t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _check(self, rc):
+        self.L.check(rc)
+        self.torch.cuda.synchronize(self.dev)
+
+    def force_tpp(self, tpp):
+        self.lib.smcdet_debug_force_tpp(int(tpp))
+
+    # -- ABI calls
+    def loglik(self, model, tiles, locs, fluxes):
+        t = self.torch
+        tiles, locs, fluxes = self._d(tiles), self._d(locs), self._d(fluxes)
+        T, h, w = tiles.shape
+        _, N, D, _ = locs.shape
+        out = self._z((T, N), t.float32)
+        self._check(self.lib.smcdet_loglik(C.byref(model), self._p(tiles), self._p(locs), self._p(fluxes), self._p(out),
+                                           T, N, D, h, w, self._stream()))
+        return out.cpu().numpy()
+
+    def psf(self, model, locs, h, w):
+        t = self.torch
+        locs = self._d(locs)
+        T, N, D, _ = locs.shape
+        out = self._z((T, h, w, N, D), t.float32)
+        self._check(self.lib.smcdet_psf(C.byref(model), self._p(locs), self._p(out), T, N, D, h, w, self._stream()))
+        return out.cpu().numpy()
+
+    def render(self, model, locs, fluxes, h, w):
+        t = self.torch
+        locs, fluxes = self._d(locs), self._d(fluxes)
+        T, N, D, _ = locs.shape
+        out = self._z((T, h, w, N), t.float32)
+        self._check(self.lib.smcdet_render(C.byref(model), self._p(locs), self._p(fluxes), self._p(out), T, N, D, h, w,
+                                           self._stream()))
+        return out.cpu().numpy()
+
+    def prior_logprob(self, prior, counts, locs, fluxes):
+        t = self.torch
+        counts, locs, fluxes = self._d(counts), self._d(locs), self._d(fluxes)
+        T, N, D, _ = locs.shape
+        out = self._z((T, N), t.float32)
+        self._check(self.lib.smcdet_prior_logprob(C.byref(prior), self._p(counts), self._p(locs), self._p(fluxes),
+                                                  self._p(out), T, N, D, self._stream()))
+        return out.cpu().numpy()
+
+    def prior_sample(self, prior, T, num_per_count, D, u_locs=None, u_fluxes=None, seed=0, tile_ids=None):
+        t = self.torch
+        M = (prior.max_objects - prior.min_objects + 1) * num_per_count
+        counts, locs, fluxes = self._z((T, M), t.float32), self._z((T, M, D, 2), t.float32), self._z((T, M, D), t.float32)
+        ul, uf = self._d(u_locs), self._d(u_fluxes)
+        ti = self._d(tile_ids, np.int64)
+        self._check(self.lib.smcdet_prior_sample(C.byref(prior), self._p(ul), self._p(uf), seed, self._p(ti),
+                                                 self._p(counts), self._p(locs), self._p(fluxes), T, num_per_count, D,
+                                                 self._stream()))
+        return counts.cpu().numpy(), locs.cpu().numpy(), fluxes.cpu().numpy()
+
+    def temper_update(self, loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True):
+        t = self.torch
+        ll = self._d(loglik_)
+        T, N = ll.shape
+        tau, tau_prev, logz = self._d(np.reshape(tau, -1)), self._d(np.reshape(tau_prev, -1)), self._d(np.reshape(logz, -1))
+        wlog, weights = self._z((T, N), t.float32), self._z((T, N), t.float32)
+        ess, calls = self._z((T,), t.float32), self._z((T,), t.int32)
+        self._check(self.lib.smcdet_temper_update(self._p(ll), self._p(tau), self._p(tau_prev), ess_threshold,
+                                                  int(do_temper), self._p(wlog), self._p(weights), self._p(ess),
+                                                  self._p(logz), self._p(calls), T, N, self._stream()))
+        g = lambda x: x.cpu().numpy()  # noqa: E731
+        return dict(tau=g(tau), tau_prev=g(tau_prev), wlog=g(wlog), weights=g(weights), ess=g(ess), logz=g(logz),
+                    funcalls=g(calls))
+
+    def resample(self, method, weights, u=None, seed=0):
+        t = self.torch
+        w = self._d(weights)
+        T, N = w.shape
+        idx, cdf = self._z((T, N), t.int64), self._z((T, N), t.float64)
+        uu = self._d(u, np.float64)
+        self._check(self.lib.smcdet_resample(int(method), self._p(w), self._p(uu), seed, None, self._p(idx), self._p(cdf),
+                                             T, N, self._stream()))
+        return idx.cpu().numpy(), cdf.cpu().numpy()
+
+    def gather(self, idx, counts, locs, fluxes):
+        t = self.torch
+        idx = self._d(idx, np.int64)
+        counts, locs, fluxes = self._d(counts), self._d(locs), self._d(fluxes)
+        T, N, D, _ = locs.shape
+        co, lo, fo = t.zeros_like(counts), t.zeros_like(locs), t.zeros_like(fluxes)
+        self._check(self.lib.smcdet_gather(self._p(idx), self._p(counts), self._p(locs), self._p(fluxes), self._p(co),
+                                           self._p(lo), self._p(fo), T, N, D, self._stream()))
+        return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
+
+    def mh_mutate(self, model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
+                  active=None):
+        t = self.torch
+        tiles, counts, locs, fluxes = self._d(tiles), self._d(counts), self._d(locs), self._d(fluxes)
+        tau = self._d(np.reshape(tau, -1))
+        T, h, w = tiles.shape
+        _, N, D, _ = locs.shape
+        iters = mh.num_iters
+        ll = self._z((T, N), t.float32)
+        acc = t.full((T,), -1.0, device=self.dev)
+        status = self._z((1,), t.int32)
+        tp = tr = None
+        keep = []
+        if tape is not None:
+            comp = self._d(np.reshape(tape["comp"], (iters, T, N)), np.int32)
+            ul = self._d(np.reshape(tape["u_loc"], (iters, T, N, 2)))
+            uf = self._d(np.reshape(tape["u_flux"], (iters, T, N)))
+            ua = self._d(np.reshape(tape["u_acc"], (iters, T, N)))
+            keep += [comp, ul, uf, ua]
+            tp = A.DrawTape(comp.data_ptr(), ul.data_ptr(), uf.data_ptr(), ua.data_ptr())
+        out = {}
+        if traces:
+            la, tg = self._z((iters, T, N), t.float32), self._z((iters, T, N), t.float32)
+            ac = self._z((iters, T, N), t.int8)
+            tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr())
+        act = self._d(active, np.int32)
+        self._check(self.lib.smcdet_mh_mutate(
+            C.byref(model), C.byref(prior), C.byref(mh), self._p(tiles), self._p(counts), self._p(locs), self._p(fluxes),
+            self._p(tau), self._p(ll), self._p(acc), C.byref(tp) if tp is not None else None,
+            C.byref(tr) if tr is not None else None, seed, offset, None, self._p(act), self._p(status), T, N, D, h, w,
+            self._stream()))
+        if traces:
+            out.update(log_alpha=la.cpu().numpy(), target_prop=tg.cpu().numpy(), accept=ac.cpu().numpy())
+        out.update(locs=locs.cpu().numpy(), fluxes=fluxes.cpu().numpy(), loglik=ll.cpu().numpy(),
+                   acc_rate=acc.cpu().numpy(), status=int(status.item()))
+        return out
+
+    def prune(self, locs, fluxes, tile_h, tile_w, thr):
+        t = self.torch
+        locs, fluxes = self._d(locs), self._d(fluxes)
+        T, N, D, _ = locs.shape
+        counts = self._z((T, N), t.int64)
+        lo, fo = t.zeros_like(locs), t.zeros_like(fluxes)
+        self._check(self.lib.smcdet_prune(self._p(locs), self._p(fluxes), tile_h, tile_w, thr, self._p(counts),
+                                          self._p(lo), self._p(fo), T, N, D, self._stream()))
+        return counts.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()

@@ -1,0 +1,127 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol the header
+declares, the ctypes mirror matches the header, the package fails loudly without CUDA, and the
+tile-sharding host logic works across two gloo ranks."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "smcdet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(smcdet_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from smcdet_b200 import _abi, _lib
+
+    path = _lib.build()
+    cdll = ctypes.CDLL(path)
+    names = header_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(cdll, n), f"{n} declared in include/smcdet_b200.h but not exported"
+    assert sorted(_abi.PROTOTYPES) == names, "smcdet_b200/_abi.py and the header disagree"
+    _abi.bind(cdll)
+    assert cdll.smcdet_version() == _abi.ABI_VERSION
+    # sm_100a SASS is in the binary
+    out = subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_struct_layouts_match_the_header():
+    from smcdet_b200 import _abi
+
+    assert ctypes.sizeof(_abi.ModelParams) == 15 * 4
+    assert ctypes.sizeof(_abi.PriorParams) == 4 * 4 + 4 + 4 * 4 + 6 * 4
+    assert ctypes.sizeof(_abi.MHParams) == 4 + 4 * 4 + 4 * 4
+    assert ctypes.sizeof(_abi.DrawTape) == 4 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_abi.MHTrace) == 3 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it can be exercised on the CPU box."""
+    from smcdet_b200 import _abi, _lib
+
+    cdll = _abi.bind(ctypes.CDLL(_lib.build()))
+    m = _abi.ModelParams()
+    m.model_kind = 7
+    assert cdll.smcdet_loglik(ctypes.byref(m), None, None, None, None, 1, 1, 1, 8, 8, None) == _abi.E_INVALID
+    assert b"smcdet_loglik" in cdll.smcdet_last_error_string()
+    m.model_kind = _abi.MODEL_M71_NORMAL
+    assert cdll.smcdet_loglik(ctypes.byref(m), None, None, None, None, 1, 1, 1, 8, 8, None) == _abi.E_INVALID
+    assert cdll.smcdet_resample(5, None, None, 0, None, None, None, 1, 1, None) == _abi.E_INVALID
+    assert cdll.smcdet_temper_update(None, None, None, 1.0, 1, None, None, None, None, None, 1, 1, None) == _abi.E_INVALID
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_cuda():
+    from smcdet_b200 import _lib
+    from smcdet_b200.images import M71ImageModel
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.device()
+    model = M71ImageModel(8, 8, background=100.0, psf_radius=8, adu_per_nmgy=240.0,
+                          psf_params=[1.1, 2.0, 2.3, 5.2, 0.73, 0.51], noise_additive=0.0, noise_multiplicative=1.9)
+    assert abs(float(model.psf_normalizing_constant) - 12.75) < 0.5  # host-side constant still computed
+    with pytest.raises((RuntimeError, TypeError)):
+        model.loglikelihood(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 4, 2, 2), torch.zeros(1, 1, 4, 2))
+
+
+def test_product_package_never_imports_the_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "smcdet_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "smcdet_b200", fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), f"{fn} mentions the oracle"
+            assert "hostsim" not in src, f"{fn} mentions hostsim"
+
+
+def test_round_robin_sharding():
+    from smcdet_b200.shard import shard_sizes, shard_tile_ids
+
+    for T, G in [(800, 8), (7, 4), (3, 8), (1024, 1)]:
+        ids = [shard_tile_ids(T, G, r) for r in range(G)]
+        assert sorted(torch.cat(ids).tolist()) == list(range(T))
+        assert [len(i) for i in ids] == shard_sizes(T, G)
+        assert max(len(i) for i in ids) - min(len(i) for i in ids) <= 1
+
+
+GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from smcdet_b200.shard import gather_tiles, shard_tile_ids
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
+rank, world = dist.get_rank(), dist.get_world_size()
+T = 7
+ids = shard_tile_ids(T, world, rank)
+local = torch.stack([torch.full((3, 2), float(t)) + torch.arange(6).view(3, 2) / 10 for t in ids.tolist()]) if len(ids) else torch.zeros(0, 3, 2)
+full = gather_tiles(local, T)
+want = torch.stack([torch.full((3, 2), float(t)) + torch.arange(6).view(3, 2) / 10 for t in range(T)])
+assert torch.equal(full, want), (rank, full)
+cnt = gather_tiles(ids.clone(), T)
+assert cnt.tolist() == list(range(T))
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gather_tiles_two_gloo_ranks(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), "2"], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

@@ -1,0 +1,272 @@
+"""The reference-facing Python classes (SMCsampler, priors, image models, MH kernel, Aggregate)
+driven on a B200 and checked against the reference's golden outputs.  All tests need the GPU."""
+
+import numpy as np
+import pytest
+import torch
+
+from goldenlib import Golden, O, oracle_model, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def build_objects(meta, iters=None):
+    from smcdet_b200.images import ImageModel, M71ImageModel
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.prior import M71Prior, ParetoStarPrior
+
+    mp, pp = meta["model_params"], meta["prior_params"]
+    t, pad, D = meta["tile"], meta["pad"], meta["D"]
+    if meta["model"] == "m71":
+        model = M71ImageModel(t, t, background=mp["background"], psf_radius=mp["psf_radius"],
+                              adu_per_nmgy=mp["adu_per_nmgy"], psf_params=mp["psf_params"],
+                              noise_additive=mp["noise_additive"], noise_multiplicative=mp["noise_multiplicative"])
+        prior = M71Prior(meta["min_objects"], D, pp["counts_rate"], t, t, flux_alpha=pp["flux_alpha"],
+                         flux_lower=pp["flux_lower"], flux_upper=pp["flux_upper"], pad=pad)
+    else:
+        model = ImageModel(t, t, background=mp["background"], psf_radius=mp["psf_radius"], psf_stdev=mp["psf_stdev"])
+        prior = ParetoStarPrior(meta["min_objects"], D, t, t, flux_scale=pp["flux_scale"], flux_alpha=pp["flux_alpha"],
+                                pad=pad)
+    mh = None
+    if "fluxes_min" in meta:
+        n_it = meta.get("iters", meta.get("mh_iters")) if iters is None else iters
+        mh = SingleComponentMH(n_it, meta["locs_stdev"], meta["fluxes_stdev"], meta["fluxes_min"], meta["fluxes_max"])
+    return model, prior, mh
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+@pytest.mark.parametrize("name", ["loglik_m71_t8_d10", "loglik_m71_t16_d10", "loglik_m71_t32_d12", "loglik_gauss_t8_d8",
+                                  "loglik_m71_t8_strata"])
+def test_image_model_and_prior_classes(name):
+    g = Golden(name)
+    model, prior, _ = build_objects(g.meta)
+    ll = model.loglikelihood(cu(g["tiles"]), cu(g["locs"]), cu(g["fluxes"]))
+    assert ll.shape == g["loglik"].shape and ll.is_cuda
+    assert rel_err(ll.cpu().numpy(), g["loglik"]) < RTOL
+    lp = prior.log_prob(cu(g["counts"]), cu(g["locs"]), cu(g["fluxes"]))
+    assert rel_err(lp.cpu().numpy(), g["logprior"]) < RTOL
+    ns = g["psf_sub"].shape[-2]
+    psf = model.psf(cu(g["locs"][:, :, :ns]))
+    assert psf.shape == g["psf_sub"].shape
+    assert np.max(np.abs(psf.cpu().numpy() - g["psf_sub"])) < 1e-6 * max(1.0, g["psf_sub"].max())
+    if g.meta["model"] == "m71":
+        assert abs(float(model.psf_normalizing_constant) / g.meta["psf_norm"] - 1) < 1e-6
+    img = model.sample(cu(g["locs"][:, :, :ns]), cu(g["fluxes"][:, :, :ns]))
+    assert img.shape == g["rate_sub"].shape and torch.isfinite(img).all()
+
+
+def test_strided_tiled_image_view_is_accepted():
+    """SMCsampler hands loglikelihood a strided unfold() view of the image (sampler.py:29-31)."""
+    g = Golden("loglik_m71_t8_d10")
+    model, _, _ = build_objects(g.meta)
+    ns, t = g.meta["nside"], g.meta["tile"]
+    image = cu(g["tiles"]).permute(0, 2, 1, 3).reshape(ns * t, ns * t).contiguous()
+    view = image.unfold(0, t, t).unfold(1, t, t)
+    assert not view.is_contiguous()
+    ll = model.loglikelihood(view, cu(g["locs"]), cu(g["fluxes"]))
+    assert rel_err(ll.cpu().numpy(), g["loglik"]) < RTOL
+
+
+def test_cpu_tensors_are_moved_not_computed_on_cpu():
+    """There is no CPU path: CPU inputs are copied to the GPU and the result lives there."""
+    g = Golden("loglik_m71_t8_d1")
+    model, _, _ = build_objects(g.meta)
+    ll = model.loglikelihood(torch.from_numpy(g["tiles"]), torch.from_numpy(g["locs"]), torch.from_numpy(g["fluxes"]))
+    assert ll.is_cuda and rel_err(ll.cpu().numpy(), g["loglik"]) < RTOL
+
+
+def test_prior_sample_class_with_tape_and_without():
+    g = Golden("prior_sample_m71")
+    _, prior, _ = build_objects(g.meta)
+    ns, npc = g.meta["nside"], g.meta["num_per_count"]
+    counts, locs, fluxes = prior._sample_grid(ns, ns, None, True, npc, tape=(cu(g["u_locs"]), cu(g["u_fluxes"])))
+    assert np.array_equal(counts.cpu().numpy(), g["counts"])
+    assert np.max(np.abs(locs.cpu().numpy() - g["locs"])) < 1e-5
+    rf = g["fluxes"]
+    f = fluxes.cpu().numpy()
+    assert np.array_equal(f == 0, rf == 0) and np.max(np.abs(f[rf > 0] / rf[rf > 0] - 1)) < RTOL
+    torch.manual_seed(3)
+    a = prior.sample(num_tiles_per_side=ns, stratify_by_count=True, num_catalogs_per_count=npc)
+    torch.manual_seed(3)
+    b = prior.sample(num_tiles_per_side=ns, stratify_by_count=True, num_catalogs_per_count=npc)
+    assert len(a) == 3 and all(torch.equal(x, y) for x, y in zip(a, b))
+    assert a[0].shape == (ns, ns, prior.num_counts * npc) and a[1].shape[-2:] == (g.meta["D"], 2)
+    with pytest.raises(ValueError):
+        prior.sample(stratify_by_count=True)
+    with pytest.raises(ValueError):
+        prior.sample(stratify_by_count=False, num_catalogs_per_count=4)
+    c, l, f = prior.sample(num_catalogs=7, num_tiles_per_side=1)  # non-stratified "truth" draw
+    assert c.shape == (1, 1, 7) and l.shape == (1, 1, 7, g.meta["D"], 2) and (f >= 0).all()
+
+
+@pytest.mark.parametrize("name", ["smc_stages_m71", "smc_stages_gauss"])
+def test_smcsampler_follows_reference_run(name):
+    """Drive SMCsampler through the reference's recorded run (sampler.py:221-256) with every draw
+    injected and WITHOUT resetting the state between stages: temperatures, ESS, log normalising
+    constants and acceptance rates track the reference over several SMC iterations."""
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden(name)
+    meta = g.meta
+    model, prior, mh = build_objects(meta)
+    N, ns = meta["N"], meta["nside"]
+    s = SMCsampler(cu(g["image"]), meta["tile"], prior, model, mh, N, meta["ess_prop"], meta["method"],
+                   meta["flux_threshold"], 100, verbose=False)
+    if meta["model"] == "m71":
+        s.initialize(tape=(cu(g["init_u_locs"]), cu(g["init_u_fluxes"])))
+        assert np.max(np.abs(s.locs.cpu().numpy() - g["init_locs"])) < 1e-5
+    else:
+        s.initialize()
+        s.counts, s.locs, s.fluxes = cu(g["init_counts"]), cu(g["init_locs"]), cu(g["init_fluxes"])
+    s.temper()
+    s.update_weights()
+    assert np.max(np.abs(s.temperature.cpu().numpy() - g["t0_tau"])) < 2e-5
+    assert rel_err(s.ess.cpu().numpy(), g["t0_ess"]) < 5e-3
+    for it in range(1, meta["n_smc"] + 1):
+        s.iter = it
+        s.resample(u=cu(g[f"i{it}_resample_u"]))
+        tape = {k: cu(g[f"i{it}_{k}"]) for k in ("comp", "u_loc", "u_flux", "u_acc")}
+        s.mutate(tape=tape)
+        s.temper()
+        s.update_weights()
+        dn = f"i{it}_done"
+        same = np.all(np.abs(s.locs.cpu().numpy() - g[f"{dn}_locs"]) < 1e-4, axis=(3, 4))
+        assert same.mean() > 0.97, f"iteration {it}: only {same.mean():.3f} of the particles track the reference"
+        assert np.max(np.abs(s.mutation_acc_rates.cpu().numpy() - g[f"i{it}_acc_rate"])) < 0.03
+        assert np.max(np.abs(s.temperature.cpu().numpy() - g[f"{dn}_tau"])) < 5e-3 * max(1.0, float(g[f"{dn}_tau"].max()))
+        assert np.max(np.abs(s.log_normalizing_constant.cpu().numpy() - g[f"{dn}_logz"])) < 0.05 * np.abs(g[f"{dn}_logz"]).max() + 0.5
+    pc, pl, pf = s.prune(s.locs, s.fluxes)
+    assert pc.dtype == torch.int64 and pl.shape == s.locs.shape
+
+
+def test_smcsampler_full_run_m71():
+    """SMCsampler.run() end to end with its own Philox draws on the canonical M71 settings
+    (notebooks/smc.ipynb cell 5, reduced particle count): reaches temperature 1, keeps every
+    particle inside the prior box, reproduces under torch.manual_seed and summarises."""
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("smc_stats_m71")
+    meta = g.meta
+    meta = dict(meta, fluxes_min=meta["prior_params"]["flux_lower"], fluxes_max=meta["prior_params"]["flux_upper"],
+                locs_stdev=0.1, fluxes_stdev=2.5)
+    runs = []
+    for rep in range(2):
+        torch.manual_seed(7)
+        model, prior, mh = build_objects(meta, iters=50)
+        s = SMCsampler(cu(g["image"]), meta["tile"], prior, model, mh, 4000, 0.5, "multinomial",
+                       meta["flux_threshold"], 200, verbose=False)
+        with pytest.raises(ValueError):
+            s.summarize()
+        s.run()
+        runs.append(s)
+    s = runs[0]
+    assert float(s.temperature.min()) == 1.0 and s.has_run
+    assert torch.equal(runs[0].locs, runs[1].locs) and torch.equal(runs[0].pruned_counts, runs[1].pruned_counts)
+    pad, t = meta["pad"], meta["tile"]
+    assert float(s.locs.min()) >= -pad and float(s.locs.max()) <= t + pad
+    assert torch.isfinite(s.log_normalizing_constant).all()
+    # posterior summaries land in the band spanned by unmodified reference runs (6 seeds, N = 1000)
+    ref = g["stats"]
+    mean_flux = float(s.posterior_mean_total_flux(s.pruned_fluxes))
+    assert 0.3 * ref[:, 2].min() < mean_flux < 3 * ref[:, 2].max()
+    logz = float(s.log_normalizing_constant)
+    assert ref[:, 3].min() - 250 < logz < ref[:, 3].max() + 250
+    s.summarize()
+    ppf = s.posterior_predictive_total_observed_flux
+    assert ppf.numel() == 4000
+
+
+def test_freeze_finished_keeps_done_tiles_fixed():
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("smc_stages_m71")
+    meta = g.meta
+    torch.manual_seed(1)
+    model, prior, mh = build_objects(meta, iters=10)
+    s = SMCsampler(cu(g["image"]), meta["tile"], prior, model, mh, 512, 0.5, "systematic", meta["flux_threshold"], 200,
+                   freeze_finished=True, verbose=False)
+    s.run()
+    assert float(s.temperature.min()) == 1.0
+    assert torch.isfinite(s.locs).all() and int(s.pruned_counts.max()) <= meta["D"]
+
+
+def test_bad_arguments_raise_like_the_reference():
+    from smcdet_b200.aggregate import Aggregate
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("smc_stages_m71")
+    model, prior, mh = build_objects(g.meta)
+    with pytest.raises(ValueError):
+        SMCsampler(cu(g["image"]), 8, prior, model, mh, 64, 0.5, "stratified", 0.25, 10)
+    with pytest.raises(NotImplementedError):
+        mh.run(None, None, torch.zeros(1, 1, 4, 6, 2), None, None, lambda *a: None)
+    w = torch.full((2, 2, 8), 1 / 8, device=dev())
+    with pytest.raises(ValueError):
+        Aggregate(prior, model, mh, torch.zeros(2, 2, 8, 8), None, None, None, w, torch.zeros(2, 2), 0.25, "bogus", 0.5)
+
+
+def test_aggregate_single_tile_sink():
+    """Aggregate on a 1x1 grid = final resample + prune (reference aggregate.py:583-589)."""
+    from smcdet_b200.aggregate import Aggregate
+
+    g = Golden("resample")
+    meta = g.meta
+    model, prior, _ = build_objects(meta)
+    from smcdet_b200.kernel import SingleComponentMH
+
+    mh = SingleComponentMH(1, 0.1, 2.5, 0.06, 1800.0)
+    k = 1
+    w = cu(g[f"k{k}_weights"][:1, :1])
+    agg = Aggregate(prior, model, mh, torch.zeros(1, 1, 8, 8, device=dev()), cu(g["counts"][:1, :1]), cu(g["locs"][:1, :1]),
+                    cu(g["fluxes"][:1, :1]), w, torch.zeros(1, 1), 0.25, "systematic", 0.5)
+    with pytest.raises(ValueError):
+        agg.summarize()
+    agg.run(u=cu(g[f"k{k}_u"][:1, :1].astype(np.float64)))
+    assert np.array_equal(agg.locs.cpu().numpy(), g[f"k{k}_f64_locs"][:1, :1])
+    pc, pl, pf = O.prune(g[f"k{k}_f64_locs"][:1, :1].reshape(1, -1, meta["D"], 2), g[f"k{k}_f64_fluxes"][:1, :1].reshape(1, -1, meta["D"]), 8, 8, 0.25)
+    assert np.array_equal(agg.pruned_counts.cpu().numpy().reshape(1, -1), pc)
+    assert abs(float(agg.ess) - meta["N"]) < 1e-2
+    agg.summarize()
+    big = Aggregate(prior, model, mh, torch.zeros(2, 2, 8, 8, device=dev()), cu(g["counts"]), cu(g["locs"]), cu(g["fluxes"]),
+                    cu(g[f"k{k}_weights"]), torch.zeros(2, 2), 0.25, "systematic", 0.5)
+    with pytest.raises(NotImplementedError):
+        big.run()
+    sink = Aggregate(prior, model, mh, torch.zeros(2, 2, 8, 8, device=dev()), cu(g["counts"]), cu(g["locs"]), cu(g["fluxes"]),
+                     cu(g[f"k{k}_weights"]), torch.zeros(2, 2), 0.25, "systematic", 0.5, merge=False)
+    sink.run(u=cu(g[f"k{k}_u"].astype(np.float64)))
+    assert np.array_equal(sink.locs.cpu().numpy(), g[f"k{k}_f64_locs"])
+
+
+def test_full_size_properties_m71():
+    """At BASELINE's full size (N = 10 000, D = 10, 8x8) the oracle is too slow to check everything, so
+    check size-independent properties: permutation equivariance over particles and stars,
+    additivity of a zero-flux star, and agreement with the oracle on a random subsample."""
+    g = Golden("loglik_m71_t8_d10")
+    model, prior, _ = build_objects(g.meta)
+    torch.manual_seed(0)
+    N, D, T = 10000, 10, 6
+    counts, locs, fluxes = prior._sample_grid(T, 1, None, True, N, seed=5)
+    tiles = cu(np.tile(g["tiles"].reshape(-1, 1, 8, 8)[:1], (T, 1, 1, 1)) * np.linspace(0.8, 1.3, T).reshape(T, 1, 1, 1).astype(np.float32))
+    ll = model.loglikelihood(tiles, locs, fluxes)
+    perm = torch.randperm(N, device=dev())
+    assert torch.equal(model.loglikelihood(tiles, locs[:, :, perm], fluxes[:, :, perm]), ll[:, :, perm])
+    sperm = torch.randperm(D, device=dev())
+    ll2 = model.loglikelihood(tiles, locs[:, :, :, sperm], fluxes[:, :, :, sperm])
+    assert rel_err(ll2.cpu().numpy(), ll.cpu().numpy()) < 1e-5
+    f0 = fluxes.clone()
+    f0[..., 3] = 0
+    l_moved = locs.clone()
+    l_moved[..., 3, :] = 1.234  # a zero-flux star contributes nothing wherever it sits
+    assert torch.equal(model.loglikelihood(tiles, l_moved, f0), model.loglikelihood(tiles, locs, f0))
+    sub = torch.randperm(N)[:300]
+    ref = O.loglik(oracle_model(g.meta), tiles.cpu().numpy().reshape(T, 8, 8), locs[:, 0, sub].cpu().numpy(),
+                   fluxes[:, 0, sub].cpu().numpy())
+    assert rel_err(ll[:, 0, sub].cpu().numpy(), ref) < RTOL

@@ -147,19 +147,21 @@ int smcdet_prior_sample(const smcdet_prior_params *prior, const float *u_locs,
  * weights = softmax((tau-tau_prev)*loglik), ess = 1/sum w^2, logz += max + log(mean exp).
  * With do_temper = 0 the given tau / tau_prev are used as they are.
  * tau, tau_prev, ess, logz [T]; wlog, weights [T,N]; funcalls [T] (nullable) counts objective
- * evaluations. */
+ * evaluations; active [T] (nullable): tiles whose entry is 0 are skipped and none of their outputs
+ * is written. */
 int smcdet_temper_update(const float *loglik, float *tau, float *tau_prev, float ess_threshold,
                          int do_temper, float *wlog, float *weights, float *ess, float *logz,
-                         int32_t *funcalls, int T, int N, void *stream);
+                         int32_t *funcalls, const int32_t *active, int T, int N, void *stream);
 
 /* SMCsampler.resample, index part (smcdet/sampler.py:127-149): inclusive CDF of the weights in
  * double precision, then for every draw the first k with cdf[k] >= u, clamped to [0,N-1].
  *   multinomial: u [T,N] iid uniforms (double), searched against u*cdf[N-1]
  *   systematic : u [T], draw i uses (i+u)/N
- * u == NULL => Philox keyed by (seed, tile_ids[t] or t).  cdf_scratch [T,N] double. */
+ * u == NULL => Philox keyed by (seed, tile_ids[t] or t).  cdf_scratch [T,N] double.
+ * active [T] (nullable): tiles whose entry is 0 get the identity index. */
 int smcdet_resample(int method, const float *weights, const double *u, uint64_t seed,
-                    const int64_t *tile_ids, int64_t *index, double *cdf_scratch, int T, int N,
-                    void *stream);
+                    const int64_t *tile_ids, const int32_t *active, int64_t *index,
+                    double *cdf_scratch, int T, int N, void *stream);
 
 /* SMCsampler.resample, gather part (smcdet/sampler.py:150-168). */
 int smcdet_gather(const int64_t *index, const float *counts_in, const float *locs_in,

@@ -41,6 +41,34 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+# kernels launched by one call of each entry point (smcdet_mh_mutate: zero + mh + divide)
+KERNELS_PER_CALL = {
+    "smcdet_loglik": 1, "smcdet_psf": 1, "smcdet_render": 1, "smcdet_prior_logprob": 1, "smcdet_prior_sample": 1,
+    "smcdet_temper_update": 1, "smcdet_resample": 1, "smcdet_gather": 1, "smcdet_mh_mutate": 3, "smcdet_prune": 1,
+}
+
+
+class _CountingLib(object):
+    """Proxy over the bound CDLL that counts kernel launches per entry point (bench.py reports them)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.launches = 0
+        self.calls = {}
+        for name, n in KERNELS_PER_CALL.items():
+            setattr(self, name, self._wrap(name, getattr(cdll, name), n))
+
+    def _wrap(self, name, fn, n):
+        def call(*args):
+            self.launches += n
+            self.calls[name] = self.calls.get(name, 0) + 1
+            return fn(*args)
+        return call
+
+    def __getattr__(self, name):
+        return getattr(self._cdll, name)
+
+
 _lib = None
 
 
@@ -56,7 +84,7 @@ def lib():
         A.bind(cdll)
         if cdll.smcdet_version() != A.ABI_VERSION:
             raise RuntimeError("libsmcdet_b200.so ABI version mismatch; rebuild it")
-        _lib = cdll
+        _lib = _CountingLib(cdll)
     return _lib
 
 

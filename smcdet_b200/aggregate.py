@@ -73,7 +73,7 @@ class Aggregate(object):
         idx = torch.empty(T, n, device=dev, dtype=torch.int64)
         cdf = torch.empty(T, n, device=dev, dtype=torch.float64)
         uu = None if u is None else u.to(device=dev, dtype=torch.float64).contiguous()
-        L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(), None,
+        L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(), None, None,
                                         L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64), T, n, L.stream_for(w)))
         return idx.view(numH, numW, n)
 

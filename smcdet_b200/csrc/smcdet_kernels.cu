@@ -360,10 +360,11 @@ __global__ void __launch_bounds__(kTB) temper_update_kernel(const float* __restr
                                                             int do_temper, float* __restrict__ wlog,
                                                             float* __restrict__ weights, float* __restrict__ ess,
                                                             float* __restrict__ logz, int32_t* __restrict__ funcalls,
-                                                            int N) {
+                                                            const int32_t* __restrict__ active, int N) {
     SMC_SHARED double s_red[2 * (kTB / 32)];
     SMC_SHARED float s_redf[kTB / 32];
     const int t = blockIdx.x;
+    if (active != nullptr && active[t] == 0) return;
     const float* ll = loglik + (size_t)t * N;
 
     float tau_old, tau_new;
@@ -445,10 +446,15 @@ __global__ void __launch_bounds__(kTB) temper_update_kernel(const float* __restr
 __global__ void __launch_bounds__(kTB) resample_kernel(int method, const float* __restrict__ weights,
                                                        const double* __restrict__ u, uint64_t seed,
                                                        const int64_t* __restrict__ tile_ids,
+                                                       const int32_t* __restrict__ active,
                                                        int64_t* __restrict__ index, double* __restrict__ cdf_all,
                                                        int N) {
     SMC_SHARED double s_warp[kTB / 32];
     const int t = blockIdx.x;
+    if (active != nullptr && active[t] == 0) {
+        for (int i = threadIdx.x; i < N; i += kTB) index[(size_t)t * N + i] = i;
+        return;
+    }
     const float* w = weights + (size_t)t * N;
     double* cdf = cdf_all + (size_t)t * N;
     const int chunk = (N + kTB - 1) / kTB;
@@ -910,23 +916,23 @@ int smcdet_prior_sample(const smcdet_prior_params* prior, const float* u_locs, c
 }
 
 int smcdet_temper_update(const float* loglik, float* tau, float* tau_prev, float ess_threshold, int do_temper,
-                         float* wlog, float* weights, float* ess, float* logz, int32_t* funcalls, int T, int N,
-                         void* stream) {
+                         float* wlog, float* weights, float* ess, float* logz, int32_t* funcalls,
+                         const int32_t* active, int T, int N, void* stream) {
     SMC_REQUIRE(loglik && tau && tau_prev && wlog && weights && ess && logz, SMCDET_E_INVALID,
                 "smcdet_temper_update: null pointer");
     SMC_REQUIRE(T > 0 && N > 0, SMCDET_E_INVALID, "smcdet_temper_update: non-positive size");
     SMC_LAUNCH(temper_update_kernel, T, kTB, 0, (cudaStream_t)stream, loglik, tau, tau_prev, ess_threshold, do_temper, wlog,
-                                                              weights, ess, logz, funcalls, N);
+                                                              weights, ess, logz, funcalls, active, N);
     return launch_status("temper_update_kernel");
 }
 
 int smcdet_resample(int method, const float* weights, const double* u, uint64_t seed, const int64_t* tile_ids,
-                    int64_t* index, double* cdf_scratch, int T, int N, void* stream) {
+                    const int32_t* active, int64_t* index, double* cdf_scratch, int T, int N, void* stream) {
     SMC_REQUIRE(method == SMCDET_RESAMPLE_MULTINOMIAL || method == SMCDET_RESAMPLE_SYSTEMATIC, SMCDET_E_INVALID,
                 "smcdet_resample: unknown method");
     SMC_REQUIRE(weights && index && cdf_scratch, SMCDET_E_INVALID, "smcdet_resample: null pointer");
     SMC_REQUIRE(T > 0 && N > 0, SMCDET_E_INVALID, "smcdet_resample: non-positive size");
-    SMC_LAUNCH(resample_kernel, T, kTB, 0, (cudaStream_t)stream, method, weights, u, seed, tile_ids, index, cdf_scratch, N);
+    SMC_LAUNCH(resample_kernel, T, kTB, 0, (cudaStream_t)stream, method, weights, u, seed, tile_ids, active, index, cdf_scratch, N);
     return launch_status("resample_kernel");
 }
 

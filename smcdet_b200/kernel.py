@@ -24,6 +24,7 @@ class SingleComponentMH(object):
         self.fluxes_max = float(fluxes_max)
         self.last_loglik = None  # log-likelihood of the state returned by the last run()
         self.last_trace = None
+        self.event_log = None  # set to a list to record (start, end, active, n, iters) CUDA events per launch
 
     def _params(self):
         if self.locs_min is None or self.locs_max is None:
@@ -103,11 +104,17 @@ class SingleComponentMH(object):
         tids = None if tile_ids is None else tile_ids.to(device=dev, dtype=torch.int64).reshape(T).contiguous()
 
         mp, pp, kp = model._params(), prior._params(), self._params()
+        if self.event_log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(dev))
         L.check(L.lib().smcdet_mh_mutate(
             C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), L.ptr(cf), L.ptr(lf), L.ptr(ff), L.ptr(tau),
             L.ptr(loglik), L.ptr(acc), C.byref(tp) if tp is not None else None, C.byref(tr) if tr is not None else None,
             L.fresh_seed() if seed is None else int(seed), int(offset), L.ptr(tids, torch.int64),
             L.ptr(act, torch.int32), L.ptr(status, torch.int32), T, n, d, h, w, L.stream_for(lf)))
+        if self.event_log is not None:
+            ev1.record(torch.cuda.current_stream(dev))
+            self.event_log.append((ev0, ev1, act, T, n, d, iters))
         self._status = status
         self.last_loglik = loglik.view(numH, numW, n)
         return [lf.view(numH, numW, n, d, 2), ff.view(numH, numW, n, d), acc.view(numH, numW)]

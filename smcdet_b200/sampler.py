@@ -70,6 +70,7 @@ class SMCsampler(object):
         self.freeze_finished = freeze_finished
         self.verbose = verbose
         self._loglik_key = None
+        self._active = None
         self.iter = 0
 
     # ------------------------------------------------------------------------------------------
@@ -114,6 +115,20 @@ class SMCsampler(object):
         log_denominator = (2 * delta * loglikelihood).logsumexp(0)
         return (log_numerator - log_denominator).exp() - self.ess_threshold
 
+    def _active_i32(self):
+        """With ``freeze_finished``: int32 [T] mask of the tiles still below temperature 1 when the
+        current SMC iteration started (finished tiles are left exactly as they are, which is what
+        running each tile on its own does in the reference); None in lock-step mode."""
+        act = getattr(self, "_active", None)
+        return None if act is None else act.reshape(self._T).to(torch.int32).contiguous()
+
+    def _keep_inactive(self, new, old):
+        act = getattr(self, "_active", None)
+        if act is None:
+            return new
+        m = act.view(self.numH, self.numW, *([1] * (new.dim() - 2)))
+        return torch.where(m, new, old.to(new.device))
+
     def _temper_update(self, do_temper, logz, tau, tau_prev):
         T, n = self._T, self.num_catalogs
         ll = L.f32(self.loglik, self._device).view(T, n)
@@ -123,7 +138,8 @@ class SMCsampler(object):
         calls = torch.zeros(T, device=self._device, dtype=torch.int32)
         L.check(L.lib().smcdet_temper_update(L.ptr(ll), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold),
                                              int(do_temper), L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz),
-                                             L.ptr(calls, torch.int32), T, n, L.stream_for(ll)))
+                                             L.ptr(calls, torch.int32), L.ptr(self._active_i32(), torch.int32), T, n,
+                                             L.stream_for(ll)))
         return wlog, weights, ess, calls
 
     def temper(self):
@@ -133,7 +149,7 @@ class SMCsampler(object):
             self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)
             self._loglik_key = self._state_key()
         tau = L.f32(self.temperature, self._device).reshape(self._T).clone()
-        tau_prev = torch.empty_like(tau)
+        tau_prev = L.f32(self.temperature_prev, self._device).reshape(self._T).clone()
         scratch_logz = torch.zeros(self._T, device=self._device)
         _, _, _, calls = self._temper_update(1, scratch_logz, tau, tau_prev)
         self.tempering_funcalls = calls.view(self.numH, self.numW)
@@ -147,9 +163,9 @@ class SMCsampler(object):
         logz = L.f32(self.log_normalizing_constant, self._device).reshape(self._T).clone()
         wlog, weights, ess, _ = self._temper_update(0, logz, tau, tau_prev)
         n = self.num_catalogs
-        self.weights_log_unnorm = wlog.view(self.numH, self.numW, n)
-        self.weights = weights.view(self.numH, self.numW, n)
-        self.ess = ess.view(self.numH, self.numW)
+        self.weights_log_unnorm = self._keep_inactive(wlog.view(self.numH, self.numW, n), self.weights_log_unnorm)
+        self.weights = self._keep_inactive(weights.view(self.numH, self.numW, n), self.weights)
+        self.ess = self._keep_inactive(ess.view(self.numH, self.numW), self.ess)
         self.log_normalizing_constant = logz.view(self.numH, self.numW)
 
     def resample(self, *, u=None):
@@ -163,12 +179,8 @@ class SMCsampler(object):
         cdf = torch.empty(T, n, device=dev, dtype=torch.float64)
         uu = None if u is None else u.to(device=dev, dtype=torch.float64).contiguous()
         L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(),
-                                        L.ptr(self.tile_ids, torch.int64), L.ptr(idx, torch.int64),
-                                        L.ptr(cdf, torch.float64), T, n, L.stream_for(w)))
-        active = self._active_mask()
-        if active is not None:  # frozen tiles keep their particles (identity index)
-            ident = torch.arange(n, device=dev, dtype=torch.int64).expand(T, n)
-            idx = torch.where(active.view(T, 1), idx, ident).contiguous()
+                                        L.ptr(self.tile_ids, torch.int64), L.ptr(self._active_i32(), torch.int32),
+                                        L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64), T, n, L.stream_for(w)))
         d = self.fluxes.shape[-1]
         cin = L.f32(self.counts, dev).view(T, n)
         lin = L.f32(self.locs, dev).view(T, n, d, 2)
@@ -181,34 +193,29 @@ class SMCsampler(object):
         self.locs = lout.view(self.numH, self.numW, n, d, 2)
         self.fluxes = fout.view(self.numH, self.numW, n, d)
         uniform = torch.full((self.numH, self.numW, n), 1.0 / n, device=dev)
-        self.weights = uniform if active is None else torch.where(active.unsqueeze(-1), uniform, self.weights)
-        self._loglik_key = None
-
-    def _active_mask(self):
-        """With ``freeze_finished``: tiles whose particles have not yet been resampled and mutated at
-        temperature 1 ([numH, numW] bool); None in the reference's lock-step mode."""
-        if not self.freeze_finished:
-            return None
-        return self.temperature_prev < 1
+        self.weights = self._keep_inactive(uniform, self.weights)
+        if getattr(self, "_active", None) is None:
+            self._loglik_key = None
+        else:  # frozen tiles keep their particles, so their cached log-likelihood row stays valid
+            self._loglik_key = ("resampled", self.locs.data_ptr())
 
     def mutate(self, **kw):
         """MH mutation of every particle (reference sampler.py:171-179)."""
-        if self.freeze_finished and "active" not in kw:
-            kw["active"] = self._active_mask().to(torch.int32)
+        act = getattr(self, "_active", None)
+        if act is not None and "active" not in kw:
+            kw["active"] = act.to(torch.int32)
         kw.setdefault("inplace", True)  # resample() just produced fresh buffers
         kw.setdefault("tile_ids", self.tile_ids)
         kw.setdefault("offset", self.iter)
         self.locs, self.fluxes, acc = self.MutationKernel.run(
             self.tiled_image, self.counts, self.locs, self.fluxes, self.temperature, self.log_target, **kw)
-        if kw.get("active") is not None:
-            act = kw["active"].to(acc.device).bool().view_as(acc)
-            acc = torch.where(act, acc, self.mutation_acc_rates.to(acc.device))
-            ll_new = getattr(self.MutationKernel, "last_loglik", None)
-            if ll_new is not None and hasattr(self, "loglik"):
-                ll_new = torch.where(act.unsqueeze(-1), ll_new, self.loglik)
-                self.MutationKernel.last_loglik = ll_new
-        self.mutation_acc_rates = acc
         ll = getattr(self.MutationKernel, "last_loglik", None)
+        if kw.get("active") is not None:
+            m = kw["active"].to(acc.device).bool().view_as(acc)
+            acc = torch.where(m, acc, self.mutation_acc_rates.to(acc.device))
+            if ll is not None:
+                ll = torch.where(m.unsqueeze(-1), ll, self.loglik)
+        self.mutation_acc_rates = acc
         if ll is not None:
             self.loglik = ll
             self._loglik_key = self._state_key()
@@ -246,11 +253,14 @@ class SMCsampler(object):
                     f"acceptance rate in [{round(self.mutation_acc_rates.min().item(), 2)}, "
                     f"{round(self.mutation_acc_rates.max().item(), 2)}]"
                 )
+            if self.freeze_finished:
+                self._active = self.temperature < 1
             self.resample()
             self.mutate()
             self.temper()
             self.update_weights()
 
+        self._active = None
         self.resample()
         self.pruned_counts, self.pruned_locs, self.pruned_fluxes = self.prune(self.locs, self.fluxes)
         if hasattr(self.MutationKernel, "check_status"):

@@ -108,7 +108,7 @@ class GpuBackend:
                                                  self._stream()))
         return counts.cpu().numpy(), locs.cpu().numpy(), fluxes.cpu().numpy()
 
-    def temper_update(self, loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True):
+    def temper_update(self, loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True, active=None):
         t = self.torch
         ll = self._d(loglik_)
         T, N = ll.shape
@@ -117,19 +117,21 @@ class GpuBackend:
         ess, calls = self._z((T,), t.float32), self._z((T,), t.int32)
         self._check(self.lib.smcdet_temper_update(self._p(ll), self._p(tau), self._p(tau_prev), ess_threshold,
                                                   int(do_temper), self._p(wlog), self._p(weights), self._p(ess),
-                                                  self._p(logz), self._p(calls), T, N, self._stream()))
+                                                  self._p(logz), self._p(calls), self._p(self._d(active, np.int32)), T, N,
+                                                  self._stream()))
         g = lambda x: x.cpu().numpy()  # noqa: E731
         return dict(tau=g(tau), tau_prev=g(tau_prev), wlog=g(wlog), weights=g(weights), ess=g(ess), logz=g(logz),
                     funcalls=g(calls))
 
-    def resample(self, method, weights, u=None, seed=0):
+    def resample(self, method, weights, u=None, seed=0, active=None):
         t = self.torch
         w = self._d(weights)
         T, N = w.shape
         idx, cdf = self._z((T, N), t.int64), self._z((T, N), t.float64)
         uu = self._d(u, np.float64)
-        self._check(self.lib.smcdet_resample(int(method), self._p(w), self._p(uu), seed, None, self._p(idx), self._p(cdf),
-                                             T, N, self._stream()))
+        self._check(self.lib.smcdet_resample(int(method), self._p(w), self._p(uu), seed, None,
+                                             self._p(self._d(active, np.int32)), self._p(idx), self._p(cdf), T, N,
+                                             self._stream()))
         return idx.cpu().numpy(), cdf.cpu().numpy()
 
     def gather(self, idx, counts, locs, fluxes):

@@ -101,25 +101,27 @@ def prior_sample(prior, T, num_per_count, D, u_locs=None, u_fluxes=None, seed=0,
     return counts, locs, fluxes
 
 
-def temper_update(loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True):
+def temper_update(loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True, active=None):
     ll = _f(loglik_)
     T, N = ll.shape
     tau, tau_prev, logz = _f(tau).reshape(-1).copy(), _f(tau_prev).reshape(-1).copy(), _f(logz).reshape(-1).copy()
     wlog, weights = np.zeros((T, N), np.float32), np.zeros((T, N), np.float32)
     ess = np.zeros(T, np.float32)
     calls = np.zeros(T, np.int32)
+    act = np.ascontiguousarray(active, np.int32) if active is not None else None
     check(lib().smcdet_temper_update(_p(ll), _p(tau), _p(tau_prev), ess_threshold, int(do_temper), _p(wlog), _p(weights),
-                                     _p(ess), _p(logz), _p(calls), T, N, None))
+                                     _p(ess), _p(logz), _p(calls), _p(act), T, N, None))
     return dict(tau=tau, tau_prev=tau_prev, wlog=wlog, weights=weights, ess=ess, logz=logz, funcalls=calls)
 
 
-def resample(method, weights, u=None, seed=0):
+def resample(method, weights, u=None, seed=0, active=None):
     w = _f(weights)
     T, N = w.shape
     idx = np.zeros((T, N), np.int64)
     cdf = np.zeros((T, N), np.float64)
     uu = np.ascontiguousarray(u, np.float64) if u is not None else None
-    check(lib().smcdet_resample(int(method), _p(w), _p(uu), seed, None, _p(idx), _p(cdf), T, N, None))
+    act = np.ascontiguousarray(active, np.int32) if active is not None else None
+    check(lib().smcdet_resample(int(method), _p(w), _p(uu), seed, None, _p(act), _p(idx), _p(cdf), T, N, None))
     return idx, cdf
 
 

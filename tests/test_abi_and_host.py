@@ -59,8 +59,8 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert b"smcdet_loglik" in cdll.smcdet_last_error_string()
     m.model_kind = _abi.MODEL_M71_NORMAL
     assert cdll.smcdet_loglik(ctypes.byref(m), None, None, None, None, 1, 1, 1, 8, 8, None) == _abi.E_INVALID
-    assert cdll.smcdet_resample(5, None, None, 0, None, None, None, 1, 1, None) == _abi.E_INVALID
-    assert cdll.smcdet_temper_update(None, None, None, 1.0, 1, None, None, None, None, None, 1, 1, None) == _abi.E_INVALID
+    assert cdll.smcdet_resample(5, None, None, 0, None, None, None, None, 1, 1, None) == _abi.E_INVALID
+    assert cdll.smcdet_temper_update(None, None, None, 1.0, 1, None, None, None, None, None, None, 1, 1, None) == _abi.E_INVALID
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -15,7 +15,7 @@ from . import _abi as A
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _SRC_DIR = os.path.join(_PKG, "csrc")
-LIB_PATH = os.path.join(_PKG, "libsmcdet_b200.so")
+LIB_PATH = os.environ.get("SMCDET_B200_LIB") or os.path.join(_PKG, "libsmcdet_b200.so")
 _SOURCES = [os.path.join(_SRC_DIR, "smcdet_kernels.cu"), os.path.join(_SRC_DIR, "smcdet_math.cuh"),
             os.path.join(os.path.dirname(_PKG), "include", "smcdet_b200.h")]
 

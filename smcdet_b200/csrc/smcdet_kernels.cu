@@ -533,9 +533,24 @@ __global__ void gather_kernel(const int64_t* __restrict__ index, const float* __
 // ---------------------------------------------------------------------------------------------
 // Kernel 4: fused single-component MH
 // ---------------------------------------------------------------------------------------------
+// count prior log-pmf, out of line (lgammaf is large and this runs once per particle)
+__device__ __noinline__ float count_logpmf_scalar(int kind, float rate, int mn, int mx, float c) {
+    smcdet_prior_params p;
+    p.count_kind = kind; p.count_rate = rate; p.min_objects = mn; p.max_objects = mx;
+    return count_logpmf(p, c);
+}
+
+// the reference's two-erf arithmetic for proposal boxes narrower than 12 sigma: kept out of line so the
+// rarely taken path does not bloat the hot loop
+__device__ __noinline__ TruncNormal truncnormal_make_general(float mu, float sigma, float lb, float ub) {
+    return truncnormal_make(mu, sigma, lb, ub);
+}
+
 struct MHArgs {
     ModelK m;
-    smcdet_prior_params prior;
+    PriorK pk;
+    int count_kind, min_objects, max_objects;
+    float count_rate;
     smcdet_mh_params mh;
     const float* tiles;
     const float* counts;
@@ -558,8 +573,11 @@ struct MHArgs {
     int T, N, D, blocks_per_tile;
 };
 
+#ifndef SMC_MH_MINB
+#define SMC_MH_MINB 3
+#endif
 template <int MODEL, int H, int W, int TPP>
-__global__ void __launch_bounds__(kBT) mh_kernel(const MHArgs a) {
+__global__ void __launch_bounds__(kBT, (H == 8 && TPP == 1) ? SMC_MH_MINB : 1) mh_kernel(const MHArgs a) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
     float* s_tile = smem;
@@ -586,84 +604,148 @@ __global__ void __launch_bounds__(kBT) mh_kernel(const MHArgs a) {
     float* my_rate = s_rate + threadIdx.x;
     const float* my_star = s_star + pi;
 
-    // ---- state on entry: rate image, log-likelihood, log prior, cached log target (kernel.py:88-96)
-    float acc[PPT];
-    render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) my_rate[p * kBT] = acc[p] + m.bg;
-    float ll = group_sum<TPP>(pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int p) { return acc[p] + m.bg; }));
+    // ---- per-particle constants
     const float count = valid ? a.counts[pn] : (float)D;
     const float tau = a.tau[t];
-    const float prior0 = prior_logprob_catalog(a.prior, count, D, [&](int d, float& l0, float& l1, float& f) {
-        l0 = my_star[(d * 3 + 0) * PB]; l1 = my_star[(d * 3 + 1) * PB]; f = my_star[(d * 3 + 2) * PB];
-    });
-    float cached = prior0 + tau * ll;
-
-    if (a.status != nullptr && valid && sub == 0) {
+    // log prior (prior.py:67-75, :220-226) kept as: count term + sum of finite star terms, and the number
+    // of live stars outside the location prior's support (each contributes -inf); a single-star move
+    // then updates it in O(1)
+    const float count_lp = count_logpmf_scalar(a.count_kind, a.count_rate, a.min_objects, a.max_objects, count);
+    float prior_fin = 0.0f;
+    int prior_bad = 0;
+    {
         bool oob = false;
         for (int d = 0; d < D; ++d) {
             const float l0 = my_star[(d * 3 + 0) * PB], l1 = my_star[(d * 3 + 1) * PB], f = my_star[(d * 3 + 2) * PB];
+            if ((float)d < count) {
+                int bad;
+                prior_fin += star_prior_term(a.pk, l0, l1, f, bad);
+                prior_bad += bad;
+            }
             oob |= !(l0 >= a.mh.locs_min[0] && l0 <= a.mh.locs_max[0] && l1 >= a.mh.locs_min[1] &&
                      l1 <= a.mh.locs_max[1] && f >= a.mh.fluxes_min && f <= a.mh.fluxes_max);
         }
-        if (oob) atomicOr(a.status, SMCDET_STATUS_OUT_OF_BOX);
+        if (a.status != nullptr && valid && sub == 0 && oob) atomicOr(a.status, SMCDET_STATUS_OUT_OF_BOX);
     }
 
     const uint64_t tile_key = a.tile_ids ? (uint64_t)a.tile_ids[t] : (uint64_t)t;
     const uint32_t pidx = (uint32_t)(n0 + pi);
     const float sl = a.mh.locs_stdev, sf = a.mh.fluxes_stdev;
+    const float isl = (1.0f / sl) * kInvSqrt2, isf = (1.0f / sf) * kInvSqrt2;
+    // every proposal box of the reference is far wider than 12 sigma; narrower ones take the general path
+    const bool wide_l = fminf(a.mh.locs_max[0] - a.mh.locs_min[0], a.mh.locs_max[1] - a.mh.locs_min[1]) >= 12.0f * sl;
+    const bool wide_f = (a.mh.fluxes_max - a.mh.fluxes_min) >= 12.0f * sf;
+    Philox4 rc = {{0u, 0u, 0u, 0u}};
     int last_acc = 0;
+    float ll = 0.0f, cached = 0.0f;
+    float acc[PPT];
 
-    for (int it = 0; it < a.mh.num_iters; ++it) {
-        // ---- draws: component, 2 location uniforms, flux uniform, accept uniform
+    // One loop, one copy of the render / pixel code (the unrolled body is large, so it must not be
+    // replicated: instruction-cache misses were 12% of the stalls when it was):
+    //   it = -1          full render of the entry state -> rate image, log-likelihood, cached log target
+    //                    (the log_denom_target of kernel.py:88-96)
+    //   it = 0..iters-1  one MH sweep: rate' = rate - old star + new star on the lane's pixels
+    //   it = iters       fresh full render of the final state -> loglik_out (what sampler.py:100-102 recomputes)
+    const int it_end = a.mh.num_iters + (a.loglik_out != nullptr ? 1 : 0);
+    for (int it = -1; it < it_end; ++it) {
+        const bool full = (it < 0) || (it == a.mh.num_iters);
         int k = 0;
         float u0 = 0.5f, u1 = 0.5f, uf = 0.5f, ua = 0.5f;
-        const size_t e = ((size_t)it * a.T + t) * N + (n0 + pi);
-        if (a.tape_comp != nullptr) {
-            if (valid) {
-                k = a.tape_comp[e];
-                u0 = a.tape_u_loc[2 * e]; u1 = a.tape_u_loc[2 * e + 1];
-                uf = a.tape_u_flux[e]; ua = a.tape_u_acc[e];
+        float l0 = 0.f, l1 = 0.f, f = 0.f, pl0 = 0.f, pl1 = 0.f, pf = 0.f, lq = 0.f;
+        const size_t e = ((size_t)max(it, 0) * a.T + t) * N + (n0 + pi);
+        if (!full) {
+            // ---- draws: component, 2 location uniforms, flux uniform, accept uniform
+            if (a.tape_comp != nullptr) {
+                if (valid) {
+                    k = a.tape_comp[e];
+                    u0 = a.tape_u_loc[2 * e]; u1 = a.tape_u_loc[2 * e + 1];
+                    uf = a.tape_u_flux[e]; ua = a.tape_u_acc[e];
+                }
+            } else {
+                const uint32_t c2 = (uint32_t)(a.offset << 16) ^ (uint32_t)it;
+                const Philox4 r = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHDraws, (uint32_t)a.seed,
+                                                (uint32_t)(a.seed >> 32));
+                if ((it & 3) == 0)  // one Philox call yields the components of four iterations
+                    rc = philox4x32_10(pidx, (uint32_t)tile_key, (uint32_t)(a.offset << 16) ^ (uint32_t)(it >> 2),
+                                       kStreamMHComp, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]); ua = u01_f(r.v[3]);
+                const int sel = it & 3;
+                const uint32_t cw = sel == 0 ? rc.v[0] : (sel == 1 ? rc.v[1] : (sel == 2 ? rc.v[2] : rc.v[3]));
+                k = (int)(((uint64_t)cw * (uint64_t)D) >> 32);
             }
-        } else {
-            const uint32_t c2 = (uint32_t)(a.offset << 16) ^ (uint32_t)it;
-            const Philox4 r = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHDraws, (uint32_t)a.seed,
-                                            (uint32_t)(a.seed >> 32));
-            const Philox4 rc = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHComp, (uint32_t)a.seed,
-                                             (uint32_t)(a.seed >> 32));
-            u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]); ua = u01_f(r.v[3]);
-            k = (int)(((uint64_t)rc.v[0] * (uint64_t)D) >> 32);
+
+            // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
+            l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
+            TruncNormal q0, q1, qf, r0, r1, rf;
+            if (wide_l) {
+                q0 = truncnormal_make_wide(l0, isl, a.mh.locs_min[0], a.mh.locs_max[0]);
+                q1 = truncnormal_make_wide(l1, isl, a.mh.locs_min[1], a.mh.locs_max[1]);
+            } else {
+                q0 = truncnormal_make_general(l0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
+                q1 = truncnormal_make_general(l1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
+            }
+            qf = wide_f ? truncnormal_make_wide(f, isf, a.mh.fluxes_min, a.mh.fluxes_max)
+                        : truncnormal_make_general(f, sf, a.mh.fluxes_min, a.mh.fluxes_max);
+            pl0 = truncnormal_draw(q0, l0, sl, a.mh.locs_min[0], a.mh.locs_max[0], u0);
+            pl1 = truncnormal_draw(q1, l1, sl, a.mh.locs_min[1], a.mh.locs_max[1], u1);
+            pf = truncnormal_draw(qf, f, sf, a.mh.fluxes_min, a.mh.fluxes_max, uf);
+            if (wide_l) {
+                r0 = truncnormal_make_wide(pl0, isl, a.mh.locs_min[0], a.mh.locs_max[0]);
+                r1 = truncnormal_make_wide(pl1, isl, a.mh.locs_min[1], a.mh.locs_max[1]);
+            } else {
+                r0 = truncnormal_make_general(pl0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
+                r1 = truncnormal_make_general(pl1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
+            }
+            rf = wide_f ? truncnormal_make_wide(pf, isf, a.mh.fluxes_min, a.mh.fluxes_max)
+                        : truncnormal_make_general(pf, sf, a.mh.fluxes_min, a.mh.fluxes_max);
+            // log q(prev|prop) - log q(prop|prev): the Gaussian parts are identical and cancel, leaving the
+            // box masses (kernel.py:71-85, :97-111)
+            lq = ((q0.log_mass + q1.log_mass) + qf.log_mass) - ((r0.log_mass + r1.log_mass) + rf.log_mass);
         }
 
-        // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
-        const float l0 = my_star[(k * 3 + 0) * PB], l1 = my_star[(k * 3 + 1) * PB], f = my_star[(k * 3 + 2) * PB];
-        const TruncNormal q0 = truncnormal_make(l0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
-        const TruncNormal q1 = truncnormal_make(l1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
-        const TruncNormal qf = truncnormal_make(f, sf, a.mh.fluxes_min, a.mh.fluxes_max);
-        const float pl0 = truncnormal_draw(q0, l0, sl, a.mh.locs_min[0], a.mh.locs_max[0], u0);
-        const float pl1 = truncnormal_draw(q1, l1, sl, a.mh.locs_min[1], a.mh.locs_max[1], u1);
-        const float pf = truncnormal_draw(qf, f, sf, a.mh.fluxes_min, a.mh.fluxes_max, uf);
-        const TruncNormal r0 = truncnormal_make(pl0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
-        const TruncNormal r1 = truncnormal_make(pl1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
-        const TruncNormal rf = truncnormal_make(pf, sf, a.mh.fluxes_min, a.mh.fluxes_max);
-        // log q(prev|prop) - log q(prop|prev): the Gaussian parts are identical and cancel, leaving the
-        // box masses (kernel.py:71-85, :97-111)
-        const float lq = ((q0.log_mass + q1.log_mass) + qf.log_mass) - ((r0.log_mass + r1.log_mass) + rf.log_mass);
-
-        // ---- likelihood of the proposal: rate' = rate - old star + new star on the lane's pixels
+        // ---- expected counts: all D stars (full render) or -old star +new star (MH sweep)
 #pragma unroll
         for (int p = 0; p < PPT; ++p) acc[p] = 0.0f;
-        if (f != 0.0f) star_accumulate<MODEL, RPT, W>(m, l0, l1, -(m.c0 * f), row0, acc);
-        if (pf != 0.0f) star_accumulate<MODEL, RPT, W>(m, pl0, pl1, m.c0 * pf, row0, acc);
+        const int ns = full ? D : 2;
+#pragma unroll 1
+        for (int s = 0; s < ns; ++s) {
+            float s0, s1, sw;
+            if (full) {
+                s0 = my_star[(s * 3 + 0) * PB]; s1 = my_star[(s * 3 + 1) * PB]; sw = m.c0 * my_star[(s * 3 + 2) * PB];
+            } else if (s == 0) {
+                s0 = l0; s1 = l1; sw = -(m.c0 * f);
+            } else {
+                s0 = pl0; s1 = pl1; sw = m.c0 * pf;
+            }
+            if (sw != 0.0f) star_accumulate<MODEL, RPT, W>(m, s0, s1, sw, row0, acc);
+        }
+        if (full) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                my_rate[p * kBT] = acc[p] + m.bg;
+                acc[p] = 0.0f;
+            }
+        }
         const float llp = group_sum<TPP>(
             pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int p) { return my_rate[p * kBT] + acc[p]; }));
 
+        if (full) {
+            ll = llp;
+            if (it < 0) cached = (prior_bad ? -INFINITY : count_lp + prior_fin) + tau * ll;
+            continue;
+        }
+
         // ---- prior of the proposal and the MH ratio (sampler.py:87-91, kernel.py:114-116)
-        const float priorp = prior_logprob_catalog(a.prior, count, D, [&](int d, float& x0, float& x1, float& xf) {
-            if (d == k) { x0 = pl0; x1 = pl1; xf = pf; }
-            else { x0 = my_star[(d * 3 + 0) * PB]; x1 = my_star[(d * 3 + 1) * PB]; xf = my_star[(d * 3 + 2) * PB]; }
-        });
-        const float target_p = priorp + tau * llp;
+        float fin_p = prior_fin;
+        int bad_p = prior_bad;
+        if ((float)k < count) {
+            int bad_old, bad_new;
+            const float t_old = star_prior_term(a.pk, l0, l1, f, bad_old);
+            const float t_new = star_prior_term(a.pk, pl0, pl1, pf, bad_new);
+            fin_p = (prior_fin - t_old) + t_new;
+            bad_p = prior_bad - bad_old + bad_new;
+        }
+        const float target_p = (bad_p ? -INFINITY : count_lp + fin_p) + tau * llp;
         const float log_alpha = (target_p - cached) + lq;
         float alpha = expf(log_alpha);
         if (alpha > 1.0f) alpha = 1.0f;  // clamp(max=1) keeps nan
@@ -674,6 +756,8 @@ __global__ void __launch_bounds__(kBT) mh_kernel(const MHArgs a) {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) my_rate[p * kBT] += acc[p];
             ll = llp;
+            prior_fin = fin_p;
+            prior_bad = bad_p;
             if (sub == 0) {
                 s_star[(k * 3 + 0) * PB + pi] = pl0;
                 s_star[(k * 3 + 1) * PB + pi] = pl1;
@@ -690,13 +774,7 @@ __global__ void __launch_bounds__(kBT) mh_kernel(const MHArgs a) {
             if (a.tr_accept) a.tr_accept[e] = (int8_t)last_acc;
         }
     }
-
-    // ---- log-likelihood of the final state from a fresh render (what sampler.py:100-102 recomputes)
-    if (a.loglik_out != nullptr) {
-        render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
-        ll = group_sum<TPP>(pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int p) { return acc[p] + m.bg; }));
-        if (valid && sub == 0) a.loglik_out[pn] = ll;
-    }
+    if (a.loglik_out != nullptr && valid && sub == 0) a.loglik_out[pn] = ll;
     const unsigned votes = __ballot_sync(0xffffffffu, valid && sub == 0 && last_acc);
     if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(a.acc_count + t, (float)__popc(votes));
     __syncthreads();
@@ -968,7 +1046,9 @@ int smcdet_mh_mutate(const smcdet_model_params* model, const smcdet_prior_params
     MHArgs a;
     memset(&a, 0, sizeof(a));
     a.m = make_model_k(*model);
-    a.prior = *prior;
+    a.pk = make_prior_k(*prior);
+    a.count_kind = prior->count_kind; a.min_objects = prior->min_objects; a.max_objects = prior->max_objects;
+    a.count_rate = prior->count_rate;
     a.mh = *mh;
     a.tiles = tiles; a.counts = counts; a.locs = locs; a.fluxes = fluxes; a.tau = tau;
     a.loglik_out = loglik_out; a.acc_count = acc_rate;

@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define SMC_HD __host__ __device__ __forceinline__
+#define SMC_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define SMC_HD inline
+#define SMC_HD_NOINLINE inline
 #endif
 
 namespace smc {
@@ -281,20 +283,37 @@ SMC_HD float normal_cdf_f(float x, float mu, float sigma) {
 
 struct TruncNormal {
     float cdf_lb;
-    float log_mass;  // nan_to_num(log(cdf(ub)-cdf(lb)))
+    float mass;      // cdf(ub) - cdf(lb)
+    float log_mass;  // nan_to_num(log(mass))
 };
 
+// the reference's arithmetic, any box (distributions.py:33-35)
 SMC_HD TruncNormal truncnormal_make(float mu, float sigma, float lb, float ub) {
     TruncNormal d;
     d.cdf_lb = normal_cdf_f(lb, mu, sigma);
     d.log_mass = nan_to_num_f(logf(normal_cdf_f(ub, mu, sigma) - d.cdf_lb));
+    d.mass = expf(d.log_mass);
+    return d;
+}
+
+// Box at least 12 sigma wide (every configuration of the reference): at most one bound is within
+// 6 sigma of mu, and beyond 5.6 sigma the float32 normal cdf is exactly 0 / 1, so
+//   cdf(ub) - cdf(lb) = 1 - q,  q = Phi(-min(mu - lb, ub - mu)/sigma) = 0.5 - 0.5 erf(z / sqrt 2)
+// with ONE erf instead of two, to float32 rounding of the reference's expression.
+SMC_HD TruncNormal truncnormal_make_wide(float mu, float inv_sigma_sqrt2, float lb, float ub) {
+    TruncNormal d;
+    const float a = mu - lb, b = ub - mu;
+    const float q = 0.5f - 0.5f * erff(fminf(a, b) * inv_sigma_sqrt2);
+    d.cdf_lb = (a < b) ? q : 0.0f;
+    d.mass = 1.0f - q;
+    d.log_mass = nan_to_num_f(logf(d.mass));
     return d;
 }
 
 SMC_HD float truncnormal_draw(const TruncNormal& d, float mu, float sigma, float lb, float ub, float u) {
     const float lo = 1e-6f, hi = (float)(1.0 - 1e-6);
     const float p = clamp_f(u, lo, hi);
-    const float pt = d.cdf_lb + p * expf(d.log_mass);
+    const float pt = d.cdf_lb + p * d.mass;  // reference: p * exp(log_prob_in_box)
     const float q = clamp_f(pt, lo, hi);
     const float x = mu + sigma * erfinv_f(2.0f * q - 1.0f) * kSqrt2;
     return clamp_f(x, lb, ub);
@@ -334,6 +353,54 @@ SMC_HD float loc_logpdf(const smcdet_prior_params& p, float l0, float l1) {
     const float in0 = (p.loc_low[0] <= l0 && p.loc_high[0] > l0) ? 0.0f : -INFINITY;
     const float in1 = (p.loc_low[1] <= l1 && p.loc_high[1] > l1) ? 0.0f : -INFINITY;
     return (in0 - logf(p.loc_high[0] - p.loc_low[0])) + (in1 - logf(p.loc_high[1] - p.loc_low[1]));
+}
+
+// Launch constants of the prior folded for the MH kernel.  Both Pareto families have a flux log density of
+// the form A - B log f (distributions.py:87-89; torch Pareto = Exponential -> exp -> affine), so one
+// branch-free expression serves them; empty slots (f == 0) are evaluated at `repl` (prior.py:187, :224).
+struct PriorK {
+    float loc_low[2], loc_high[2];
+    float loc_norm;          // log(h0-l0) + log(h1-l1)
+    float flux_a, flux_b;    // log density = flux_a - flux_b * log f
+    float repl;
+    int flux_is_normal;
+    float flux_mean, flux_inv2var, flux_lognorm;
+};
+
+inline PriorK make_prior_k(const smcdet_prior_params& p) {
+    PriorK k;
+    for (int c = 0; c < 2; ++c) { k.loc_low[c] = p.loc_low[c]; k.loc_high[c] = p.loc_high[c]; }
+    k.loc_norm = logf(p.loc_high[0] - p.loc_low[0]) + logf(p.loc_high[1] - p.loc_low[1]);
+    k.flux_is_normal = (p.flux_kind == SMCDET_FLUX_NORMAL) ? 1 : 0;
+    k.repl = p.flux_lower;
+    k.flux_a = k.flux_b = 0.f;
+    k.flux_mean = p.flux_mean;
+    k.flux_inv2var = 1.0f / (2.0f * p.flux_stdev * p.flux_stdev);
+    k.flux_lognorm = logf(p.flux_stdev) + kLogSqrt2Pi;
+    if (p.flux_kind == SMCDET_FLUX_TRUNCATED_PARETO) {
+        k.flux_a = p.flux_logpdf_const;
+        k.flux_b = p.flux_alpha + 1.0f;
+    } else if (p.flux_kind == SMCDET_FLUX_PARETO) {
+        k.flux_a = (float)(log((double)p.flux_alpha) + (double)p.flux_alpha * log((double)p.flux_lower));
+        k.flux_b = p.flux_alpha + 1.0f;
+    }
+    return k;
+}
+
+// One star's contribution to the prior, split into its finite part and an "outside the support of
+// the location prior" flag (whose log density is -inf), so that the MH kernel can update the prior
+// of a catalog incrementally when a single star moves.
+SMC_HD float star_prior_term(const PriorK& p, float l0, float l1, float f, int& bad) {
+    const bool inside = (p.loc_low[0] <= l0 && p.loc_high[0] > l0) && (p.loc_low[1] <= l1 && p.loc_high[1] > l1);
+    bad = inside ? 0 : 1;
+    float t;
+    if (p.flux_is_normal) {
+        const float d = f - p.flux_mean;
+        t = -(d * d) * p.flux_inv2var - p.flux_lognorm;
+    } else {
+        t = p.flux_a - p.flux_b * logf((f == 0.0f) ? p.repl : f);
+    }
+    return t - p.loc_norm;
 }
 
 template <class StarAt>

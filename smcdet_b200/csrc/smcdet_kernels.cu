@@ -23,7 +23,7 @@
 #else
 #include <cuda_runtime.h>
 #define SMC_SHARED __shared__
-#define SMC_DYN_SHARED(type, name) extern __shared__ type name[]
+#define SMC_DYN_SHARED(type, name) extern __shared__ __align__(16) type name[]
 #define SMC_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
@@ -163,8 +163,9 @@ __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float
     const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
     float acc[PPT];
     render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
-    const float part = pixel_loglik_sum<MODEL, PPT>(m, s_tile + row0 * W, s_lgam + row0 * W,
-                                                    [&](int p) { return acc[p] + m.bg; });
+    const float part = pixel_loglik_sum<MODEL, PPT>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
+        return make_float4(acc[4 * g] + m.bg, acc[4 * g + 1] + m.bg, acc[4 * g + 2] + m.bg, acc[4 * g + 3] + m.bg);
+    });
     const float ll = group_sum<TPP>(part);
     if (sub == 0 && pi < n_here) out[pbase + pi] = ll;
 }
@@ -540,10 +541,22 @@ __device__ __noinline__ float count_logpmf_scalar(int kind, float rate, int mn, 
     return count_logpmf(p, c);
 }
 
-// the reference's two-erf arithmetic for proposal boxes narrower than 12 sigma: kept out of line so the
-// rarely taken path does not bloat the hot loop
-__device__ __noinline__ TruncNormal truncnormal_make_general(float mu, float sigma, float lb, float ub) {
-    return truncnormal_make(mu, sigma, lb, ub);
+// One coordinate of the random-walk proposal (kernel.py:47-61, :71-85, :97-111; distributions.py:25-52):
+// draws x ~ TruncNormal(mu, sigma, [lb, ub]) from the uniform u and returns
+//   lq = log q(mu | x) - log q(x | mu) = log mass(mu) - log mass(x)
+// (the Gaussian parts of the two proposal densities are identical and cancel).  Out of line: it is called
+// three times per sweep and inlining its erf / erfinv / log bodies pushed the hot loop past the
+// instruction cache.  `wide` selects the one-erf form valid for boxes of at least 12 sigma.
+__device__ __noinline__ float truncnormal_step(float mu, float sigma, float inv_sigma_sqrt2, float lb, float ub,
+                                                float u, bool wide, float& lq) {
+    TruncNormal q, r;
+    if (wide) q = truncnormal_make_wide(mu, inv_sigma_sqrt2, lb, ub);
+    else q = truncnormal_make(mu, sigma, lb, ub);
+    const float x = truncnormal_draw(q, mu, sigma, lb, ub, u);
+    if (wide) r = truncnormal_make_wide(x, inv_sigma_sqrt2, lb, ub);
+    else r = truncnormal_make(x, sigma, lb, ub);
+    lq = q.log_mass - r.log_mass;
+    return x;
 }
 
 struct MHArgs {
@@ -601,7 +614,7 @@ __global__ void __launch_bounds__(kBT, (H == 8 && TPP == 1) ? SMC_MH_MINB : 1) m
     const size_t pn = pbase + pi;
     const float* xs = s_tile + row0 * W;
     const float* lg = s_lgam + row0 * W;
-    float* my_rate = s_rate + threadIdx.x;
+    float4* my_rate = reinterpret_cast<float4*>(s_rate) + threadIdx.x;  // [PPT/4][kBT] float4, conflict-free
     const float* my_star = s_star + pi;
 
     // ---- per-particle constants
@@ -676,31 +689,11 @@ __global__ void __launch_bounds__(kBT, (H == 8 && TPP == 1) ? SMC_MH_MINB : 1) m
 
             // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
             l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
-            TruncNormal q0, q1, qf, r0, r1, rf;
-            if (wide_l) {
-                q0 = truncnormal_make_wide(l0, isl, a.mh.locs_min[0], a.mh.locs_max[0]);
-                q1 = truncnormal_make_wide(l1, isl, a.mh.locs_min[1], a.mh.locs_max[1]);
-            } else {
-                q0 = truncnormal_make_general(l0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
-                q1 = truncnormal_make_general(l1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
-            }
-            qf = wide_f ? truncnormal_make_wide(f, isf, a.mh.fluxes_min, a.mh.fluxes_max)
-                        : truncnormal_make_general(f, sf, a.mh.fluxes_min, a.mh.fluxes_max);
-            pl0 = truncnormal_draw(q0, l0, sl, a.mh.locs_min[0], a.mh.locs_max[0], u0);
-            pl1 = truncnormal_draw(q1, l1, sl, a.mh.locs_min[1], a.mh.locs_max[1], u1);
-            pf = truncnormal_draw(qf, f, sf, a.mh.fluxes_min, a.mh.fluxes_max, uf);
-            if (wide_l) {
-                r0 = truncnormal_make_wide(pl0, isl, a.mh.locs_min[0], a.mh.locs_max[0]);
-                r1 = truncnormal_make_wide(pl1, isl, a.mh.locs_min[1], a.mh.locs_max[1]);
-            } else {
-                r0 = truncnormal_make_general(pl0, sl, a.mh.locs_min[0], a.mh.locs_max[0]);
-                r1 = truncnormal_make_general(pl1, sl, a.mh.locs_min[1], a.mh.locs_max[1]);
-            }
-            rf = wide_f ? truncnormal_make_wide(pf, isf, a.mh.fluxes_min, a.mh.fluxes_max)
-                        : truncnormal_make_general(pf, sf, a.mh.fluxes_min, a.mh.fluxes_max);
-            // log q(prev|prop) - log q(prop|prev): the Gaussian parts are identical and cancel, leaving the
-            // box masses (kernel.py:71-85, :97-111)
-            lq = ((q0.log_mass + q1.log_mass) + qf.log_mass) - ((r0.log_mass + r1.log_mass) + rf.log_mass);
+            float lq0, lq1, lqf;
+            pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
+            pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
+            pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
+            lq = (lq0 + lq1) + lqf;
         }
 
         // ---- expected counts: all D stars (full render) or -old star +new star (MH sweep)
@@ -721,13 +714,17 @@ __global__ void __launch_bounds__(kBT, (H == 8 && TPP == 1) ? SMC_MH_MINB : 1) m
         }
         if (full) {
 #pragma unroll
-            for (int p = 0; p < PPT; ++p) {
-                my_rate[p * kBT] = acc[p] + m.bg;
-                acc[p] = 0.0f;
+            for (int g = 0; g < PPT / 4; ++g) {
+                my_rate[g * kBT] = make_float4(acc[4 * g] + m.bg, acc[4 * g + 1] + m.bg, acc[4 * g + 2] + m.bg,
+                                               acc[4 * g + 3] + m.bg);
+                acc[4 * g] = acc[4 * g + 1] = acc[4 * g + 2] = acc[4 * g + 3] = 0.0f;
             }
         }
         const float llp = group_sum<TPP>(
-            pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int p) { return my_rate[p * kBT] + acc[p]; }));
+            pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int g) {
+                const float4 r = my_rate[g * kBT];
+                return make_float4(r.x + acc[4 * g], r.y + acc[4 * g + 1], r.z + acc[4 * g + 2], r.w + acc[4 * g + 3]);
+            }));
 
         if (full) {
             ll = llp;
@@ -747,14 +744,18 @@ __global__ void __launch_bounds__(kBT, (H == 8 && TPP == 1) ? SMC_MH_MINB : 1) m
         }
         const float target_p = (bad_p ? -INFINITY : count_lp + fin_p) + tau * llp;
         const float log_alpha = (target_p - cached) + lq;
-        float alpha = expf(log_alpha);
+        float alpha = ex2_fast(log_alpha * kLog2e);
         if (alpha > 1.0f) alpha = 1.0f;  // clamp(max=1) keeps nan
         const bool accept = (ua <= alpha);
 
         __syncwarp();  // every lane of the particle has read the old star
         if (accept) {
 #pragma unroll
-            for (int p = 0; p < PPT; ++p) my_rate[p * kBT] += acc[p];
+            for (int g = 0; g < PPT / 4; ++g) {
+                float4 r = my_rate[g * kBT];
+                r.x += acc[4 * g]; r.y += acc[4 * g + 1]; r.z += acc[4 * g + 2]; r.w += acc[4 * g + 3];
+                my_rate[g * kBT] = r;
+            }
             ll = llp;
             prior_fin = fin_p;
             prior_bad = bad_p;

@@ -21,6 +21,11 @@
 #define SMC_HD_NOINLINE inline
 #endif
 
+#if !defined(__CUDACC__)
+struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#endif
+
 namespace smc {
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -162,17 +167,17 @@ struct ColFactors {
 
 template <int MODEL, int W>
 SMC_HD void col_factors(const ModelK& m, float l1, ColFactors<MODEL, W>& c) {
-    const float fl = floorf(l1);
+    // columns outside the (2R+1) patch anchored at floor(l1) get squared distance +inf: their Gaussian
+    // factors become ex2(-inf) = 0 and their wing argument +inf
+    const float lo = floorf(l1) - m.radius, hi = floorf(l1) + m.radius;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        const float dj = (float)j - fl;
-        const bool in = (dj >= -m.radius) && (dj <= m.radius);
         const float dx = ((float)j + 0.5f) - l1;
-        const float d2 = dx * dx;
-        c.e1[j] = in ? ex2_fast(-m.k1 * d2) : 0.0f;
+        const float d2 = ((float)j >= lo && (float)j <= hi) ? dx * dx : INFINITY;
+        c.e1[j] = ex2_fast(-m.k1 * d2);
         if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-            c.e2[j] = in ? ex2_fast(-m.k2 * d2) : 0.0f;
-            c.bx[j] = in ? m.cpl * d2 : INFINITY;
+            c.e2[j] = ex2_fast(-m.k2 * d2);
+            c.bx[j] = m.cpl * d2;
         }
     }
 }
@@ -182,29 +187,29 @@ template <int MODEL, int RPT, int W>
 SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int row0, float (&acc)[RPT * W]) {
     ColFactors<MODEL, W> c;
     col_factors<MODEL, W>(m, l1, c);
-    const float fl = floorf(l0);
+    const float lo = floorf(l0) - m.radius, hi = floorf(l0) + m.radius;
     float lw = 0.f, sgn = 1.f;
     if (MODEL == SMCDET_MODEL_M71_NORMAL) {
         lw = lg2_fast(fabsf(wgt) * m.p0);
         sgn = (wgt < 0.f) ? -1.f : 1.f;
     }
+    const float wb = wgt * m.b;
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const float fi = (float)(row0 + r);
-        const float di = fi - fl;
-        const bool in = (di >= -m.radius) && (di <= m.radius);
         const float dy = (fi + 0.5f) - l0;
-        const float d2 = dy * dy;
-        const float g1 = in ? wgt * ex2_fast(-m.k1 * d2) : 0.0f;
+        const float d2 = (fi >= lo && fi <= hi) ? dy * dy : INFINITY;
+        const float g1 = wgt * ex2_fast(-m.k1 * d2);
         if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-            const float g2 = in ? (wgt * m.b) * ex2_fast(-m.k2 * d2) : 0.0f;
-            const float ay = in ? fmaf(m.cpl, d2, 1.0f) : INFINITY;
+            const float g2 = wb * ex2_fast(-m.k2 * d2);
+            const float ay = fmaf(m.cpl, d2, 1.0f);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 const float t = ay + c.bx[j];
                 const float pw = ex2_fast(fmaf(m.hb, lg2_fast(t), lw));
-                const float g = fmaf(g2, c.e2[j], g1 * c.e1[j]);
-                acc[r * W + j] = fmaf(sgn, pw, acc[r * W + j] + g);
+                float v = fmaf(g1, c.e1[j], acc[r * W + j]);
+                v = fmaf(g2, c.e2[j], v);
+                acc[r * W + j] = fmaf(sgn, pw, v);
             }
         } else {
 #pragma unroll
@@ -221,38 +226,60 @@ SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int 
 //     where rate > 50000.  lgam[p] = lgamma(x[p]+1).
 // rate_at(p) returns the expected count of the thread's p-th pixel.
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, int NPIX, class RateAt>
-SMC_HD float pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam, RateAt rate_at) {
+template <int MODEL, int NPIX, class Rate4>
+SMC_HD float pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam, Rate4 rate4) {
+    // x / lgam: the lane's NPIX observed pixels (16-byte aligned); rate4(q) returns the expected counts
+    // of pixels 4q..4q+3
+    const float4* x4 = reinterpret_cast<const float4*>(x);
     if (MODEL == SMCDET_MODEL_M71_NORMAL) {
         float q0 = 0.f, q1 = 0.f, s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int p = 0; p < NPIX; p += 2) {
-            const float ra = rate_at(p), rb = rate_at(p + 1);
-            const float va = fmaf(m.nm, ra, m.na), vb = fmaf(m.nm, rb, m.na);
-            const float da = x[p] - ra, db = x[p + 1] - rb;
-            const float den = va * vb;
-            const float num = fmaf(da * da, vb, (db * db) * va);
-            const float q = num * rcp_fast(den);
-            const float l = lg2_fast(den);
-            if ((p >> 1) & 1) { q1 += q; s1 += l; } else { q0 += q; s0 += l; }
+        for (int g = 0; g < NPIX / 4; ++g) {
+            const float4 r = rate4(g);
+            const float4 xv = x4[g];
+            {
+                const float va = fmaf(m.nm, r.x, m.na), vb = fmaf(m.nm, r.y, m.na);
+                const float da = xv.x - r.x, db = xv.y - r.y;
+                const float den = va * vb;
+                const float num = fmaf(da * da, vb, (db * db) * va);
+                q0 = fmaf(num, rcp_fast(den), q0);
+                s0 += lg2_fast(den);
+            }
+            {
+                const float va = fmaf(m.nm, r.z, m.na), vb = fmaf(m.nm, r.w, m.na);
+                const float da = xv.z - r.z, db = xv.w - r.w;
+                const float den = va * vb;
+                const float num = fmaf(da * da, vb, (db * db) * va);
+                q1 = fmaf(num, rcp_fast(den), q1);
+                s1 += lg2_fast(den);
+            }
         }
         return fmaf(-0.5f, q0 + q1, fmaf(-0.5f * kLn2, s0 + s1, -(float)NPIX * kLogSqrt2Pi));
     } else {
+        const float4* l4 = reinterpret_cast<const float4*>(lgam);
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int p = 0; p < NPIX; ++p) {
-            const float r = rate_at(p);
-            const float xv = x[p];
-            const float lg = lg2_fast(r) * kLn2;
-            float term;
-            if (r > m.nswitch) {
-                const float d = xv - r;
-                term = fmaf(-0.5f * (d * d), rcp_fast(r), fmaf(-0.5f, lg, -kLogSqrt2Pi));
-            } else {
-                const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
-                term = (xl - r) - lgam[p];
+        for (int g = 0; g < NPIX / 4; ++g) {
+            const float4 r4 = rate4(g);
+            const float4 xv4 = x4[g];
+            const float4 lg4 = l4[g];
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+            const float xx[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+            const float gg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float r = rr[e], xv = xx[e];
+                const float lg = lg2_fast(r) * kLn2;
+                float term;
+                if (r > m.nswitch) {
+                    const float d = xv - r;
+                    term = fmaf(-0.5f * (d * d), rcp_fast(r), fmaf(-0.5f, lg, -kLogSqrt2Pi));
+                } else {
+                    const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
+                    term = (xl - r) - gg[e];
+                }
+                if (e & 1) a1 += term; else a0 += term;
             }
-            if (p & 1) a1 += term; else a0 += term;
         }
         return a0 + a1;
     }
@@ -306,7 +333,7 @@ SMC_HD TruncNormal truncnormal_make_wide(float mu, float inv_sigma_sqrt2, float 
     const float q = 0.5f - 0.5f * erff(fminf(a, b) * inv_sigma_sqrt2);
     d.cdf_lb = (a < b) ? q : 0.0f;
     d.mass = 1.0f - q;
-    d.log_mass = nan_to_num_f(logf(d.mass));
+    d.log_mass = lg2_fast(d.mass) * kLn2;  // mass in [0.5, 1]: absolute error of lg2.approx <= 2^-22
     return d;
 }
 
@@ -398,7 +425,7 @@ SMC_HD float star_prior_term(const PriorK& p, float l0, float l1, float f, int& 
         const float d = f - p.flux_mean;
         t = -(d * d) * p.flux_inv2var - p.flux_lognorm;
     } else {
-        t = p.flux_a - p.flux_b * logf((f == 0.0f) ? p.repl : f);
+        t = p.flux_a - p.flux_b * (lg2_fast((f == 0.0f) ? p.repl : f) * kLn2);
     }
     return t - p.loc_norm;
 }

@@ -270,3 +270,57 @@ def test_full_size_properties_m71():
     ref = O.loglik(oracle_model(g.meta), tiles.cpu().numpy().reshape(T, 8, 8), locs[:, 0, sub].cpu().numpy(),
                    fluxes[:, 0, sub].cpu().numpy())
     assert rel_err(ll[:, 0, sub].cpu().numpy(), ref) < RTOL
+
+
+def test_notebook_flow_runs_unchanged():
+    """notebooks/smc.ipynb cells 3-9 of the reference with only the imports swapped: generate an 8x8 image
+    from the true prior, run the sampler (fewer particles), summarise."""
+    from smcdet_b200.images import M71ImageModel, generate_images
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.prior import M71Prior
+    from smcdet_b200.sampler import SMCsampler
+
+    params = dict(background=104.1486587524414, adu_per_nmgy=241.02658081054688,
+                  psf_params=[1.107237458229065, 2.0800251960754395, 2.3254318237304688, 5.240590572357178,
+                              0.7346734404563904, 0.5114791393280029],
+                  psf_radius=8, noise_additive=1.0000007072408224e-10, noise_multiplicative=1.936462640762329,
+                  counts_rate=0.030264640226960182, flux_alpha=0.21411753249015655, flux_lower=0.06291294097900389,
+                  flux_upper=1804.6791992187502, flux_detection_threshold=0.25165176391601557)
+    torch.manual_seed(0)
+    image_dim, pad = 8, 4
+    TruePrior = M71Prior(min_objects=0, max_objects=100, counts_rate=params["counts_rate"], image_height=image_dim,
+                         image_width=image_dim, flux_alpha=params["flux_alpha"],
+                         flux_lower=params["flux_detection_threshold"], flux_upper=params["flux_upper"], pad=pad)
+    TrueImageModel = M71ImageModel(image_height=image_dim, image_width=image_dim, background=params["background"],
+                                   adu_per_nmgy=params["adu_per_nmgy"], psf_params=params["psf_params"],
+                                   psf_radius=params["psf_radius"], noise_additive=params["noise_additive"],
+                                   noise_multiplicative=params["noise_multiplicative"])
+    res = generate_images(TruePrior, TrueImageModel, flux_threshold=params["flux_detection_threshold"],
+                          loc_threshold_lower=0, loc_threshold_upper=image_dim, num_images=1)
+    unpruned_counts, unpruned_locs, unpruned_fluxes, pruned_counts, pruned_locs, pruned_fluxes, images = res
+    assert images.shape == (1, 8, 8) and unpruned_locs.shape == (1, 100, 2)
+    assert int(pruned_counts[0]) <= int(unpruned_counts[0])
+    assert float(images.min()) > 0
+
+    tile_dim = 8
+    TilePrior = M71Prior(min_objects=10, max_objects=10, counts_rate=params["counts_rate"], image_height=tile_dim,
+                         image_width=tile_dim, flux_alpha=params["flux_alpha"], flux_lower=params["flux_lower"],
+                         flux_upper=params["flux_upper"], pad=pad)
+    TileImageModel = M71ImageModel(image_height=tile_dim, image_width=tile_dim, background=params["background"],
+                                   adu_per_nmgy=params["adu_per_nmgy"], psf_params=params["psf_params"],
+                                   psf_radius=params["psf_radius"], noise_additive=params["noise_additive"],
+                                   noise_multiplicative=params["noise_multiplicative"])
+    MHKernel = SingleComponentMH(num_iters=100, locs_stdev=0.1, fluxes_stdev=2.5, fluxes_min=TilePrior.flux_lower,
+                                 fluxes_max=TilePrior.flux_upper)
+    sampler = SMCsampler(image=images[0], tile_dim=tile_dim, Prior=TilePrior, ImageModel=TileImageModel,
+                         MutationKernel=MHKernel, num_catalogs=2000, ess_threshold_prop=0.5,
+                         resample_method="multinomial", flux_detection_threshold=params["flux_detection_threshold"],
+                         max_smc_iters=100, print_every=2)
+    sampler.run()
+    sampler.summarize()
+    assert float(sampler.temperature) == 1.0
+    assert 0.05 < float(sampler.mutation_acc_rates) < 0.95
+    assert sampler.posterior_predictive_total_observed_flux.shape == (2000,)
+    # the posterior predictive total flux brackets the observed total flux
+    ppf = sampler.posterior_predictive_total_observed_flux
+    assert float(ppf.min()) < float(images[0].sum()) < float(ppf.max())

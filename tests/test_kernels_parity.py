@@ -314,3 +314,24 @@ def test_smc_stages_follow_the_reference(backend, name):
         prev = dn
     c, l, f = backend.prune(g.flat(f"{prev}_locs"), g.flat(f"{prev}_fluxes"), t, t, meta["flux_threshold"])
     assert np.array_equal(c, g.flat("pruned_counts")) and np.array_equal(l, g.flat("pruned_locs"))
+
+
+def test_active_mask_skips_tiles(backend):
+    """active[t] == 0: smcdet_temper_update writes nothing for the tile, smcdet_resample returns the identity."""
+    g = Golden("temper")
+    thr = g.meta["ess_threshold"]
+    ll, tin = g.flat("s2_loglik"), g["s2_tau_in"].reshape(-1)
+    T = ll.shape[0]
+    act = (np.arange(T) % 2).astype(np.int32)
+    full = backend.temper_update(ll, tin, tin, thr, g["s2_logz_in"])
+    part = backend.temper_update(ll, tin, tin, thr, g["s2_logz_in"], active=act)
+    on = act == 1
+    assert np.array_equal(part["tau"][on], full["tau"][on]) and np.array_equal(part["weights"][on], full["weights"][on])
+    assert np.array_equal(part["tau"][~on], tin[~on]) and np.all(part["weights"][~on] == 0)
+    assert np.array_equal(part["logz"][~on], g["s2_logz_in"].reshape(-1)[~on])
+    w = g.flat("s2_weights")
+    u = np.random.default_rng(1).random(w.shape)
+    idx, _ = backend.resample(A.RESAMPLE_MULTINOMIAL, w, u, active=act)
+    ref, _ = backend.resample(A.RESAMPLE_MULTINOMIAL, w, u)
+    assert np.array_equal(idx[on], ref[on])
+    assert np.array_equal(idx[~on], np.tile(np.arange(w.shape[1]), (int((~on).sum()), 1)))

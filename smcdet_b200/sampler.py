@@ -71,6 +71,9 @@ class SMCsampler(object):
         self.verbose = verbose
         self._loglik_key = None
         self._active = None
+        self._base_seed = None
+        self._seed_uses = {}
+        self._final = False
         self.iter = 0
 
     # ------------------------------------------------------------------------------------------
@@ -82,6 +85,18 @@ class SMCsampler(object):
         """Identity + in-place version of the particle tensors the cached log-likelihood belongs to."""
         return (self.locs.data_ptr(), self.locs._version, self.fluxes.data_ptr(), self.fluxes._version)
 
+    def _seed(self, stage, it=None):
+        """Philox key of one stage of one SMC iteration.  Derived from a single base seed (one draw from
+        torch's global generator per sampler) and (iteration, stage) only, so that -- together with streams
+        keyed by the global tile id -- a tile's trajectory does not depend on which other tiles share its
+        launches, nor on how many iterations they need."""
+        if self._base_seed is None:
+            self._base_seed = L.fresh_seed()
+        it = self.iter if it is None else it
+        rep = self._seed_uses.get((it, stage), 0)  # repeated manual calls at one iteration get new streams
+        self._seed_uses[(it, stage)] = rep + 1
+        return (self._base_seed + 0x9E3779B97F4A7C15 * (8 * (it + 1) + stage) + 0xD1B54A32D192ED03 * rep) & ((1 << 62) - 1)
+
     def _print(self, *a):
         if self.verbose:
             print(*a)
@@ -90,7 +105,7 @@ class SMCsampler(object):
         """Prior draws, first likelihood, uniform weights (reference sampler.py:57-85).
         ``tape`` = (u_locs, u_fluxes) injects the uniforms of the prior draw."""
         self.counts, self.locs, self.fluxes = self.Prior._sample_grid(
-            self.numH, self.numW, None, True, self.num_catalogs, tape=tape, tile_ids=self.tile_ids)
+            self.numH, self.numW, None, True, self.num_catalogs, tape=tape, seed=self._seed(0), tile_ids=self.tile_ids)
         dev = self._device
         self.temperature_prev = torch.zeros(self.numH, self.numW, device=dev)
         self.temperature = torch.zeros(self.numH, self.numW, device=dev)
@@ -178,7 +193,8 @@ class SMCsampler(object):
         idx = torch.empty(T, n, device=dev, dtype=torch.int64)
         cdf = torch.empty(T, n, device=dev, dtype=torch.float64)
         uu = None if u is None else u.to(device=dev, dtype=torch.float64).contiguous()
-        L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(),
+        L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64),
+                                        self._seed(7, -1) if self._final else self._seed(1),
                                         L.ptr(self.tile_ids, torch.int64), L.ptr(self._active_i32(), torch.int32),
                                         L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64), T, n, L.stream_for(w)))
         d = self.fluxes.shape[-1]
@@ -207,6 +223,7 @@ class SMCsampler(object):
         kw.setdefault("inplace", True)  # resample() just produced fresh buffers
         kw.setdefault("tile_ids", self.tile_ids)
         kw.setdefault("offset", self.iter)
+        kw.setdefault("seed", self._seed(2))
         self.locs, self.fluxes, acc = self.MutationKernel.run(
             self.tiled_image, self.counts, self.locs, self.fluxes, self.temperature, self.log_target, **kw)
         ll = getattr(self.MutationKernel, "last_loglik", None)
@@ -237,6 +254,8 @@ class SMCsampler(object):
     def run(self):
         """reference sampler.py:221-256"""
         self.iter = 0
+        self._base_seed = None
+        self._seed_uses = {}
         self._print("starting...")
 
         self.initialize()
@@ -261,7 +280,9 @@ class SMCsampler(object):
             self.update_weights()
 
         self._active = None
+        self._final = True  # the closing resample uses an iteration-independent key
         self.resample()
+        self._final = False
         self.pruned_counts, self.pruned_locs, self.pruned_fluxes = self.prune(self.locs, self.fluxes)
         if hasattr(self.MutationKernel, "check_status"):
             self.MutationKernel.check_status()

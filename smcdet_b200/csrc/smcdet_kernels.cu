@@ -590,7 +590,7 @@ struct MHArgs {
 #define SMC_MH_MINB 3
 #endif
 template <int MODEL, int H, int W, int TPP>
-__global__ void __launch_bounds__(kBT, (H == 8 && TPP == 1) ? SMC_MH_MINB : 1) mh_kernel(const MHArgs a) {
+__global__ void __launch_bounds__(kBT, ((H / TPP) * W >= 64) ? SMC_MH_MINB : 4) mh_kernel(const MHArgs a) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
     float* s_tile = smem;
@@ -821,7 +821,9 @@ __global__ void prune_kernel(const float* __restrict__ locs, const float* __rest
 int choose_tpp(int side, long long particles) {
     const int min_tpp = side == 8 ? 1 : (side == 16 ? 4 : 16);
     const int max_tpp = side == 8 ? 8 : (side == 16 ? 16 : 32);
-    const long long want = (long long)num_sms() * 768;  // threads that keep every SM busy
+    // measured on B200 (scripts/gpu_probe3.py, N = 10 000, 8x8): splitting a particle over more lanes only pays
+    // while the grid has fewer than ~256 threads per SM
+    const long long want = (long long)num_sms() * 256;
     int tpp = min_tpp;
     while (tpp < max_tpp && particles * tpp < want) tpp *= 2;
     return tpp;

@@ -358,3 +358,95 @@ def test_tiles_are_independent_of_batching_and_sharding():
     finally:
         L.lib().smcdet_debug_force_tpp(0)
     assert float(full.temperature.min()) == 1.0
+
+
+def test_other_prior_classes_match_torch_formulas():
+    """StarPrior / GeometricProcessPrior / base PointProcessPrior (reference prior.py:8-154) are thin classes
+    over the same kernels; check them against the reference's formulas written with torch.distributions."""
+    from torch.distributions import Geometric, Normal
+
+    from smcdet_b200.prior import GeometricProcessPrior, PointProcessPrior, PoissonProcessPrior, StarPrior
+
+    torch.manual_seed(0)
+    T, N, D, pad, t = 2, 32, 5, 2, 8
+    star = StarPrior(2, D, t, t, pad=pad, flux_mean=900.0, flux_stdev=120.0)
+    counts, locs, fluxes = star.sample(num_tiles_per_side=T, stratify_by_count=True, num_catalogs_per_count=N)
+    assert counts.shape == (T, T, 4 * N) and torch.equal(counts[0, 0, ::N].cpu(), torch.tensor([2.0, 3.0, 4.0, 5.0]))
+    mask = torch.arange(D, device=dev()) < counts.unsqueeze(-1)
+    assert (fluxes[~mask] == 0).all() and (locs[~mask] == 0).all()
+    assert abs(float(fluxes[mask].mean()) - 900.0) < 30 and abs(float(fluxes[mask].std()) - 120.0) < 20
+    lp = star.log_prob(counts, locs, fluxes)
+    width = float(t + 2 * pad)
+    ref = (-torch.log(torch.tensor(4.0)) + (mask * (-2 * torch.log(torch.tensor(width)))).sum(-1)
+           + (Normal(900.0, 120.0).log_prob(fluxes) * mask).sum(-1))
+    assert rel_err(lp.cpu().numpy(), ref.cpu().numpy()) < RTOL
+    base = PointProcessPrior(2, D, t, t, pad=pad)
+    lp0 = base.log_prob(counts, locs)
+    ref0 = -torch.log(torch.tensor(4.0)) + (mask * (-2 * torch.log(torch.tensor(width)))).sum(-1)
+    assert rel_err(lp0.cpu().numpy(), ref0.cpu().numpy()) < RTOL
+    assert len(base.sample(num_tiles_per_side=1, stratify_by_count=True, num_catalogs_per_count=4)) == 2
+    geo = GeometricProcessPrior(2, D, t, t, pad=pad)
+    lpg = geo.log_prob(counts, locs)
+    refg = Geometric(1 - torch.exp(torch.tensor(-1.5))).log_prob(counts.cpu()) + (ref0.cpu() + torch.log(torch.tensor(4.0)))
+    assert rel_err(lpg.cpu().numpy(), refg.numpy()) < RTOL
+    poi = PoissonProcessPrior(0, D, 0.03, t, t, pad=pad)
+    c2, l2 = poi.sample(num_catalogs=50)
+    assert c2.shape == (1, 1, 50) and float(c2.max()) <= D and l2.shape == (1, 1, 50, D, 2)
+    # a star outside the support of the location prior: -inf, as torch Uniform.log_prob gives
+    bad = locs.clone()
+    bad[0, 0, 0, 0, 0] = float(t + pad)
+    assert torch.isneginf(star.log_prob(counts, bad, fluxes)[0, 0, 0])
+
+
+def test_basic_config_full_run():
+    """experiments/basic of the reference (Gaussian PSF, Poisson noise, Pareto fluxes, D = 8): a full run with
+    Philox draws, systematic resampling and lock-step semantics."""
+    from smcdet_b200.images import ImageModel, generate_images
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.prior import ParetoStarPrior
+    from smcdet_b200.sampler import SMCsampler
+
+    torch.manual_seed(1)
+    flux_scale, flux_alpha = 384.265, 2.0
+    model = ImageModel(8, 8, background=200, psf_radius=8, psf_stdev=0.93)
+    true_prior = ParetoStarPrior(0, 8, 8, 8, flux_scale=0.9 * flux_scale, flux_alpha=flux_alpha, pad=2)
+    res = generate_images(true_prior, model, flux_scale, 0, 8, num_images=4)
+    images = res[-1]
+    assert images.shape == (4, 8, 8) and (images == images.round()).all() and float(images.min()) >= 0
+    big = torch.cat([torch.cat([images[0], images[1]], 1), torch.cat([images[2], images[3]], 1)], 0)  # 16x16 -> 2x2 tiles
+    prior = ParetoStarPrior(8, 8, 8, 8, flux_scale=0.9 * flux_scale, flux_alpha=flux_alpha, pad=2)
+    mh = SingleComponentMH(50, 0.1, 100, fluxes_min=prior.flux_scale, fluxes_max=1e6)
+    s = SMCsampler(big, 8, prior, model, mh, 3000, 0.5, "systematic", flux_scale, 200, verbose=False)
+    s.run()
+    assert s.temperature.shape == (2, 2) and float(s.temperature.min()) == 1.0
+    assert float(s.locs.min()) >= -2 and float(s.locs.max()) <= 10
+    assert float(s.fluxes.min()) >= prior.flux_scale * (1 - 1e-6)
+    assert torch.isfinite(s.log_normalizing_constant).all() and (s.pruned_counts <= 8).all()
+    # the posterior mean number of detected stars is in a sane range of the truth for every tile
+    true_counts = res[3].float().view(2, 2).to(s.pruned_counts.device)
+    est = s.posterior_mean_count(s.pruned_counts.float())
+    assert float((est - true_counts).abs().max()) <= 3.0
+
+
+def test_large_particle_count_one_tile():
+    """N = 300 000 particles on one tile: tempering / resampling blocks loop over N, loglik uses TPP = 1."""
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("smc_stages_m71")
+    meta = g.meta
+    torch.manual_seed(2)
+    model, prior, mh = build_objects(meta, iters=3)
+    tile = cu(g["image"])[:8, :8].contiguous()
+    N = 300000
+    s = SMCsampler(tile, 8, prior, model, mh, N, 0.5, "systematic", meta["flux_threshold"], 3, verbose=False)
+    s.initialize()
+    s.temper()
+    s.update_weights()
+    assert abs(float(s.ess) / (0.5 * N) - 1) < 1e-3 or float(s.temperature) == 1.0
+    s.resample()
+    s.mutate()
+    sub = torch.randperm(N)[:200]
+    ref = O.loglik(oracle_model(meta), tile.cpu().numpy().reshape(1, 8, 8), s.locs[0, :, sub].cpu().numpy(),
+                   s.fluxes[0, :, sub].cpu().numpy())
+    assert rel_err(s.loglik[0, :, sub].cpu().numpy(), ref) < RTOL
+    assert abs(float(s.weights.sum()) - 1) < 1e-3

@@ -33,13 +33,17 @@ class PointProcessPrior(object):
         self.pad = pad
         self.update_attrs()
 
+    @staticmethod
+    def _dev():
+        return L.device() if torch.cuda.is_available() else torch.device("cpu")
+
     def _make_count_prior(self):
         return DiscreteUniform(self.min_objects, self.max_objects)
 
     def update_attrs(self):
         self.num_counts = self.max_objects - self.min_objects + 1
         self.count_prior = self._make_count_prior()
-        dev = L.device() if torch.cuda.is_available() else torch.device("cpu")
+        dev = self._dev()
         self.loc_prior = Uniform(
             torch.full((2,), float(0 - self.pad), device=dev),
             torch.tensor((float(self.image_height + self.pad), float(self.image_width + self.pad)), device=dev),
@@ -159,7 +163,7 @@ class PoissonProcessPrior(PointProcessPrior):
         return self.counts_rate * (self.image_height + 2 * self.pad) * (self.image_width + 2 * self.pad)
 
     def _make_count_prior(self):
-        return Poisson(torch.tensor(float(self._count_rate())))
+        return Poisson(torch.tensor(float(self._count_rate()), device=self._dev()))
 
 
 class GeometricProcessPrior(PointProcessPrior):
@@ -168,7 +172,7 @@ class GeometricProcessPrior(PointProcessPrior):
     _count_kind = A.COUNT_NONE
 
     def _make_count_prior(self):
-        return Geometric(1 - torch.exp(torch.tensor(-1.5)))
+        return Geometric(1 - torch.exp(torch.tensor(-1.5, device=self._dev())))
 
 
 class StarPrior(PointProcessPrior):

@@ -388,6 +388,7 @@ def test_other_prior_classes_match_torch_formulas():
     geo = GeometricProcessPrior(2, D, t, t, pad=pad)
     lpg = geo.log_prob(counts, locs)
     refg = Geometric(1 - torch.exp(torch.tensor(-1.5))).log_prob(counts.cpu()) + (ref0.cpu() + torch.log(torch.tensor(4.0)))
+    assert lpg.is_cuda
     assert rel_err(lpg.cpu().numpy(), refg.numpy()) < RTOL
     poi = PoissonProcessPrior(0, D, 0.03, t, t, pad=pad)
     c2, l2 = poi.sample(num_catalogs=50)

@@ -171,6 +171,25 @@ class SMCsampler(object):
         self.temperature_prev = tau_prev.view(self.numH, self.numW)
         self.temperature = tau.view(self.numH, self.numW)
 
+    def _temper_and_update(self):
+        """temper() followed by update_weights() as ONE launch (smcdet_temper_update does both); used by
+        run(), where the two always come as a pair (reference sampler.py:246-247)."""
+        if self._loglik_key is None or self._loglik_key != self._state_key():
+            self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)
+            self._loglik_key = self._state_key()
+        tau = L.f32(self.temperature, self._device).reshape(self._T).clone()
+        tau_prev = L.f32(self.temperature_prev, self._device).reshape(self._T).clone()
+        logz = L.f32(self.log_normalizing_constant, self._device).reshape(self._T).clone()
+        wlog, weights, ess, calls = self._temper_update(1, logz, tau, tau_prev)
+        n = self.num_catalogs
+        self.tempering_funcalls = calls.view(self.numH, self.numW)
+        self.temperature_prev = tau_prev.view(self.numH, self.numW)
+        self.temperature = tau.view(self.numH, self.numW)
+        self.weights_log_unnorm = self._keep_inactive(wlog.view(self.numH, self.numW, n), self.weights_log_unnorm)
+        self.weights = self._keep_inactive(weights.view(self.numH, self.numW, n), self.weights)
+        self.ess = self._keep_inactive(ess.view(self.numH, self.numW), self.ess)
+        self.log_normalizing_constant = logz.view(self.numH, self.numW)
+
     def update_weights(self):
         """weights, ESS and log normalising constant (reference sampler.py:181-196)."""
         tau = L.f32(self.temperature, self._device).reshape(self._T).clone()
@@ -259,8 +278,7 @@ class SMCsampler(object):
         self._print("starting...")
 
         self.initialize()
-        self.temper()
-        self.update_weights()
+        self._temper_and_update()
 
         while torch.any(self.temperature < 1) and self.iter <= self.max_smc_iters:
             self.iter += 1
@@ -276,8 +294,7 @@ class SMCsampler(object):
                 self._active = self.temperature < 1
             self.resample()
             self.mutate()
-            self.temper()
-            self.update_weights()
+            self._temper_and_update()
 
         self._active = None
         self._final = True  # the closing resample uses an iteration-independent key

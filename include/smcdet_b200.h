@@ -163,10 +163,11 @@ int smcdet_resample(int method, const float *weights, const double *u, uint64_t 
                     const int64_t *tile_ids, const int32_t *active, int64_t *index,
                     double *cdf_scratch, int T, int N, void *stream);
 
-/* SMCsampler.resample, gather part (smcdet/sampler.py:150-168). */
+/* SMCsampler.resample, gather part (smcdet/sampler.py:150-168).  tile_mask [T] (nullable): tiles whose
+ * entry is 0 are skipped (their output rows are left as they are). */
 int smcdet_gather(const int64_t *index, const float *counts_in, const float *locs_in,
                   const float *fluxes_in, float *counts_out, float *locs_out, float *fluxes_out,
-                  int T, int N, int D, void *stream);
+                  const int32_t *tile_mask, int T, int N, int D, void *stream);
 
 /* SingleComponentMH.run with log_target = SMCsampler.log_target
  * (smcdet/kernel.py:26-130, smcdet/sampler.py:87-91): num_iters single-site random-walk MH

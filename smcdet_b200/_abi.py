@@ -68,7 +68,7 @@ PROTOTYPES = {
     "smcdet_prior_sample": (C.c_int, [C.POINTER(PriorParams), _P, _P, C.c_uint64, _P, _P, _P, _P, _I, _I, _I, _P]),
     "smcdet_temper_update": (C.c_int, [_P, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "smcdet_resample": (C.c_int, [_I, _P, _P, C.c_uint64, _P, _P, _P, _P, _I, _I, _P]),
-    "smcdet_gather": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "smcdet_gather": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "smcdet_mh_mutate": (C.c_int, [C.POINTER(ModelParams), C.POINTER(PriorParams), C.POINTER(MHParams),
                                    _P, _P, _P, _P, _P, _P, _P, C.POINTER(DrawTape), C.POINTER(MHTrace),
                                    C.c_uint64, C.c_uint64, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -90,7 +90,7 @@ class Aggregate(object):
             raise NotImplementedError("resampling to a different number of catalogs belongs to the tree merge")
         cs, ls, fs = torch.empty_like(cin), torch.empty_like(lin), torch.empty_like(fin)
         L.check(L.lib().smcdet_gather(L.ptr(idx, torch.int64), L.ptr(cin), L.ptr(lin), L.ptr(fin), L.ptr(cs), L.ptr(ls),
-                                      L.ptr(fs), T, n, d, L.stream_for(cin)))
+                                      L.ptr(fs), None, T, n, d, L.stream_for(cin)))
         ws = torch.full((numH, numW, n), 1.0 / n, device=dev)
         return cs.view(numH, numW, n), ls.view(numH, numW, n, d, 2), fs.view(numH, numW, n, d), ws
 

@@ -517,13 +517,15 @@ __global__ void __launch_bounds__(kTB) resample_kernel(int method, const float* 
 __global__ void gather_kernel(const int64_t* __restrict__ index, const float* __restrict__ counts_in,
                               const float* __restrict__ locs_in, const float* __restrict__ fluxes_in,
                               float* __restrict__ counts_out, float* __restrict__ locs_out,
-                              float* __restrict__ fluxes_out, int T, int N, int D) {
+                              float* __restrict__ fluxes_out, const int32_t* __restrict__ tile_mask, int T, int N,
+                              int D) {
     const int row = 3 * D + 1;
     const size_t total = (size_t)T * N * row;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const size_t pn = e / row;
         const int c = (int)(e - pn * row);
         const size_t t = pn / N;
+        if (tile_mask != nullptr && tile_mask[t] == 0) continue;
         const size_t src = t * N + (size_t)index[pn];
         if (c < 2 * D) locs_out[pn * 2 * D + c] = locs_in[src * 2 * D + c];
         else if (c < 3 * D) fluxes_out[pn * D + (c - 2 * D)] = fluxes_in[src * D + (c - 2 * D)];
@@ -1018,7 +1020,8 @@ int smcdet_resample(int method, const float* weights, const double* u, uint64_t 
 }
 
 int smcdet_gather(const int64_t* index, const float* counts_in, const float* locs_in, const float* fluxes_in,
-                  float* counts_out, float* locs_out, float* fluxes_out, int T, int N, int D, void* stream) {
+                  float* counts_out, float* locs_out, float* fluxes_out, const int32_t* tile_mask, int T, int N, int D,
+                  void* stream) {
     SMC_REQUIRE(index && counts_in && locs_in && fluxes_in && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID,
                 "smcdet_gather: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_gather: non-positive size");
@@ -1026,7 +1029,7 @@ int smcdet_gather(const int64_t* index, const float* counts_in, const float* loc
                 "smcdet_gather: in-place gather is not supported");
     const size_t total = (size_t)T * N * (3 * D + 1);
     SMC_LAUNCH(gather_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, index, counts_in, locs_in, fluxes_in,
-                                                                          counts_out, locs_out, fluxes_out, T, N, D);
+                                                                          counts_out, locs_out, fluxes_out, tile_mask, T, N, D);
     return launch_status("gather_kernel");
 }
 

@@ -220,9 +220,26 @@ class SMCsampler(object):
         cin = L.f32(self.counts, dev).view(T, n)
         lin = L.f32(self.locs, dev).view(T, n, d, 2)
         fin = L.f32(self.fluxes, dev).view(T, n, d)
-        cout, lout, fout = torch.empty_like(cin), torch.empty_like(lin), torch.empty_like(fin)
+        mask = None
+        act = getattr(self, "_active", None)
+        if act is None:
+            cout, lout, fout = torch.empty_like(cin), torch.empty_like(lin), torch.empty_like(fin)
+            self._spare = None
+        else:
+            # frozen tiles are not copied every iteration: two persistent buffer sets alternate, and a tile is
+            # copied while it is live and once more right after it finishes, after which both sets hold its
+            # final particles
+            spare = getattr(self, "_spare", None)
+            prev = getattr(self, "_active_prev", None)
+            if spare is None or spare[0].shape != cin.shape or prev is None:
+                cout, lout, fout = torch.empty_like(cin), torch.empty_like(lin), torch.empty_like(fin)
+            else:
+                cout, lout, fout = spare
+                mask = (act | prev).reshape(T).to(torch.int32).contiguous()
+            self._spare = (cin, lin, fin)
+            self._active_prev = act
         L.check(L.lib().smcdet_gather(L.ptr(idx, torch.int64), L.ptr(cin), L.ptr(lin), L.ptr(fin), L.ptr(cout),
-                                      L.ptr(lout), L.ptr(fout), T, n, d, L.stream_for(w)))
+                                      L.ptr(lout), L.ptr(fout), L.ptr(mask, torch.int32), T, n, d, L.stream_for(w)))
         self.resampled_index = idx.view(self.numH, self.numW, n)
         self.counts = cout.view(self.numH, self.numW, n)
         self.locs = lout.view(self.numH, self.numW, n, d, 2)
@@ -297,6 +314,7 @@ class SMCsampler(object):
             self._temper_and_update()
 
         self._active = None
+        self._spare = self._active_prev = None
         self._final = True  # the closing resample uses an iteration-independent key
         self.resample()
         self._final = False

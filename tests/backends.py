@@ -141,7 +141,7 @@ class GpuBackend:
         T, N, D, _ = locs.shape
         co, lo, fo = t.zeros_like(counts), t.zeros_like(locs), t.zeros_like(fluxes)
         self._check(self.lib.smcdet_gather(self._p(idx), self._p(counts), self._p(locs), self._p(fluxes), self._p(co),
-                                           self._p(lo), self._p(fo), T, N, D, self._stream()))
+                                           self._p(lo), self._p(fo), None, T, N, D, self._stream()))
         return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
 
     def mh_mutate(self, model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
@@ -188,5 +188,5 @@ class GpuBackend:
         counts = self._z((T, N), t.int64)
         lo, fo = t.zeros_like(locs), t.zeros_like(fluxes)
         self._check(self.lib.smcdet_prune(self._p(locs), self._p(fluxes), tile_h, tile_w, thr, self._p(counts),
-                                          self._p(lo), self._p(fo), T, N, D, self._stream()))
+                                          self._p(lo), self._p(fo), None, T, N, D, self._stream()))
         return counts.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()

@@ -130,7 +130,7 @@ def gather(idx, counts, locs, fluxes):
     counts, locs, fluxes = _f(counts), _f(locs), _f(fluxes)
     T, N, D, _ = locs.shape
     co, lo, fo = np.zeros_like(counts), np.zeros_like(locs), np.zeros_like(fluxes)
-    check(lib().smcdet_gather(_p(idx), _p(counts), _p(locs), _p(fluxes), _p(co), _p(lo), _p(fo), T, N, D, None))
+    check(lib().smcdet_gather(_p(idx), _p(counts), _p(locs), _p(fluxes), _p(co), _p(lo), _p(fo), None, T, N, D, None))
     return co, lo, fo
 
 

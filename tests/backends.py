@@ -188,5 +188,5 @@ class GpuBackend:
         counts = self._z((T, N), t.int64)
         lo, fo = t.zeros_like(locs), t.zeros_like(fluxes)
         self._check(self.lib.smcdet_prune(self._p(locs), self._p(fluxes), tile_h, tile_w, thr, self._p(counts),
-                                          self._p(lo), self._p(fo), None, T, N, D, self._stream()))
+                                          self._p(lo), self._p(fo), T, N, D, self._stream()))
         return counts.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()

@@ -325,13 +325,22 @@ def run_own(a):
     value = evals_all / (elapsed_ms * 1e-3)
     tiles_per_sec = a.gpus * T * a.steps / (elapsed_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (mh_kernel), timed live with CUDA events per launch
+    # ---- roofline of the dominant kernel (mh_kernel), timed live with CUDA events per launch.
+    # Units one launch processes, per live particle: 2 full renders (entry state, final refresh) of D stars and
+    # num_iters sweeps that each evaluate 2 stars (the one removed and the one proposed) on the P pixels, plus
+    # P pixel terms per evaluation.  Per-unit figures are SURVEY.md 8(d)'s: 4 MUFU / 12 FP32 instr per
+    # (star, pixel) PSF evaluation of the M71 model, 2 MUFU / 7 FP32 instr per Normal pixel term.
     mh_ms = sum(ev0.elapsed_time(ev1) for log in mh_logs for (ev0, ev1, *_r) in log)
     n_launch = sum(len(log) for log in mh_logs)
     P = TILE * TILE
-    mufu_per_eval = 4 * D * P + 2 * P          # M71 PSF 4/star-pixel, Normal term 2/pixel
-    fp32_per_eval = 12 * D * P + 7 * P
-    mh_evals = live_total * N * (iters + 2)
+    star_pixels = (2 * D + 2 * iters) * P
+    pixel_terms = (iters + 2) * P
+    mufu_per_particle = 4 * star_pixels + 2 * pixel_terms
+    fp32_per_particle = 12 * star_pixels + 7 * pixel_terms
+    # what the kernel issues: separable Gaussians (2*(8+8) ex2 per star) + 2 MUFU per star-pixel for the wing +
+    # 1 for the star weight; pixel pairs share one rcp and one lg2 (1 per pixel); ~45 in the proposal step
+    exec_mufu_per_particle = (2 * D + 2 * iters) * (2 * 16 + 2 * P + 1) + pixel_terms + 45 * iters
+    live_particles = live_total * N
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -340,24 +349,53 @@ def run_own(a):
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     sfu_peak = 148 * 16 * sm_max * 1e6 / 1e12          # TOP/s (MUFU results per second)
     fp32_peak = 148 * 128 * sm_max * 1e6 / 1e12        # T instr/s (FMA = 1 instr)
-    achieved = mh_evals * mufu_per_eval / (mh_ms * 1e-3) / 1e12
-    # MUFU the kernel actually issues per proposal: 2 stars x (2*(8+8) separable + 2*64 wing + 1) + 64 pixel terms
-    exec_mufu = (mh_evals - live_total * N * 2) * (2 * (2 * 16 + 2 * P + 1) + P) + live_total * N * 2 * (D * (2 * 16 + 2 * P + 1) + P)
-    bytes_per_launch_particle = 2 * (12 * D) + 4 + 4 + 4   # read+write catalog, counts, loglik out, tile share
-    hbm_gbs = live_total * N * bytes_per_launch_particle / (mh_ms * 1e-3) / 1e9
+    achieved = live_particles * mufu_per_particle / (mh_ms * 1e-3) / 1e12
+    bytes_per_launch_particle = 2 * (12 * D) + 4 + 4   # read + write catalog, count, loglik out
+    hbm_gbs = live_particles * bytes_per_launch_particle / (mh_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per particle-launch from the committed ncu --set full capture of this kernel
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_mh_kernel.json")))
+        traffic = prof["dram_bytes_per_particle"] * live_particles / max(1, n_launch)
+    except Exception:
+        pass
     roofline = {"kernel": "mh_kernel<M71,8,8,TPP=1> (smcdet_mh_mutate)", "bound": "sfu",
                 "achieved": achieved, "peak": sfu_peak, "unit": "TOP/s (MUFU)", "frac": achieved / sfu_peak,
                 "peak_source": f"derived: 148 SMs x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); "
                                "the path is SFU/FP32-bound, not HBM- or tensor-bound (SURVEY.md 8d)",
-                "definition": "ALGORITHMIC MUFU ops of the reference formula (4 per star-pixel + 2 per pixel, dense over "
-                              "D stars) x evals / CUDA-event time of the launches; the kernel issues fewer (separable "
-                              "Gaussians, incremental rate update), see executed_frac",
-                "executed_frac": exec_mufu / (mh_ms * 1e-3) / 1e12 / sfu_peak,
-                "fp32_achieved_tinstr": mh_evals * fp32_per_eval / (mh_ms * 1e-3) / 1e12, "fp32_peak_tinstr": fp32_peak,
+                "definition": "algorithmic MUFU of the units a launch processes (SURVEY 8d: 4 per (star,pixel) PSF "
+                              "evaluation, 2 per pixel term; 2 full renders + num_iters two-star sweeps per particle) / "
+                              "CUDA-event time of the launches.  It can exceed 1 because the kernel evaluates the two "
+                              "Gaussian PSF terms separably (about 2.5 MUFU per star-pixel issued): executed_frac is "
+                              "the MUFU actually issued / peak (ncu sm__inst_executed_pipe_xu agrees, profiles/)",
+                "executed_frac": live_particles * exec_mufu_per_particle / (mh_ms * 1e-3) / 1e12 / sfu_peak,
+                "fp32_achieved_tinstr": live_particles * fp32_per_particle / (mh_ms * 1e-3) / 1e12,
+                "fp32_peak_tinstr": fp32_peak,
                 "launches": n_launch, "avg_launch_ms": mh_ms / max(1, n_launch),
-                "share_of_step": mh_ms / elapsed_ms, "traffic": None,
+                "share_of_step": mh_ms / elapsed_ms, "traffic": traffic,
+                "algorithmic_bytes_per_launch": live_particles * bytes_per_launch_particle / max(1, n_launch),
                 "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "frac": hbm_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}}
+
+    # ---- the standalone likelihood kernel on the same field (dense: D stars x P pixels per evaluation)
+    counts0, locs0, fluxes0 = prior._sample_grid(T, 1, None, True, N, seed=7)
+    for _ in range(3):
+        model.loglikelihood(tiles_dev, locs0, fluxes0)
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for x0, x1 in evs:
+        x0.record(torch.cuda.current_stream(dev))
+        model.loglikelihood(tiles_dev, locs0, fluxes0)
+        x1.record(torch.cuda.current_stream(dev))
+    torch.cuda.synchronize(dev)
+    ll_ms = sorted(x0.elapsed_time(x1) for x0, x1 in evs)[len(evs) // 2]
+    ll_rate = T * N / (ll_ms * 1e-3)
+    roofline_loglik = {"kernel": "loglik_kernel<M71,8,8,TPP=1> (smcdet_loglik)", "bound": "sfu",
+                       "evals_per_s": ll_rate, "launch_ms": ll_ms,
+                       "achieved": ll_rate * (4 * D * P + 2 * P) / 1e12, "peak": sfu_peak, "unit": "TOP/s (MUFU)",
+                       "frac": ll_rate * (4 * D * P + 2 * P) / 1e12 / sfu_peak,
+                       "executed_frac": ll_rate * (D * (2 * 16 + 2 * P + 1) + P) / 1e12 / sfu_peak,
+                       "hbm_gbs": ll_rate * (12 * D + 8) / 1e9}
+    del counts0, locs0, fluxes0
 
     # ---- end to end through the public API: pinned host tiles -> H2D -> run -> results D2H into pinned buffers.
     #      Per-tile summaries are all-gathered to every rank; each rank reads back its own posterior catalogs.
@@ -418,6 +456,7 @@ def run_own(a):
                         "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": e2e_ms / a.steps,
                         "tiles_per_sec": a.gpus * T * a.steps / (e2e_ms * 1e-3)},
                 "gpu_launches": launches, "kernel_calls": dict(lib.calls), "roofline": roofline,
+                "roofline_loglik": roofline_loglik,
                 "cpu_baseline": cpu_base, "tiles_per_sec": tiles_per_sec, "smc_iters_per_step": iters_smc,
                 "mean_smc_iters_per_tile": live_total / (T * a.steps)}
         print(json.dumps(line))

@@ -463,6 +463,89 @@ CASES = dict(loglik=case_loglik, prior_sample=case_prior_sample, truncnorm=case_
              temper=case_temper, resample=case_resample, prune=case_prune, smc_stages=case_smc_stages,
              smc_stats=case_smc_stats)
 
+
+
+def case_exact_d1():
+    """A one-star problem whose posterior can be integrated numerically: exact log evidence and posterior
+    moments from a fine 3-D grid of the oracle's float64 log-likelihood, plus what unmodified reference runs
+    (own RNG, several seeds) estimate.  End-to-end acceptance test for the whole sampler."""
+    from scipy.optimize import minimize
+
+    from oracle import api as O
+
+    tile, pad = 8, 4
+    im, pr, meta = m71_objects(tile, 1, pad)
+    torch.manual_seed(71)
+    true_loc = torch.tensor([[[[[3.3, 4.6]]]]])
+    true_flux = torch.tensor([[[[20.0]]]])
+    image = im.sample(true_loc, true_flux)[0, 0, :, :, 0].contiguous()
+    om = O.m71_model(M71["psf_radius"], M71["psf_params"], M71["background"], M71["adu_per_nmgy"], M71["noise_additive"],
+                     M71["noise_multiplicative"], dtype=np.float64)
+    op = O.m71_prior(1, 1, M71_PRIOR["counts_rate"], tile, tile, M71_PRIOR["flux_alpha"], M71_PRIOR["flux_lower"],
+                     M71_PRIOR["flux_upper"], pad=pad)
+    tiles = image.numpy()[None].astype(np.float64)
+
+    def logpost(theta):  # theta [n,3] -> log prior + log lik (float64 oracle)
+        theta = np.atleast_2d(theta)
+        locs = theta[None, :, None, :2]
+        fl = theta[None, :, None, 2]
+        ll = O.loglik(om, tiles, locs, fl, dtype=np.float64)[0]
+        lp = O.prior_logprob(op, np.ones((1, theta.shape[0])), locs, fl, dtype=np.float64)[0]
+        return ll + lp
+
+    res = minimize(lambda th: -logpost(th)[0], np.array([3.3, 4.6, 20.0]), method="Nelder-Mead",
+                   options=dict(xatol=1e-6, fatol=1e-9, maxiter=4000))
+    mode = res.x
+    # numerical Hessian -> box of +-9 posterior sd
+    h = np.array([1e-3, 1e-3, 1e-2])
+    H = np.zeros((3, 3))
+    f0 = logpost(mode)[0]
+    for i in range(3):
+        for j in range(3):
+            e_i, e_j = np.eye(3)[i] * h[i], np.eye(3)[j] * h[j]
+            H[i, j] = (logpost(mode + e_i + e_j)[0] - logpost(mode + e_i - e_j)[0] - logpost(mode - e_i + e_j)[0]
+                       + logpost(mode - e_i - e_j)[0]) / (4 * h[i] * h[j])
+    sd = np.sqrt(np.diag(np.linalg.inv(-H)))
+    G = 161
+    axes = [np.linspace(mode[i] - 9 * sd[i], mode[i] + 9 * sd[i], G) for i in range(3)]
+    axes[2] = np.clip(axes[2], M71_PRIOR["flux_lower"] * 1.0000001, M71_PRIOR["flux_upper"])
+    grid = np.stack(np.meshgrid(*axes, indexing="ij"), -1).reshape(-1, 3)
+    lpv = np.concatenate([logpost(grid[i:i + 200000]) for i in range(0, grid.shape[0], 200000)])
+    cell = np.prod([a[1] - a[0] for a in axes])
+    mx = lpv.max()
+    w = np.exp(lpv - mx)
+    logz = mx + np.log(w.sum() * cell)
+    wn = w / w.sum()
+    mean = (wn[:, None] * grid).sum(0)
+    var = (wn[:, None] * (grid - mean) ** 2).sum(0)
+    edge = wn.reshape(G, G, G)
+    edge_mass = edge[0].sum() + edge[-1].sum() + edge[:, 0].sum() + edge[:, -1].sum() + edge[:, :, 0].sum() + edge[:, :, -1].sum()
+    print("mode", mode, "laplace sd", sd, "logZ", logz, "mean", mean, "sd", np.sqrt(var), "edge mass", edge_mass)
+
+    rows = []
+    for seed in range(5):
+        torch.manual_seed(2000 + seed)
+        mh = SingleComponentMH(25, 0.1, 2.5, pr.flux_lower, pr.flux_upper)
+        s = SMCsampler(image, tile, pr, im, mh, 2000, 0.5, "multinomial", M71_DETECTION, 200, print_every=1000)
+        s.run()
+        l = s.locs[0, 0, :, 0]
+        f = s.fluxes[0, 0, :, 0]
+        rows.append([float(s.log_normalizing_constant), float(l[:, 0].mean()), float(l[:, 1].mean()), float(f.mean()),
+                     float(l[:, 0].std()), float(l[:, 1].std()), float(f.std()), float(s.iter)])
+        print("reference seed", seed, rows[-1])
+    meta.update(N_ref=2000, mh_iters_ref=25, true_loc=[3.3, 4.6], true_flux=20.0, flux_threshold=M71_DETECTION,
+                columns=["logZ", "mean_l0", "mean_l1", "mean_f", "sd_l0", "sd_l1", "sd_f", "smc_iters"])
+    # the sampler's normalising constant is the evidence CONDITIONAL on the count (particles are drawn from the
+    # location/flux prior, weights carry the likelihood only), so remove the count prior's log-pmf
+    rate = M71_PRIOR["counts_rate"] * (tile + 2 * pad) ** 2
+    count_lp = float(np.log(rate) - rate)
+    save("exact_d1", meta, image=image, exact_logz=np.array(logz), exact_logz_given_count=np.array(logz - count_lp), exact_mean=mean, exact_sd=np.sqrt(var),
+         edge_mass=np.array(edge_mass), reference_runs=np.array(rows))
+
+
+CASES["exact_d1"] = case_exact_d1
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = sys.argv[1:] or list(CASES)

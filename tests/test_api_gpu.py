@@ -451,3 +451,33 @@ def test_large_particle_count_one_tile():
                    s.fluxes[0, :, sub].cpu().numpy())
     assert rel_err(s.loglik[0, :, sub].cpu().numpy(), ref) < RTOL
     assert abs(float(s.weights.sum()) - 1) < 1e-3
+
+
+def test_end_to_end_against_exact_posterior():
+    """A one-star problem whose posterior was integrated numerically on a fine grid of the float64 oracle
+    (oracle/gen_golden.py: exact_d1).  The sampler, running on its own Philox draws, must reproduce the exact
+    log evidence and posterior moments -- as the unmodified reference does (its runs are in the fixture)."""
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("exact_d1")
+    meta = dict(g.meta, fluxes_min=g.meta["prior_params"]["flux_lower"], fluxes_max=g.meta["prior_params"]["flux_upper"],
+                locs_stdev=0.1, fluxes_stdev=2.5)
+    exact_logz, mean, sd = float(g["exact_logz_given_count"]), g["exact_mean"], g["exact_sd"]
+    ref = g["reference_runs"]
+    # the reference itself is consistent with the exact answer
+    assert abs(ref[:, 0].mean() - exact_logz) < 0.5 and np.all(np.abs(ref[:, 1:4].mean(0) - mean) < 0.2 * sd)
+    logz, means, sds = [], [], []
+    for method, freeze, seed in [("multinomial", False, 0), ("systematic", True, 1), ("multinomial", True, 2)]:
+        torch.manual_seed(seed)
+        model, prior, mh = build_objects(meta, iters=25)
+        s = SMCsampler(cu(g["image"]), 8, prior, model, mh, 20000, 0.5, method, meta["flux_threshold"], 200,
+                       freeze_finished=freeze, verbose=False)
+        s.run()
+        l, f = s.locs[0, 0, :, 0], s.fluxes[0, 0, :, 0]
+        logz.append(float(s.log_normalizing_constant))
+        means.append([float(l[:, 0].mean()), float(l[:, 1].mean()), float(f.mean())])
+        sds.append([float(l[:, 0].std()), float(l[:, 1].std()), float(f.std())])
+    logz, means, sds = np.array(logz), np.array(means), np.array(sds)
+    assert np.all(np.abs(logz - exact_logz) < 0.35), (logz, exact_logz)
+    assert np.all(np.abs(means - mean) < 0.1 * sd), (means, mean)
+    assert np.all(np.abs(sds / sd - 1) < 0.1), (sds, sd)

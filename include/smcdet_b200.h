@@ -105,6 +105,8 @@ typedef struct smcdet_mh_trace {
     float *log_alpha;   /* [iters,T,N] log acceptance ratio before the clamp */
     float *target_prop; /* [iters,T,N] log target of the proposal (log_num_target, kernel.py:64-70) */
     int8_t *accept;     /* [iters,T,N] */
+    float *chain_locs;   /* [T,N,iters,D,2] catalog after every sweep: the chain MHsampler keeps      */
+    float *chain_fluxes; /* [T,N,iters,D]   (smcdet/sampler.py:516-523); meant for N = 1               */
 } smcdet_mh_trace;
 
 int smcdet_version(void);

@@ -546,6 +546,45 @@ def case_exact_d1():
 CASES["exact_d1"] = case_exact_d1
 
 
+def case_mcmc():
+    """MHsampler (sampler.py:301-576): one long single-site MH chain per tile, every draw on tape."""
+    from smcdet.sampler import MHsampler
+
+    torch.manual_seed(81)
+    tile, pad, D, nside, total, burn, thin = 8, 4, 5, 2, 41, 4, 3
+    im, pr, meta = m71_objects(tile, D, pad)
+    tiles = synth_tiles(im, 3, nside, tile, pad, "m71")
+    image = tiles.permute(0, 2, 1, 3).reshape(nside * tile, nside * tile).contiguous()
+    u_l, u_f = REAL_RAND(nside, nside, 1, D, 2), REAL_RAND(nside, nside, 1, D)
+    tape = DrawTape()
+    tape.push_rand(u_l)
+    tape.push_rand(u_f)
+    iters = total - 1
+    comp = torch.randint(0, D, (iters, nside, nside, 1))
+    ulf = REAL_RAND(iters, nside, nside, 1, D, 2)
+    uff = REAL_RAND(iters, nside, nside, 1, D)
+    ua = REAL_RAND(iters, nside, nside)
+    with tape.active():
+        s = MHsampler(image, tile, pr, im, 0.1, 2.5, M71_DETECTION, total, burn, keep_every_k=thin, print_every=10**9)
+        init_locs, init_fluxes = s.locs[..., 0, :, :].clone(), s.fluxes[..., 0, :].clone()
+        for k in range(iters):
+            tape.push_multinomial(comp[k].reshape(-1, 1))
+            tape.push_rand(ulf[k])
+            tape.push_rand(uff[k])
+            tape.push_rand(ua[k])
+        s.run()
+    ci = comp.unsqueeze(-1)
+    meta.update(nside=nside, total=total, burnin=burn, keep_every_k=thin, locs_stdev=0.1, fluxes_stdev=2.5,
+                fluxes_min=float(pr.flux_lower), fluxes_max=float(pr.flux_upper), flux_threshold=M71_DETECTION)
+    save("mcmc_m71", meta, image=image, init_u_locs=u_l, init_u_fluxes=u_f, init_locs=init_locs, init_fluxes=init_fluxes,
+         comp=comp.to(torch.int32), u_loc=torch.gather(ulf, 4, ci.unsqueeze(-1).expand(-1, -1, -1, -1, 1, 2)).squeeze(4),
+         u_flux=torch.gather(uff, 4, ci).squeeze(4), u_acc=ua, accept=s.accept, locs=s.locs, fluxes=s.fluxes,
+         counts=s.counts, pruned_counts=s.pruned_counts, pruned_locs=s.pruned_locs, pruned_fluxes=s.pruned_fluxes)
+
+
+CASES["mcmc"] = case_mcmc
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = sys.argv[1:] or list(CASES)

@@ -52,7 +52,8 @@ class DrawTape(C.Structure):
 
 
 class MHTrace(C.Structure):
-    _fields_ = [("log_alpha", C.c_void_p), ("target_prop", C.c_void_p), ("accept", C.c_void_p)]
+    _fields_ = [("log_alpha", C.c_void_p), ("target_prop", C.c_void_p), ("accept", C.c_void_p),
+                ("chain_locs", C.c_void_p), ("chain_fluxes", C.c_void_p)]
 
 
 _P = C.c_void_p

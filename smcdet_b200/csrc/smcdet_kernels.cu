@@ -581,6 +581,8 @@ struct MHArgs {
     float* tr_log_alpha;
     float* tr_target_prop;
     int8_t* tr_accept;
+    float* tr_chain_locs;
+    float* tr_chain_fluxes;
     uint64_t seed, offset;
     const int64_t* tile_ids;
     const int32_t* active;
@@ -775,6 +777,14 @@ __global__ void __launch_bounds__(kBT, ((H / TPP) * W >= 64) ? SMC_MH_MINB : 4) 
             if (a.tr_log_alpha) a.tr_log_alpha[e] = log_alpha;
             if (a.tr_target_prop) a.tr_target_prop[e] = target_p;
             if (a.tr_accept) a.tr_accept[e] = (int8_t)last_acc;
+            if (a.tr_chain_locs != nullptr) {  // the chain of MHsampler (sampler.py:516-523)
+                const size_t row = (pn * (size_t)a.mh.num_iters + (size_t)it) * D;
+                for (int d = 0; d < D; ++d) {
+                    a.tr_chain_locs[(row + d) * 2] = my_star[(d * 3 + 0) * PB];
+                    a.tr_chain_locs[(row + d) * 2 + 1] = my_star[(d * 3 + 1) * PB];
+                    a.tr_chain_fluxes[row + d] = my_star[(d * 3 + 2) * PB];
+                }
+            }
         }
     }
     if (a.loglik_out != nullptr && valid && sub == 0) a.loglik_out[pn] = ll;
@@ -1059,7 +1069,8 @@ int smcdet_mh_mutate(const smcdet_model_params* model, const smcdet_prior_params
     a.tiles = tiles; a.counts = counts; a.locs = locs; a.fluxes = fluxes; a.tau = tau;
     a.loglik_out = loglik_out; a.acc_count = acc_rate;
     if (tape) { a.tape_comp = tape->comp; a.tape_u_loc = tape->u_loc; a.tape_u_flux = tape->u_flux; a.tape_u_acc = tape->u_acc; }
-    if (trace) { a.tr_log_alpha = trace->log_alpha; a.tr_target_prop = trace->target_prop; a.tr_accept = trace->accept; }
+    if (trace) { a.tr_log_alpha = trace->log_alpha; a.tr_target_prop = trace->target_prop; a.tr_accept = trace->accept;
+                 a.tr_chain_locs = trace->chain_locs; a.tr_chain_fluxes = trace->chain_fluxes; }
     a.seed = seed; a.offset = offset; a.tile_ids = tile_ids; a.active = active; a.status = status;
     a.T = T; a.N = N; a.D = D;
     SMC_LAUNCH(zero_active_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, T);

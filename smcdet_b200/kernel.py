@@ -54,13 +54,14 @@ class SingleComponentMH(object):
         return prior, model
 
     def run(self, data, counts, locs, fluxes, temperature, log_target, *, tape=None, trace=False, seed=None,
-            offset=0, tile_ids=None, active=None, inplace=False):
+            offset=0, tile_ids=None, active=None, inplace=False, chain=False):
         """Returns [locs, fluxes, acceptance rate of the last iteration [numH, numW]] (reference
         kernel.py:26-130).  Keyword-only extras (not in the reference):
           tape   dict(comp[iters,numH,numW,n] int32, u_loc[...,2], u_flux, u_acc) of injected draws
           trace  keep per-iteration log_alpha / target_prop / accept in ``self.last_trace``
           seed, offset, tile_ids   Philox stream selection when no tape is given
           active [numH, numW] int32 mask of tiles to mutate; inplace  update locs/fluxes in place
+          chain  also keep the catalog after every sweep in ``self.last_trace`` (what MHsampler records)
         """
         prior, model = self._resolve_target(log_target)
         numH, numW, n, d, _ = locs.shape
@@ -93,13 +94,21 @@ class SingleComponentMH(object):
             tp = A.DrawTape(comp.data_ptr(), ul.data_ptr(), uf.data_ptr(), ua.data_ptr())
         tr = None
         self.last_trace = None
-        if trace:
+        if trace or chain:
             la = torch.empty(iters, T, n, device=dev, dtype=torch.float32)
             tg = torch.empty(iters, T, n, device=dev, dtype=torch.float32)
             ac = torch.empty(iters, T, n, device=dev, dtype=torch.int8)
-            tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr())
+            cl = cf_ = None
+            if chain:
+                cl = torch.empty(T, n, iters, d, 2, device=dev, dtype=torch.float32)
+                cf_ = torch.empty(T, n, iters, d, device=dev, dtype=torch.float32)
+            tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr(), cl.data_ptr() if chain else None,
+                           cf_.data_ptr() if chain else None)
             self.last_trace = dict(log_alpha=la.view(iters, numH, numW, n), target_prop=tg.view(iters, numH, numW, n),
                                    accept=ac.view(iters, numH, numW, n))
+            if chain:
+                self.last_trace.update(chain_locs=cl.view(numH, numW, n, iters, d, 2),
+                                       chain_fluxes=cf_.view(numH, numW, n, iters, d))
         act = None if active is None else active.to(device=dev, dtype=torch.int32).reshape(T).contiguous()
         tids = None if tile_ids is None else tile_ids.to(device=dev, dtype=torch.int64).reshape(T).contiguous()
 

@@ -350,8 +350,100 @@ class SMCsampler(object):
 
 
 class MHsampler(object):
-    """Reference sampler.py:301-576: a single long MH chain per tile.  Sequential by construction and
-    outside the data-parallel hot path."""
+    """Single-site random-walk MH chain per tile with the reference's interface (smcdet/sampler.py:301-576).
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("MHsampler is outside the B200 hot path (SURVEY.md section 2, item 7)")
+    The chain is the same kernel step as ``SingleComponentMH`` at temperature 1, so the whole run is ONE
+    launch of ``smcdet_mh_mutate`` with one particle per tile, ``num_samples_total - 1`` sweeps and the
+    chain-recording trace; a tile's sweeps are sequential by nature, tiles run in parallel."""
+
+    def __init__(self, image, tile_dim, Prior, ImageModel, locs_stdev, fluxes_stdev, flux_detection_threshold,
+                 num_samples_total, num_samples_burnin, keep_every_k: int = 1, print_every: int = 1000, *, tape=None):
+        from .kernel import SingleComponentMH
+
+        dev = image.device if (isinstance(image, torch.Tensor) and image.is_cuda) else L.device()
+        self._device = dev
+        self.image = image
+        self.image_dim = image.shape[0]
+        self.tile_dim = tile_dim
+        self.num_tiles_per_side = self.image_dim // self.tile_dim
+        self.tiled_image = L.f32(image, dev).unfold(0, tile_dim, tile_dim).unfold(1, tile_dim, tile_dim)
+
+        self.Prior = Prior
+        self.ImageModel = ImageModel
+        self.locs_stdev = torch.tensor(locs_stdev)
+        self.locs_min = Prior.loc_prior.low
+        self.locs_max = Prior.loc_prior.high
+        self.fluxes_stdev = torch.tensor(fluxes_stdev)
+        self.fluxes_min = torch.tensor(Prior.flux_lower)
+        self.fluxes_max = torch.tensor(Prior.flux_upper)
+        self.flux_detection_threshold = flux_detection_threshold
+
+        self.num_samples_total = num_samples_total
+        self.burn_thin_idx = torch.arange(num_samples_burnin, num_samples_total, step=keep_every_k, device=dev)
+
+        ns, D = self.num_tiles_per_side, Prior.max_objects
+        self.counts = torch.ones(ns, ns, num_samples_total, device=dev) * D
+        self.locs = torch.zeros(ns, ns, num_samples_total, D, 2, device=dev)
+        self.fluxes = torch.zeros(ns, ns, num_samples_total, D, device=dev)
+        # initial state: one prior draw per tile (reference sampler.py:360-366); ``tape`` injects its uniforms
+        _, l, f = self.Prior._sample_grid(ns, ns, None, True, 1, tape=tape)
+        self.locs[..., 0, :, :] = l[..., 0, :, :]
+        self.fluxes[..., 0, :] = f[..., 0, :]
+        self.accept = torch.zeros(ns, ns, num_samples_total - 1, dtype=torch.int, device=dev)
+
+        self._kernel = SingleComponentMH(num_samples_total - 1, float(locs_stdev), float(fluxes_stdev),
+                                         float(Prior.flux_lower), float(Prior.flux_upper))
+        self._kernel.locs_min, self._kernel.locs_max = self.locs_min, self.locs_max
+        self.print_every = print_every
+        self.has_run = False
+
+    def log_target(self, data, counts, locs, fluxes, temperature=None):
+        """log prior + log-likelihood (reference sampler.py:392-396; no tempering)."""
+        return self.Prior.log_prob(counts, locs, fluxes) + self.ImageModel.loglikelihood(data, locs, fluxes)
+
+    def prune(self, locs, fluxes):
+        return SMCsampler.prune(self, locs, fluxes)
+
+    def run(self, *, tape=None):
+        """reference sampler.py:419-533.  ``tape`` injects the draws (as for SingleComponentMH.run)."""
+        ns = self.num_tiles_per_side
+        one = torch.ones(ns, ns, device=self._device)
+        self._kernel.run(self.tiled_image, self.counts[..., :1], self.locs[..., 0, :, :].unsqueeze(2),
+                         self.fluxes[..., 0, :].unsqueeze(2), one, self.log_target, tape=tape, chain=True)
+        tr = self._kernel.last_trace
+        self.locs[..., 1:, :, :] = tr["chain_locs"][:, :, 0]
+        self.fluxes[..., 1:, :] = tr["chain_fluxes"][:, :, 0]
+        self.accept = tr["accept"][..., 0].permute(1, 2, 0).to(torch.int)
+        n = self.num_samples_total - 1
+        for k in range(self.print_every, n, self.print_every):
+            mean_acc = self.accept[..., (k - self.print_every):k].float().mean()
+            print(f"iteration {k}, acceptance rate in past {self.print_every} iters = {mean_acc:.2f}\n")
+        # discard burn-in samples and thin the chain
+        self.counts = self.counts[..., self.burn_thin_idx]
+        self.locs = self.locs[..., self.burn_thin_idx, :, :]
+        self.fluxes = self.fluxes[..., self.burn_thin_idx, :]
+        self.pruned_counts, self.pruned_locs, self.pruned_fluxes = self.prune(self.locs, self.fluxes)
+        self._kernel.check_status()
+        self.has_run = True
+
+    def posterior_mean_count(self, counts):
+        return counts.float().mean(-1)
+
+    def posterior_mean_total_flux(self, fluxes):
+        return fluxes.sum(-1).mean()
+
+    @property
+    def posterior_predictive_total_observed_flux(self):
+        return self.ImageModel.sample(self.locs, self.fluxes).sum([-2, -3]).squeeze()
+
+    def summarize(self):
+        if self.has_run is False:
+            raise ValueError("Sampler hasn't been run yet.")
+        values, freq = self.pruned_counts.unique(return_counts=True)
+        print("posterior distribution of number of detectable stars within image boundary:")
+        print(values.cpu())
+        print((freq / self.pruned_counts.shape[-1]).round(decimals=3).cpu(), "\n")
+        print("posterior mean total intrinsic flux (including undetectable and/or in padding) =",
+              f"{self.posterior_mean_total_flux(self.fluxes).item()}\n")
+        print("posterior mean total intrinsic flux of detectable stars within image boundary =",
+              f"{self.posterior_mean_total_flux(self.pruned_fluxes).item()}\n")

@@ -145,7 +145,7 @@ class GpuBackend:
         return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
 
     def mh_mutate(self, model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-                  active=None):
+                  active=None, chain=False):
         t = self.torch
         tiles, counts, locs, fluxes = self._d(tiles), self._d(counts), self._d(locs), self._d(fluxes)
         tau = self._d(np.reshape(tau, -1))
@@ -168,7 +168,10 @@ class GpuBackend:
         if traces:
             la, tg = self._z((iters, T, N), t.float32), self._z((iters, T, N), t.float32)
             ac = self._z((iters, T, N), t.int8)
-            tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr())
+            cl = self._z((T, N, iters, D, 2), t.float32) if chain else None
+            cf = self._z((T, N, iters, D), t.float32) if chain else None
+            tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr(), cl.data_ptr() if chain else None,
+                           cf.data_ptr() if chain else None)
         act = self._d(active, np.int32)
         self._check(self.lib.smcdet_mh_mutate(
             C.byref(model), C.byref(prior), C.byref(mh), self._p(tiles), self._p(counts), self._p(locs), self._p(fluxes),
@@ -177,6 +180,8 @@ class GpuBackend:
             self._stream()))
         if traces:
             out.update(log_alpha=la.cpu().numpy(), target_prop=tg.cpu().numpy(), accept=ac.cpu().numpy())
+            if chain:
+                out.update(chain_locs=cl.cpu().numpy(), chain_fluxes=cf.cpu().numpy())
         out.update(locs=locs.cpu().numpy(), fluxes=fluxes.cpu().numpy(), loglik=ll.cpu().numpy(),
                    acc_rate=acc.cpu().numpy(), status=int(status.item()))
         return out

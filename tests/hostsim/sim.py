@@ -135,7 +135,7 @@ def gather(idx, counts, locs, fluxes):
 
 
 def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-              active=None):
+              active=None, chain=False):
     tiles, counts = _f(tiles), _f(counts)
     locs, fluxes = _f(locs).copy(), _f(fluxes).copy()
     tau = _f(tau).reshape(-1)
@@ -157,8 +157,13 @@ def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, see
     if traces:
         la, tg = np.zeros((iters, T, N), np.float32), np.zeros((iters, T, N), np.float32)
         ac = np.zeros((iters, T, N), np.int8)
-        tr = A.MHTrace(_p(la).value, _p(tg).value, _p(ac).value)
+        cl = np.zeros((T, N, iters, D, 2), np.float32) if chain else None
+        cf = np.zeros((T, N, iters, D), np.float32) if chain else None
+        tr = A.MHTrace(_p(la).value, _p(tg).value, _p(ac).value, _p(cl).value if chain else None,
+                       _p(cf).value if chain else None)
         out.update(log_alpha=la, target_prop=tg, accept=ac)
+        if chain:
+            out.update(chain_locs=cl, chain_fluxes=cf)
     act = np.ascontiguousarray(active, np.int32) if active is not None else None
     check(lib().smcdet_mh_mutate(C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes),
                                  _p(tau), _p(ll), _p(acc), C.byref(tp) if tp is not None else None,

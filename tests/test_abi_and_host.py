@@ -45,7 +45,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_abi.PriorParams) == 4 * 4 + 4 + 4 * 4 + 6 * 4
     assert ctypes.sizeof(_abi.MHParams) == 4 + 4 * 4 + 4 * 4
     assert ctypes.sizeof(_abi.DrawTape) == 4 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(_abi.MHTrace) == 3 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_abi.MHTrace) == 5 * ctypes.sizeof(ctypes.c_void_p)
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu():

@@ -481,3 +481,31 @@ def test_end_to_end_against_exact_posterior():
     assert np.all(np.abs(logz - exact_logz) < 0.35), (logz, exact_logz)
     assert np.all(np.abs(means - mean) < 0.1 * sd), (means, mean)
     assert np.all(np.abs(sds / sd - 1) < 0.1), (sds, sd)
+
+
+def test_mhsampler_class_matches_reference_chain():
+    """MHsampler with the reference's constructor (experiments/m71/run_mcmc.py:109-121 is its HEAD caller)."""
+    from smcdet_b200.sampler import MHsampler
+
+    g = Golden("mcmc_m71")
+    meta = g.meta
+    model, prior, _ = build_objects(meta)
+    s = MHsampler(cu(g["image"]), meta["tile"], prior, model, meta["locs_stdev"], meta["fluxes_stdev"],
+                  meta["flux_threshold"], meta["total"], meta["burnin"], keep_every_k=meta["keep_every_k"],
+                  tape=(cu(g["init_u_locs"]), cu(g["init_u_fluxes"])))
+    with pytest.raises(ValueError):
+        s.summarize()
+    s.run(tape={k: cu(g[k]) for k in ("comp", "u_loc", "u_flux", "u_acc")})
+    assert torch.equal(s.accept.cpu(), torch.from_numpy(g["accept"]))
+    assert s.locs.shape == g["locs"].shape and np.max(np.abs(s.locs.cpu().numpy() - g["locs"])) < 1e-5
+    assert np.max(np.abs(s.fluxes.cpu().numpy() / g["fluxes"] - 1)) < RTOL
+    assert np.array_equal(s.pruned_counts.cpu().numpy(), g["pruned_counts"])
+    assert np.array_equal(s.counts.cpu().numpy(), g["counts"])
+    s.summarize()
+    # a longer chain on its own Philox draws mixes to a sane posterior
+    torch.manual_seed(5)
+    s2 = MHsampler(cu(g["image"]), meta["tile"], prior, model, 0.1, 2.5, meta["flux_threshold"], 4001, 1000, keep_every_k=10,
+                   print_every=100000)
+    s2.run()
+    assert s2.locs.shape == (2, 2, 301, meta["D"], 2) and 0.1 < float(s2.accept.float().mean()) < 0.9
+    assert torch.isfinite(s2.fluxes).all()

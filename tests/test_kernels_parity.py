@@ -335,3 +335,32 @@ def test_active_mask_skips_tiles(backend):
     ref, _ = backend.resample(A.RESAMPLE_MULTINOMIAL, w, u)
     assert np.array_equal(idx[on], ref[on])
     assert np.array_equal(idx[~on], np.tile(np.arange(w.shape[1]), (int((~on).sum()), 1)))
+
+
+def test_mcmc_chain_matches_reference(backend):
+    """MHsampler (sampler.py:301-576) = the same MH sweep at temperature 1 with the whole chain recorded:
+    one launch of smcdet_mh_mutate with N = 1 and the chain trace reproduces the reference's chain, accept
+    flags and thinned / pruned output on the same draw tape."""
+    g = Golden("mcmc_m71")
+    meta = g.meta
+    T, D, total = meta["nside"] ** 2, meta["D"], meta["total"]
+    iters = total - 1
+    t = meta["tile"]
+    tiles = g["image"].reshape(meta["nside"], t, meta["nside"], t).transpose(0, 2, 1, 3).reshape(T, t, t)
+    m, p = abi_model(meta), abi_prior(meta)
+    c0, l0, f0 = backend.prior_sample(p, T, 1, D, g["init_u_locs"].reshape(T, 1, D, 2), g["init_u_fluxes"].reshape(T, 1, D))
+    assert np.max(np.abs(l0 - g["init_locs"].reshape(T, 1, D, 2))) < 1e-5
+    tape = dict(comp=g["comp"], u_loc=g["u_loc"], u_flux=g["u_flux"], u_acc=g["u_acc"])
+    r = backend.mh_mutate(m, p, abi_mh(meta, iters), tiles, np.full((T, 1), float(D), np.float32),
+                          g["init_locs"].reshape(T, 1, D, 2), g["init_fluxes"].reshape(T, 1, D), np.ones(T, np.float32),
+                          tape=tape, chain=True)
+    assert np.array_equal(r["accept"][:, :, 0].T, g["accept"].reshape(T, iters))
+    chain_l = np.concatenate([g["init_locs"].reshape(T, 1, D, 2), r["chain_locs"][:, 0]], 1)      # [T,total,D,2]
+    chain_f = np.concatenate([g["init_fluxes"].reshape(T, 1, D), r["chain_fluxes"][:, 0]], 1)
+    keep = np.arange(meta["burnin"], total, meta["keep_every_k"])
+    assert np.max(np.abs(chain_l[:, keep] - g["locs"].reshape(T, len(keep), D, 2))) < 1e-5
+    assert np.max(np.abs(chain_f[:, keep] / g["fluxes"].reshape(T, len(keep), D) - 1)) < RTOL
+    assert np.array_equal(r["locs"][:, 0], r["chain_locs"][:, 0, -1])
+    pc, pl, pf = backend.prune(chain_l[:, keep], chain_f[:, keep], t, t, meta["flux_threshold"])
+    assert np.array_equal(pc, g["pruned_counts"].reshape(T, len(keep)))
+    assert np.max(np.abs(pl - g["pruned_locs"].reshape(pl.shape))) < 1e-5

@@ -186,6 +186,19 @@ int smcdet_mh_mutate(const smcdet_model_params *model, const smcdet_prior_params
                      const int32_t *active, int32_t *status, int T, int N, int D, int h, int w,
                      void *stream);
 
+/* SingleComponentMALA.run with log_target = SMCsampler.log_target (smcdet/kernel.py:133-275): as
+ * smcdet_mh_mutate, but each sweep proposes from a truncated normal centred at
+ * value + step^2/2 * grad(log target) (the gradient the reference takes with autograd is evaluated
+ * analytically inside the kernel) and the cached target follows torch.where, not the arithmetic
+ * blend.  mh->locs_stdev / fluxes_stdev are the step sizes (locs_step, fluxes_step). */
+int smcdet_mala_mutate(const smcdet_model_params *model, const smcdet_prior_params *prior,
+                       const smcdet_mh_params *mh, const float *tiles, const float *counts,
+                       float *locs, float *fluxes, const float *tau, float *loglik_out,
+                       float *acc_rate, const smcdet_draw_tape *tape, const smcdet_mh_trace *trace,
+                       uint64_t seed, uint64_t offset, const int64_t *tile_ids,
+                       const int32_t *active, int32_t *status, int T, int N, int D, int h, int w,
+                       void *stream);
+
 /* SMCsampler.prune (smcdet/sampler.py:198-219): keep stars strictly inside the tile with
  * flux above the detection threshold, compacted to the front in their original order.
  * counts_out [T,N] int64. */

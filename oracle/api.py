@@ -268,6 +268,29 @@ def mh_run(model, prior, mh, tiles, counts, locs, fluxes, tau, comp, u_loc, u_fl
                 logden=logden, alpha=alpha, accept=accept)
 
 
+def mala_run(model, prior, mh, tiles, counts, locs, fluxes, tau, comp, u_loc, u_flux, u_acc, dtype=np.float32):
+    """SingleComponentMALA.run (smcdet/kernel.py:133-275); ``mh`` carries the step sizes in locs_stdev /
+    fluxes_stdev.  Returns dict(locs, fluxes, acc_rate, alpha, accept, grad)."""
+    tiles, counts = _arr(tiles, dtype), _arr(counts, dtype)
+    locs, fluxes = _arr(locs, dtype).copy(), _arr(fluxes, dtype).copy()
+    tau = _arr(tau, dtype).reshape(-1)
+    T, h, w = tiles.shape
+    _, N, D, _ = locs.shape
+    iters = mh.num_iters
+    comp = _arr(comp, np.int32).reshape(iters, T, N)
+    u_loc = _arr(u_loc, dtype).reshape(iters, T, N, 2)
+    u_flux = _arr(u_flux, dtype).reshape(iters, T, N)
+    u_acc = _arr(u_acc, dtype).reshape(iters, T, N)
+    acc_rate = np.zeros(T, dtype=dtype)
+    alpha = np.zeros((iters, T, N), dtype=dtype)
+    accept = np.zeros((iters, T, N), dtype=np.int8)
+    grad = np.zeros((iters, T, N, 3), dtype=dtype)
+    getattr(lib(), "oracle_mala_run_" + _suffix(dtype))(
+        C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes), _p(tau), T, N, D, h, w,
+        _p(comp), _p(u_loc), _p(u_flux), _p(u_acc), _p(acc_rate), _p(alpha), _p(accept), _p(grad))
+    return dict(locs=locs, fluxes=fluxes, acc_rate=acc_rate, alpha=alpha, accept=accept, grad=grad)
+
+
 def ess_objective(loglik, delta, ess_threshold, dtype=np.float32):
     ll = _arr(loglik, dtype).reshape(-1)
     return float(getattr(lib(), "oracle_ess_objective_" + _suffix(dtype))(_p(ll), ll.size, C.c_double(delta), C.c_double(ess_threshold)))

@@ -585,6 +585,58 @@ def case_mcmc():
 CASES["mcmc"] = case_mcmc
 
 
+def case_mala():
+    """SingleComponentMALA.run (kernel.py:133-275) with every draw on tape, for 1..n iterations, plus the
+    autograd gradient of the log target at the entry state (what its proposals are built from)."""
+    from smcdet.kernel import SingleComponentMALA
+
+    specs = [("mala_m71", "m71", 8, 6, 4, 2, 64, 5, dict(locs_step=0.04, fluxes_step=0.6)),
+             ("mala_gauss", "gauss", 8, 5, 2, 1, 64, 5, dict(locs_step=0.05, fluxes_step=40.0))]
+    for si, (name, model, tile, D, pad, nside, N, iters, kw) in enumerate(specs):
+        torch.manual_seed(400 + si)
+        mk = m71_objects if model == "m71" else basic_objects
+        im, pr, meta = mk(tile, D, pad)
+        tiles = synth_tiles(im, min(D, 4), nside, tile, pad, model)
+        counts, locs, fluxes = pr.sample(num_tiles_per_side=nside, stratify_by_count=True, num_catalogs_per_count=N)
+        fmin, fmax = (pr.flux_lower, pr.flux_upper) if model == "m71" else (pr.flux_scale, 1e6)
+        tau = torch.linspace(0.05, 0.8, nside * nside).reshape(nside, nside)
+        comp = torch.randint(0, D, (iters, nside, nside, N))
+        ulf = REAL_RAND(iters, nside, nside, N, D, 2)
+        uff = REAL_RAND(iters, nside, nside, N, D)
+        ua = REAL_RAND(iters, nside, nside, N)
+        mala = SingleComponentMALA(iters, kw["locs_step"], kw["fluxes_step"], fmin, fmax)
+        mala.locs_min, mala.locs_max = pr.loc_prior.low, pr.loc_prior.high
+        sm = SMCsampler(torch.zeros(tile * nside, tile * nside), tile, pr, im, mala, N, 0.5, "multinomial", 0.0, 10)
+        l0 = locs.clone().requires_grad_(True)
+        f0 = fluxes.clone().requires_grad_(True)
+        lt = sm.log_target(tiles, counts, l0, f0, tau)
+        gl, gf = torch.autograd.grad(lt, [l0, f0], grad_outputs=torch.ones_like(lt))
+        finals_l, finals_f, accs = [], [], []
+        for j in range(1, iters + 1):
+            mala.num_iters = j
+            tape = DrawTape()
+            for it in range(j):
+                tape.push_multinomial(comp[it].reshape(-1, 1))
+                tape.push_rand(ulf[it])
+                tape.push_rand(uff[it])
+                tape.push_rand(ua[it])
+            with tape.active():
+                lo, fo, acc = mala.run(tiles, counts, locs.clone(), fluxes.clone(), tau, sm.log_target)
+            finals_l.append(lo.detach())
+            finals_f.append(fo.detach())
+            accs.append(acc)
+        ci = comp.unsqueeze(-1)
+        meta.update(nside=nside, N=N, iters=iters, fluxes_min=float(fmin), fluxes_max=float(fmax),
+                    locs_stdev=kw["locs_step"], fluxes_stdev=kw["fluxes_step"])
+        save(name, meta, tiles=tiles, counts=counts, locs=locs, fluxes=fluxes, tau=tau, comp=comp.to(torch.int32),
+             u_loc=torch.gather(ulf, 4, ci.unsqueeze(-1).expand(-1, -1, -1, -1, 1, 2)).squeeze(4),
+             u_flux=torch.gather(uff, 4, ci).squeeze(4), u_acc=ua, log_target0=lt.detach(), grad_locs0=gl, grad_fluxes0=gf,
+             locs_after=torch.stack(finals_l), fluxes_after=torch.stack(finals_f), acc_rate=torch.stack(accs))
+
+
+CASES["mala"] = case_mala
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = sys.argv[1:] or list(CASES)

@@ -12,6 +12,7 @@ The reference never passes ``generator=``; its RNG call sites are
                                   ``Multinomial.sample`` at smcdet/kernel.py:44
   * ``Tensor.multinomial``        smcdet/sampler.py:129
   * ``Uniform(...).sample()``     smcdet/kernel.py:115, smcdet/prior.py:59  (-> ``torch.rand``)
+  * ``torch.rand_like``           smcdet/kernel.py:261 (SingleComponentMALA)
 """
 
 import contextlib
@@ -43,6 +44,13 @@ class DrawTape:
         dtype = kw.get("dtype", None)
         return t.clone() if dtype is None else t.to(dtype)
 
+    def _rand_like(self, other, **kw):
+        t = self.rand_queue.pop(0)
+        if tuple(t.shape) != tuple(other.shape):
+            raise RuntimeError(f"tape rand_like shape {tuple(t.shape)} != requested {tuple(other.shape)}")
+        self.log.append(("rand_like", tuple(other.shape)))
+        return t.to(other.dtype)
+
     def _multinomial(self, probs, num_samples, replacement=False, **kw):
         t = self.multinomial_queue.pop(0)
         want = tuple(probs.shape[:-1]) + (num_samples,)
@@ -54,6 +62,7 @@ class DrawTape:
     @contextlib.contextmanager
     def active(self):
         orig_rand = torch.rand
+        orig_rand_like = torch.rand_like
         orig_mn = torch.multinomial
         orig_tmn = torch.Tensor.multinomial
         tape = self
@@ -62,11 +71,13 @@ class DrawTape:
             return tape._multinomial(self_t, num_samples, replacement, **kw)
 
         torch.rand = self._rand
+        torch.rand_like = self._rand_like
         torch.multinomial = self._multinomial
         torch.Tensor.multinomial = tensor_multinomial
         try:
             yield self
         finally:
             torch.rand = orig_rand
+            torch.rand_like = orig_rand_like
             torch.multinomial = orig_mn
             torch.Tensor.multinomial = orig_tmn

@@ -102,6 +102,13 @@ typedef struct {
                                 real *loglik_out /* [T,N] nullable */,                            \
                                 real *trace_lognum, real *trace_logden, real *trace_alpha,        \
                                 int8_t *trace_accept);                                            \
+    /* smcdet/kernel.py:133-275 (SingleComponentMALA); OracleMH.locs_stdev / fluxes_stdev are the steps */ \
+    void oracle_mala_run_##suffix(const OracleModel *m, const OraclePrior *p, const OracleMH *k,  \
+                                  const real *tiles, const real *counts, real *locs, real *fluxes,\
+                                  const real *tau, int T, int N, int D, int h, int w,             \
+                                  const int32_t *comp, const real *u_loc, const real *u_flux,     \
+                                  const real *u_acc, real *acc_rate, real *trace_alpha,           \
+                                  int8_t *trace_accept, real *trace_grad);                        \
     /* smcdet/sampler.py:93-125 */                                                                \
     double oracle_ess_objective_##suffix(const real *loglik, int N, double delta,                 \
                                          double ess_threshold);                                   \

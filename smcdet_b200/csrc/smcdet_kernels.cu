@@ -561,6 +561,24 @@ __device__ __noinline__ float truncnormal_step(float mu, float sigma, float inv_
     return x;
 }
 
+// MALA (kernel.py:170-195, :214-259): the proposal is a truncated normal around mean = value + step^2/2 * gradient,
+// so the Gaussian parts of the forward and reverse densities do not cancel.
+//   truncnormal_propose: draw x ~ TruncNormal(mean, sigma, [lb, ub]) from u; logq = log q(x | mean)
+//   truncnormal_logq   : log q(x | mean)
+__device__ __noinline__ float truncnormal_propose(float mean, float sigma, float inv_sigma_sqrt2, float lb, float ub,
+                                                   float u, bool wide, float& logq) {
+    const TruncNormal q = wide ? truncnormal_make_wide(mean, inv_sigma_sqrt2, lb, ub) : truncnormal_make(mean, sigma, lb, ub);
+    const float x = truncnormal_draw(q, mean, sigma, lb, ub, u);
+    logq = truncnormal_logpdf(q, mean, sigma, x);
+    return x;
+}
+
+__device__ __noinline__ float truncnormal_logq(float mean, float sigma, float inv_sigma_sqrt2, float lb, float ub,
+                                                bool wide, float x) {
+    const TruncNormal q = wide ? truncnormal_make_wide(mean, inv_sigma_sqrt2, lb, ub) : truncnormal_make(mean, sigma, lb, ub);
+    return truncnormal_logpdf(q, mean, sigma, x);
+}
+
 struct MHArgs {
     ModelK m;
     PriorK pk;
@@ -593,8 +611,8 @@ struct MHArgs {
 #ifndef SMC_MH_MINB
 #define SMC_MH_MINB 3
 #endif
-template <int MODEL, int H, int W, int TPP>
-__global__ void __launch_bounds__(kBT, ((H / TPP) * W >= 64) ? SMC_MH_MINB : 4) mh_kernel(const MHArgs a) {
+template <int MODEL, int H, int W, int TPP, bool MALA>
+__global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_MH_MINB : 4)) mh_kernel(const MHArgs a) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
     float* s_tile = smem;
@@ -650,8 +668,10 @@ __global__ void __launch_bounds__(kBT, ((H / TPP) * W >= 64) ? SMC_MH_MINB : 4) 
     const float sl = a.mh.locs_stdev, sf = a.mh.fluxes_stdev;
     const float isl = (1.0f / sl) * kInvSqrt2, isf = (1.0f / sf) * kInvSqrt2;
     // every proposal box of the reference is far wider than 12 sigma; narrower ones take the general path
-    const bool wide_l = fminf(a.mh.locs_max[0] - a.mh.locs_min[0], a.mh.locs_max[1] - a.mh.locs_min[1]) >= 12.0f * sl;
-    const bool wide_f = (a.mh.fluxes_max - a.mh.fluxes_min) >= 12.0f * sf;
+    // (MALA centres its proposals at value + step^2/2 * gradient, which may lie far outside the box, where the
+    // box mass underflows; it always takes the reference's two-erf arithmetic so that regime behaves alike)
+    const bool wide_l = !MALA && fminf(a.mh.locs_max[0] - a.mh.locs_min[0], a.mh.locs_max[1] - a.mh.locs_min[1]) >= 12.0f * sl;
+    const bool wide_f = !MALA && (a.mh.fluxes_max - a.mh.fluxes_min) >= 12.0f * sf;
     Philox4 rc = {{0u, 0u, 0u, 0u}};
     int last_acc = 0;
     float ll = 0.0f, cached = 0.0f;
@@ -693,17 +713,47 @@ __global__ void __launch_bounds__(kBT, ((H / TPP) * W >= 64) ? SMC_MH_MINB : 4) 
 
             // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
             l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
-            float lq0, lq1, lqf;
-            pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
-            pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
-            pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
-            lq = (lq0 + lq1) + lqf;
+            if constexpr (!MALA) {
+                float lq0, lq1, lqf;
+                pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
+                pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
+                pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
+                lq = (lq0 + lq1) + lqf;
+            }
         }
 
         // ---- expected counts: all D stars (full render) or -old star +new star (MH sweep)
 #pragma unroll
         for (int p = 0; p < PPT; ++p) acc[p] = 0.0f;
-        const int ns = full ? D : 2;
+        if constexpr (MALA) {
+            if (!full) {
+                // gradient of the log target wrt star k at the current state (kernel.py:159-167), removing the star
+                // from the rate image in the same pass, then the Langevin proposal (kernel.py:170-195)
+                float sP, s0, s1;
+                const float wgt_old = m.c0 * f;
+                star_grad_accumulate<MODEL, RPT, W, true>(m, l0, l1, -wgt_old, row0, [&](int r, float (&wr)[W]) {
+#pragma unroll
+                    for (int g = 0; g < W / 4; ++g) {
+                        const float4 rt = my_rate[(r * (W / 4) + g) * kBT];
+                        const float4 xv = reinterpret_cast<const float4*>(xs)[r * (W / 4) + g];
+                        wr[4 * g] = pixel_dlogpdf<MODEL>(m, xv.x, rt.x); wr[4 * g + 1] = pixel_dlogpdf<MODEL>(m, xv.y, rt.y);
+                        wr[4 * g + 2] = pixel_dlogpdf<MODEL>(m, xv.z, rt.z); wr[4 * g + 3] = pixel_dlogpdf<MODEL>(m, xv.w, rt.w);
+                    }
+                }, acc, sP, s0, s1);
+                sP = group_sum<TPP>(sP); s0 = group_sum<TPP>(s0); s1 = group_sum<TPP>(s1);
+                const float dpr = ((float)k < count) ? star_prior_dflux(a.pk, f) : 0.0f;
+                const float hl = 0.5f * (sl * sl), hf = 0.5f * (sf * sf);
+                const float qm0 = fmaf(hl, tau * wgt_old * s0, l0), qm1 = fmaf(hl, tau * wgt_old * s1, l1);
+                const float qmf = fmaf(hf, fmaf(tau * m.c0, sP, dpr), f);
+                float q0, q1, qf;
+                pl0 = truncnormal_propose(qm0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, q0);
+                pl1 = truncnormal_propose(qm1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, q1);
+                pf = truncnormal_propose(qmf, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, qf);
+                lq = -((q0 + q1) + qf);  // - log q(proposal | current); the reverse term is added below
+                if (pf != 0.0f) star_accumulate<MODEL, RPT, W>(m, pl0, pl1, m.c0 * pf, row0, acc);
+            }
+        }
+        const int ns = full ? D : (MALA ? 0 : 2);
 #pragma unroll 1
         for (int s = 0; s < ns; ++s) {
             float s0, s1, sw;
@@ -747,6 +797,31 @@ __global__ void __launch_bounds__(kBT, ((H / TPP) * W >= 64) ? SMC_MH_MINB : 4) 
             bad_p = prior_bad - bad_old + bad_new;
         }
         const float target_p = (bad_p ? -INFINITY : count_lp + fin_p) + tau * llp;
+        if constexpr (MALA) {
+            // gradient at the proposal (kernel.py:199-213) and the density of the reverse move (kernel.py:214-240)
+            float sP, s0, s1;
+            const float wgt_new = m.c0 * pf;
+            star_grad_accumulate<MODEL, RPT, W, false>(m, pl0, pl1, 0.0f, row0, [&](int r, float (&wr)[W]) {
+#pragma unroll
+                for (int g = 0; g < W / 4; ++g) {
+                    const float4 rt = my_rate[(r * (W / 4) + g) * kBT];
+                    const float4 xv = reinterpret_cast<const float4*>(xs)[r * (W / 4) + g];
+                    const int p = r * W + 4 * g;
+                    wr[4 * g] = pixel_dlogpdf<MODEL>(m, xv.x, rt.x + acc[p]);
+                    wr[4 * g + 1] = pixel_dlogpdf<MODEL>(m, xv.y, rt.y + acc[p + 1]);
+                    wr[4 * g + 2] = pixel_dlogpdf<MODEL>(m, xv.z, rt.z + acc[p + 2]);
+                    wr[4 * g + 3] = pixel_dlogpdf<MODEL>(m, xv.w, rt.w + acc[p + 3]);
+                }
+            }, acc, sP, s0, s1);
+            sP = group_sum<TPP>(sP); s0 = group_sum<TPP>(s0); s1 = group_sum<TPP>(s1);
+            const float dpr = ((float)k < count) ? star_prior_dflux(a.pk, pf) : 0.0f;
+            const float hl = 0.5f * (sl * sl), hf = 0.5f * (sf * sf);
+            const float rm0 = fmaf(hl, tau * wgt_new * s0, pl0), rm1 = fmaf(hl, tau * wgt_new * s1, pl1);
+            const float rmf = fmaf(hf, fmaf(tau * m.c0, sP, dpr), pf);
+            lq += (truncnormal_logq(rm0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], wide_l, l0) +
+                   truncnormal_logq(rm1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], wide_l, l1)) +
+                  truncnormal_logq(rmf, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, wide_f, f);
+        }
         const float log_alpha = (target_p - cached) + lq;
         float alpha = ex2_fast(log_alpha * kLog2e);
         if (alpha > 1.0f) alpha = 1.0f;  // clamp(max=1) keeps nan
@@ -769,8 +844,12 @@ __global__ void __launch_bounds__(kBT, ((H / TPP) * W >= 64) ? SMC_MH_MINB : 4) 
                 s_star[(k * 3 + 2) * PB + pi] = pf;
             }
         }
-        // arithmetic blend with the bool as in kernel.py:125 (-inf * 0 = nan poisons the cache)
-        cached = target_p * (accept ? 1.0f : 0.0f) + cached * (accept ? 0.0f : 1.0f);
+        if constexpr (MALA) {
+            cached = accept ? target_p : cached;  // torch.where (kernel.py:273)
+        } else {
+            // arithmetic blend with the bool as in kernel.py:125 (-inf * 0 = nan poisons the cache)
+            cached = target_p * (accept ? 1.0f : 0.0f) + cached * (accept ? 0.0f : 1.0f);
+        }
         last_acc = accept ? 1 : 0;
         __syncwarp();
         if (valid && sub == 0) {
@@ -858,12 +937,12 @@ int launch_loglik_t(const ModelK& m, const float* tiles, const float* locs, cons
     return launch_status("loglik_kernel");
 }
 
-template <int MODEL, int H, int TPP>
+template <int MODEL, int H, int TPP, bool MALA>
 int launch_mh_t(MHArgs& a, cudaStream_t st) {
     constexpr int PB = kBT / TPP, PPT = (H / TPP) * H;
     a.blocks_per_tile = (a.N + PB - 1) / PB;
     const size_t smem = sizeof(float) * (2 * H * H + 3 * (size_t)a.D * PB + (size_t)PPT * kBT);
-    auto kern = mh_kernel<MODEL, H, H, TPP>;
+    auto kern = mh_kernel<MODEL, H, H, TPP, MALA>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mh)");
@@ -890,9 +969,15 @@ int dispatch_loglik_tpp(int tpp, const ModelK& m, const float* tiles, const floa
     SMC_DISPATCH_TPP(launch_loglik_t, MODEL, H, tpp, m, tiles, locs, fluxes, out, T, N, D, st)
 }
 
+template <int MODEL, int H, int TPP>
+int launch_mh_plain(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, false>(a, st); }
+template <int MODEL, int H, int TPP>
+int launch_mh_mala(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, true>(a, st); }
+
 template <int MODEL, int H>
-int dispatch_mh_tpp(int tpp, MHArgs& a, cudaStream_t st) {
-    SMC_DISPATCH_TPP(launch_mh_t, MODEL, H, tpp, a, st)
+int dispatch_mh_tpp(int tpp, bool mala, MHArgs& a, cudaStream_t st) {
+    if (mala) { SMC_DISPATCH_TPP(launch_mh_mala, MODEL, H, tpp, a, st) }
+    SMC_DISPATCH_TPP(launch_mh_plain, MODEL, H, tpp, a, st)
 }
 
 template <int MODEL>
@@ -904,10 +989,10 @@ int dispatch_loglik_side(int side, int tpp, const ModelK& m, const float* tiles,
 }
 
 template <int MODEL>
-int dispatch_mh_side(int side, int tpp, MHArgs& a, cudaStream_t st) {
-    if (side == 8) return dispatch_mh_tpp<MODEL, 8>(tpp, a, st);
-    if (side == 16) return dispatch_mh_tpp<MODEL, 16>(tpp, a, st);
-    return dispatch_mh_tpp<MODEL, 32>(tpp, a, st);
+int dispatch_mh_side(int side, int tpp, bool mala, MHArgs& a, cudaStream_t st) {
+    if (side == 8) return dispatch_mh_tpp<MODEL, 8>(tpp, mala, a, st);
+    if (side == 16) return dispatch_mh_tpp<MODEL, 16>(tpp, mala, a, st);
+    return dispatch_mh_tpp<MODEL, 32>(tpp, mala, a, st);
 }
 
 bool model_ok(const smcdet_model_params* p) {
@@ -1043,7 +1128,7 @@ int smcdet_gather(const int64_t* index, const float* counts_in, const float* loc
     return launch_status("gather_kernel");
 }
 
-int smcdet_mh_mutate(const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
+static int mutate_impl(bool mala, const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
                      const float* tiles, const float* counts, float* locs, float* fluxes, const float* tau,
                      float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
                      uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
@@ -1076,11 +1161,29 @@ int smcdet_mh_mutate(const smcdet_model_params* model, const smcdet_prior_params
     SMC_LAUNCH(zero_active_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, T);
     const int tpp = g_force_tpp ? g_force_tpp : choose_tpp(h, (long long)T * N);
     int rc;
-    if (model->model_kind == SMCDET_MODEL_M71_NORMAL) rc = dispatch_mh_side<SMCDET_MODEL_M71_NORMAL>(h, tpp, a, st);
-    else rc = dispatch_mh_side<SMCDET_MODEL_GAUSS_POISSON>(h, tpp, a, st);
+    if (model->model_kind == SMCDET_MODEL_M71_NORMAL) rc = dispatch_mh_side<SMCDET_MODEL_M71_NORMAL>(h, tpp, mala, a, st);
+    else rc = dispatch_mh_side<SMCDET_MODEL_GAUSS_POISSON>(h, tpp, mala, a, st);
     if (rc != 0) return rc;
     SMC_LAUNCH(divide_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, (float)N, T);
     return launch_status("divide_kernel");
+}
+
+int smcdet_mh_mutate(const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
+                     const float* tiles, const float* counts, float* locs, float* fluxes, const float* tau,
+                     float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
+                     uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
+                     int T, int N, int D, int h, int w, void* stream) {
+    return mutate_impl(false, model, prior, mh, tiles, counts, locs, fluxes, tau, loglik_out, acc_rate, tape, trace, seed,
+                       offset, tile_ids, active, status, T, N, D, h, w, stream);
+}
+
+int smcdet_mala_mutate(const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
+                       const float* tiles, const float* counts, float* locs, float* fluxes, const float* tau,
+                       float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
+                       uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
+                       int T, int N, int D, int h, int w, void* stream) {
+    return mutate_impl(true, model, prior, mh, tiles, counts, locs, fluxes, tau, loglik_out, acc_rate, tape, trace, seed,
+                       offset, tile_ids, active, status, T, N, D, h, w, stream);
 }
 
 int smcdet_prune(const float* locs, const float* fluxes, float tile_h, float tile_w, float flux_threshold,

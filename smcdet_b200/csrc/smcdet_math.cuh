@@ -118,6 +118,8 @@ struct ModelK {
     float cn;       // PSF normalisation: M71 1/((1+b+p0) Z); Gaussian 1/(stdev sqrt(2pi))
     float c0;       // flux -> weight: cn * adu_per_nmgy (M71), cn (Gaussian)
     float bg, na, nm, nswitch;
+    float is1, is2, isp;  // 1/sigma1, 1/sigma2, 1/sigmap (M71); is1 = 1/stdev^2 (Gaussian): PSF gradients (MALA)
+    float lp0;            // lg2(p0)
 };
 
 inline ModelK make_model_k(const smcdet_model_params& p) {
@@ -137,6 +139,9 @@ inline ModelK make_model_k(const smcdet_model_params& p) {
         m.c0 = (float)((double)p.adu_per_nmgy / ((1.0 + (double)p.b + (double)p.p0) * (double)p.psf_norm));
         m.na = p.noise_additive;
         m.nm = p.noise_multiplicative;
+        m.is1 = (float)(1.0 / (double)p.sigma1); m.is2 = (float)(1.0 / (double)p.sigma2);
+        m.isp = (float)(1.0 / (double)p.sigmap);
+        m.lp0 = (float)log2((double)p.p0);
     } else {
         double s = (double)p.psf_stdev;
         m.k1 = (float)(1.4426950408889634 / (2.0 * s * s));
@@ -144,6 +149,7 @@ inline ModelK make_model_k(const smcdet_model_params& p) {
         m.cn = (float)(1.0 / (s * 2.5066282746310002));
         m.c0 = m.cn;
         m.na = 0.f; m.nm = 1.f;
+        m.is1 = (float)(1.0 / (s * s)); m.is2 = 0.f; m.isp = 0.f; m.lp0 = 0.f;
     }
     return m;
 }
@@ -286,6 +292,84 @@ SMC_HD float pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gradient pieces for MALA (reference kernel.py:133-275 differentiates log_target with autograd).
+//   pixel_dlogpdf : d log p(x | rate) / d rate of one pixel (images.py:91-102, :169-175)
+//   star_grad_accumulate : for one star, with per-pixel weights w_p = d loglik / d rate_p (w_row(r, w[W])
+//        fills those of the lane's r-th row),
+//        sP = sum_p w_p P_p,  s0 = sum_p w_p Q_p dy_p,  s1 = sum_p w_p Q_p dx_p
+//     where the star's contribution to the rate is wgt * P (P = e1 + b e2 + p0 t^(-beta/2), un-normalised
+//     as in star_accumulate) and dP/dl0 = Q dy, dP/dl1 = Q dx with
+//     Q = e1/s1 + b e2/s2 + (p0/sp) t^(-beta/2 - 1)   (Gaussian model: Q = P / stdev^2).
+//     Optionally accumulates acc_wgt * P into acc (to remove the star from the rate image in the same pass).
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+SMC_HD float pixel_dlogpdf(const ModelK& m, float x, float r) {
+    if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+        const float v = fmaf(m.nm, r, m.na), d = x - r, iv = rcp_fast(v);
+        return fmaf(0.5f * m.nm * iv, fmaf(d, d, -v) * iv, d * iv);
+    }
+    const float ir = rcp_fast(r);
+    if (r > m.nswitch) {
+        const float d = x - r;
+        return fmaf(0.5f * ir, fmaf(d, d, -r) * ir, d * ir);
+    }
+    return fmaf(x, ir, -1.0f);
+}
+
+template <int MODEL, int RPT, int W, bool ACC, class WRow>
+SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_wgt, int row0, WRow w_row,
+                                 float (&acc)[RPT * W], float& sP, float& s0, float& s1) {
+    ColFactors<MODEL, W> c;
+    col_factors<MODEL, W>(m, l1, c);
+    float dxs[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) dxs[j] = ((float)j + 0.5f) - l1;
+    const float lo = floorf(l0) - m.radius, hi = floorf(l0) + m.radius;
+    sP = 0.f; s0 = 0.f; s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const float fi = (float)(row0 + r);
+        const float dy = (fi + 0.5f) - l0;
+        const float d2 = (fi >= lo && fi <= hi) ? dy * dy : INFINITY;
+        const float g1 = ex2_fast(-m.k1 * d2);
+        float rowQ0 = 0.f;  // sum_j w Q over the row (times dy afterwards)
+        float wr[W];        // w_p = d loglik / d rate_p of the row's pixels
+        w_row(r, wr);
+        if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+            const float g2 = m.b * ex2_fast(-m.k2 * d2);
+            const float ay = fmaf(m.cpl, d2, 1.0f);
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const float t = ay + c.bx[j];
+                const float pw = ex2_fast(fmaf(m.hb, lg2_fast(t), m.lp0));
+                const float e1 = g1 * c.e1[j], e2 = g2 * c.e2[j];
+                const float P = (e1 + e2) + pw;
+                const float Q = fmaf(pw * rcp_fast(t), m.isp, fmaf(e2, m.is2, e1 * m.is1));
+                const float wp = wr[j];
+                if (ACC) acc[r * W + j] = fmaf(acc_wgt, P, acc[r * W + j]);
+                sP = fmaf(wp, P, sP);
+                const float wq = wp * Q;
+                rowQ0 += wq;
+                s1 = fmaf(wq, dxs[j], s1);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const float P = g1 * c.e1[j];
+                const float wp = wr[j];
+                if (ACC) acc[r * W + j] = fmaf(acc_wgt, P, acc[r * W + j]);
+                sP = fmaf(wp, P, sP);
+                const float wq = wp * (P * m.is1);
+                rowQ0 += wq;
+                s1 = fmaf(wq, dxs[j], s1);
+            }
+        }
+        // a masked row has dy finite but every Q exactly 0
+        s0 = fmaf(rowQ0, dy, s0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Direct (non-separable) PSF value for the generic kernels (psf / render / arbitrary tile size)
 // ---------------------------------------------------------------------------------------------
 SMC_HD float psf_direct(const ModelK& m, float l0, float l1, int i, int j) {
@@ -333,7 +417,7 @@ SMC_HD TruncNormal truncnormal_make_wide(float mu, float inv_sigma_sqrt2, float 
     const float q = 0.5f - 0.5f * erff(fminf(a, b) * inv_sigma_sqrt2);
     d.cdf_lb = (a < b) ? q : 0.0f;
     d.mass = 1.0f - q;
-    d.log_mass = lg2_fast(d.mass) * kLn2;  // mass in [0.5, 1]: absolute error of lg2.approx <= 2^-22
+    d.log_mass = nan_to_num_f(lg2_fast(d.mass) * kLn2);  // mass in [0.5, 1] for mu inside the box: abs error <= 2^-22
     return d;
 }
 
@@ -344,6 +428,12 @@ SMC_HD float truncnormal_draw(const TruncNormal& d, float mu, float sigma, float
     const float q = clamp_f(pt, lo, hi);
     const float x = mu + sigma * erfinv_f(2.0f * q - 1.0f) * kSqrt2;
     return clamp_f(x, lb, ub);
+}
+
+// log density of x under the truncated normal d with mean mu (distributions.py:50-52)
+SMC_HD float truncnormal_logpdf(const TruncNormal& d, float mu, float sigma, float x) {
+    const float z = x - mu;
+    return -(z * z) / (2.0f * (sigma * sigma)) - logf(sigma) - kLogSqrt2Pi - d.log_mass;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,6 +518,12 @@ SMC_HD float star_prior_term(const PriorK& p, float l0, float l1, float f, int& 
         t = p.flux_a - p.flux_b * (lg2_fast((f == 0.0f) ? p.repl : f) * kLn2);
     }
     return t - p.loc_norm;
+}
+
+// d log prior / d flux of one live star (autograd of prior.py:183-189, :220-226, :152-154)
+SMC_HD float star_prior_dflux(const PriorK& p, float f) {
+    if (p.flux_is_normal) return -(f - p.flux_mean) * (2.0f * p.flux_inv2var);
+    return -p.flux_b / ((f == 0.0f) ? p.repl : f);
 }
 
 template <class StarAt>

@@ -14,6 +14,8 @@ from . import _lib as L
 
 
 class SingleComponentMH(object):
+    _entry = "smcdet_mh_mutate"
+
     def __init__(self, num_iters, locs_stdev, fluxes_stdev, fluxes_min, fluxes_max):
         self.num_iters = num_iters
         self.locs_stdev = float(locs_stdev)
@@ -116,7 +118,7 @@ class SingleComponentMH(object):
         if self.event_log is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(dev))
-        L.check(L.lib().smcdet_mh_mutate(
+        L.check(getattr(L.lib(), self._entry)(
             C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), L.ptr(cf), L.ptr(lf), L.ptr(ff), L.ptr(tau),
             L.ptr(loglik), L.ptr(acc), C.byref(tp) if tp is not None else None, C.byref(tr) if tr is not None else None,
             L.fresh_seed() if seed is None else int(seed), int(offset), L.ptr(tids, torch.int64),
@@ -137,9 +139,16 @@ class SingleComponentMH(object):
                                  "(reference smcdet/distributions.py:51)")
 
 
-class SingleComponentMALA(object):
-    """Reference kernel.py:133-275 (gradient-based proposals).  Out of scope of the B200 hot path
-    (SURVEY.md section 8f, item 3): only the deprecated jsm2024 scripts use it."""
+class SingleComponentMALA(SingleComponentMH):
+    """Single-component Metropolis-adjusted Langevin kernel with the reference's interface (kernel.py:133-275).
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("SingleComponentMALA is not part of the B200 hot path (SURVEY.md 8f)")
+    Each sweep proposes star k from a truncated normal centred at value + step^2/2 * grad log target; the
+    gradient the reference takes with autograd is evaluated analytically inside the fused kernel
+    (``smcdet_mala_mutate``): d loglik / d rate per pixel times the PSF and its location derivatives."""
+
+    _entry = "smcdet_mala_mutate"
+
+    def __init__(self, num_iters, locs_step, fluxes_step, fluxes_min, fluxes_max):
+        super().__init__(num_iters, locs_step, fluxes_step, fluxes_min, fluxes_max)
+        self.locs_step = float(locs_step)
+        self.fluxes_step = float(fluxes_step)

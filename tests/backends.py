@@ -145,7 +145,7 @@ class GpuBackend:
         return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
 
     def mh_mutate(self, model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-                  active=None, chain=False):
+                  active=None, chain=False, mala=False):
         t = self.torch
         tiles, counts, locs, fluxes = self._d(tiles), self._d(counts), self._d(locs), self._d(fluxes)
         tau = self._d(np.reshape(tau, -1))
@@ -173,7 +173,8 @@ class GpuBackend:
             tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr(), cl.data_ptr() if chain else None,
                            cf.data_ptr() if chain else None)
         act = self._d(active, np.int32)
-        self._check(self.lib.smcdet_mh_mutate(
+        fn = self.lib.smcdet_mala_mutate if mala else self.lib.smcdet_mh_mutate
+        self._check(fn(
             C.byref(model), C.byref(prior), C.byref(mh), self._p(tiles), self._p(counts), self._p(locs), self._p(fluxes),
             self._p(tau), self._p(ll), self._p(acc), C.byref(tp) if tp is not None else None,
             C.byref(tr) if tr is not None else None, seed, offset, None, self._p(act), self._p(status), T, N, D, h, w,

@@ -135,7 +135,7 @@ def gather(idx, counts, locs, fluxes):
 
 
 def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-              active=None, chain=False):
+              active=None, chain=False, mala=False):
     tiles, counts = _f(tiles), _f(counts)
     locs, fluxes = _f(locs).copy(), _f(fluxes).copy()
     tau = _f(tau).reshape(-1)
@@ -165,7 +165,8 @@ def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, see
         if chain:
             out.update(chain_locs=cl, chain_fluxes=cf)
     act = np.ascontiguousarray(active, np.int32) if active is not None else None
-    check(lib().smcdet_mh_mutate(C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes),
+    fn = lib().smcdet_mala_mutate if mala else lib().smcdet_mh_mutate
+    check(fn(C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes),
                                  _p(tau), _p(ll), _p(acc), C.byref(tp) if tp is not None else None,
                                  C.byref(tr) if tr is not None else None, seed, offset, None, _p(act), _p(status),
                                  T, N, D, h, w, None))

@@ -509,3 +509,35 @@ def test_mhsampler_class_matches_reference_chain():
     s2.run()
     assert s2.locs.shape == (2, 2, 301, meta["D"], 2) and 0.1 < float(s2.accept.float().mean()) < 0.9
     assert torch.isfinite(s2.fluxes).all()
+
+
+def test_mala_kernel_class_inside_smcsampler():
+    """SingleComponentMALA as the MutationKernel of SMCsampler (the deprecated jsm2024 usage of the reference):
+    tape parity through the class, then a full run on its own draws that reproduces the exact one-star posterior."""
+    from smcdet_b200.kernel import SingleComponentMALA
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("mala_m71")
+    meta = g.meta
+    model, prior, _ = build_objects(meta)
+    mala = SingleComponentMALA(meta["iters"], meta["locs_stdev"], meta["fluxes_stdev"], meta["fluxes_min"], meta["fluxes_max"])
+    ns, t = meta["nside"], meta["tile"]
+    image = cu(g["tiles"]).permute(0, 2, 1, 3).reshape(ns * t, ns * t).contiguous()
+    s = SMCsampler(image, t, prior, model, mala, meta["N"], 0.5, "multinomial", 0.25, 10, verbose=False)
+    tape = {k: cu(g[k]) for k in ("comp", "u_loc", "u_flux", "u_acc")}
+    lo, fo, acc = mala.run(s.tiled_image, cu(g["counts"]), cu(g["locs"]), cu(g["fluxes"]), cu(g["tau"]), s.log_target, tape=tape)
+    same = np.all(np.abs(lo.cpu().numpy() - g["locs_after"][-1]) < 1e-4, axis=(3, 4))
+    assert same.mean() > 0.99 and np.max(np.abs(acc.cpu().numpy() - g["acc_rate"][-1])) <= 1.0 / meta["N"]
+
+    e = Golden("exact_d1")
+    emeta = e.meta
+    model, prior, _ = build_objects(emeta)
+    torch.manual_seed(4)
+    mala = SingleComponentMALA(25, 0.05, 0.5, emeta["prior_params"]["flux_lower"], emeta["prior_params"]["flux_upper"])
+    s = SMCsampler(cu(e["image"]), 8, prior, model, mala, 20000, 0.5, "multinomial", emeta["flux_threshold"], 200, verbose=False)
+    s.run()
+    l, f = s.locs[0, 0, :, 0], s.fluxes[0, 0, :, 0]
+    mean, sd = e["exact_mean"], e["exact_sd"]
+    got = np.array([float(l[:, 0].mean()), float(l[:, 1].mean()), float(f.mean())])
+    assert abs(float(s.log_normalizing_constant) - float(e["exact_logz_given_count"])) < 0.35
+    assert np.all(np.abs(got - mean) < 0.1 * sd)

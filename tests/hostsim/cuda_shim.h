@@ -6,7 +6,7 @@
 // how the index logic, staging, reductions and the Brent loop are checked against the oracle in
 // the CPU-only test tier, before any GPU time is spent.  The product package never loads the
 // library built from this header (smcdet_b200/_lib.py only accepts CUDA tensors and only loads
-// libsmcdet_b200.so); it exists under tests/ and is built by tests/hostsim/build.py.
+// libsmcdet_b200.so); it exists under tests/ and is built on demand by tests/hostsim/sim.py.
 #pragma once
 
 #include <algorithm>
@@ -78,7 +78,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
             const unsigned lanes = std::min(32u, block - w * 32);
             blk.warps[w].bar.reset(new std::barrier<>(lanes));
         }
-        blk.dyn_smem.assign(smem_bytes / sizeof(float) + 16, 0.0f);
+        blk.dyn_smem.assign((smem_bytes + sizeof(float) - 1) / sizeof(float), 0.0f);  // exact size, so a host address sanitizer sees overruns
         std::vector<std::thread> threads;
         threads.reserve(block);
         for (unsigned i = 0; i < block; ++i) {

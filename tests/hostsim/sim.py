@@ -11,7 +11,7 @@ import numpy as np
 from smcdet_b200 import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libsmcdet_hostsim.so")
+_LIB = os.environ.get("SMCDET_HOSTSIM_LIB") or os.path.join(_HERE, "libsmcdet_hostsim.so")
 _SRC = [os.path.join(_HERE, "hostsim_lib.cpp"), os.path.join(_HERE, "cuda_shim.h"),
         os.path.join(_HERE, "..", "..", "smcdet_b200", "csrc", "smcdet_kernels.cu"),
         os.path.join(_HERE, "..", "..", "smcdet_b200", "csrc", "smcdet_math.cuh"),
@@ -19,6 +19,8 @@ _SRC = [os.path.join(_HERE, "hostsim_lib.cpp"), os.path.join(_HERE, "cuda_shim.h
 
 
 def build(force=False):
+    if os.environ.get("SMCDET_HOSTSIM_LIB"):  # e.g. an AddressSanitizer build (tests/hostsim/README.md)
+        return _LIB
     if (not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in _SRC)):
         return _LIB
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

@@ -9,7 +9,6 @@ gather (``smcdet_b200.shard``): per-tile catalogs from all ranks are concatenate
 axis and finished tile by tile.  The tree merge is listed as "next" in SURVEY.md section 8(f).
 """
 
-import ctypes as C
 from copy import deepcopy
 
 import torch

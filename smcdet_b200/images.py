@@ -39,9 +39,6 @@ class ImageModel(object):
         p.normal_switch_rate = 50000.0
         return p
 
-    def _flux_scale(self):
-        return 1.0
-
     @staticmethod
     def _flat(locs, fluxes=None):
         numH, numW, n, d, _ = locs.shape
@@ -120,9 +117,6 @@ class M71ImageModel(ImageModel):
         p.noise_multiplicative = float(self.noise_multiplicative)
         p.normal_switch_rate = 50000.0
         return p
-
-    def _flux_scale(self):
-        return float(self.adu_per_nmgy)
 
     def sample(self, locs, fluxes):
         """Normal image draw with variance noise_additive + noise_multiplicative * rate

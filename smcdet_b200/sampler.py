@@ -11,7 +11,6 @@ every stage is a launch of the CUDA library on the whole [numH, numW] grid of ti
 State attributes keep the reference's names and shapes ([numH, numW, ...]).
 """
 
-import ctypes as C
 
 import torch
 
@@ -45,7 +44,6 @@ class SMCsampler(object):
             self.tiled_image = L.f32(image, dev)
         else:
             raise ValueError("image must be a square 2-D tensor or a [numH, numW, h, w] tensor of tiles")
-        self._tiles = self.tiled_image.contiguous().view(self.numH * self.numW, self.tile_dim, self.tile_dim)
         self._device = dev
 
         self.Prior = Prior

@@ -561,6 +561,38 @@ __device__ __noinline__ float truncnormal_step(float mu, float sigma, float inv_
     return x;
 }
 
+// All three coordinates of a proposal in one out-of-line call, for boxes of at least 12 sigma.  Each stage is
+// written as a loop over the coordinates so that the three independent erf / erfinv / lg2 dependency chains sit
+// in one basic block and are interleaved by the scheduler (ILP 3 instead of 1 in the scalar part of a sweep).
+__device__ __noinline__ float4 truncnormal_step3_wide(float mu0, float mu1, float mu2, float sl, float isl, float sf,
+                                                       float isf, float lb0, float lb1, float lb2, float ub0, float ub1,
+                                                       float ub2, float u0, float u1, float u2) {
+    const float mu[3] = {mu0, mu1, mu2}, sigma[3] = {sl, sl, sf}, isig[3] = {isl, isl, isf};
+    const float lb[3] = {lb0, lb1, lb2}, ub[3] = {ub0, ub1, ub2}, u[3] = {u0, u1, u2};
+    float q[3], cdf_lb[3], mass[3], y[3], x[3], qr[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = mu[c] - lb[c], b = ub[c] - mu[c];
+        q[c] = 0.5f - 0.5f * erff(fminf(a, b) * isig[c]);
+        cdf_lb[c] = (a < b) ? q[c] : 0.0f;
+        mass[c] = 1.0f - q[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float lo = 1e-6f, hi = (float)(1.0 - 1e-6);
+        const float p = clamp_f(u[c], lo, hi);
+        y[c] = 2.0f * clamp_f(cdf_lb[c] + p * mass[c], lo, hi) - 1.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = clamp_f(mu[c] + sigma[c] * erfinv_f(y[c]) * kSqrt2, lb[c], ub[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) qr[c] = 0.5f - 0.5f * erff(fminf(x[c] - lb[c], ub[c] - x[c]) * isig[c]);
+    float lq = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) lq += (lg2_fast(mass[c]) - lg2_fast(1.0f - qr[c])) * kLn2;
+    return make_float4(x[0], x[1], x[2], lq);  // proposal (row, col, flux) and log q(prev|prop) - log q(prop|prev)
+}
+
 // MALA (kernel.py:170-195, :214-259): the proposal is a truncated normal around mean = value + step^2/2 * gradient,
 // so the Gaussian parts of the forward and reverse densities do not cancel.
 //   truncnormal_propose: draw x ~ TruncNormal(mean, sigma, [lb, ub]) from u; logq = log q(x | mean)
@@ -714,11 +746,18 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
             // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
             l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
             if constexpr (!MALA) {
-                float lq0, lq1, lqf;
-                pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
-                pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
-                pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
-                lq = (lq0 + lq1) + lqf;
+                if (wide_l && wide_f) {
+                    const float4 pr = truncnormal_step3_wide(l0, l1, f, sl, isl, sf, isf, a.mh.locs_min[0], a.mh.locs_min[1],
+                                                             a.mh.fluxes_min, a.mh.locs_max[0], a.mh.locs_max[1],
+                                                             a.mh.fluxes_max, u0, u1, uf);
+                    pl0 = pr.x; pl1 = pr.y; pf = pr.z; lq = pr.w;
+                } else {
+                    float lq0, lq1, lqf;
+                    pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
+                    pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
+                    pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
+                    lq = (lq0 + lq1) + lqf;
+                }
             }
         }
 

@@ -53,7 +53,10 @@ int launch_status(const char* what) {
     return 0;
 }
 
-constexpr int kBT = 128;        // threads per block of the particle kernels
+#ifndef SMC_KBT
+#define SMC_KBT 128
+#endif
+constexpr int kBT = SMC_KBT;    // threads per block of the particle kernels
 constexpr int kMaxStars = 64;   // D limit (shared-memory staging)
 
 int g_num_sms = 0;

@@ -19,7 +19,6 @@ and live tile N*(num_iters + 2) (kernel.py:64-70, :89-96; sampler.py:100-102), p
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -163,40 +162,44 @@ def run_reference(a):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU every 200 ms during the timed region, through NVML in
+    this process (a polling `nvidia-smi` child was measured to slow the timed region by several percent)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self._stop_flag = index, [], threading.Event()
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
+            import pynvml as nv
+
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self._stop_flag.is_set():
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                  [k for k, b in bits.items() if reasons & b]))
+                self._stop_flag.wait(0.2)
+        except Exception as exc:  # noqa: BLE001
+            self.error = repr(exc)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
+        self._stop_flag.set()
         self.join(timeout=2)
-        sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                continue
+        sm = [r[0] for r in self.rows]
+        power = [r[2] for r in self.rows]
+        reasons = sorted({x for r in self.rows for x in r[3]})
         busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] if power else sm
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons,
+                "source": "NVML (pynvml) every 200 ms during the timed region", **({"error": self.error} if hasattr(self, "error") else {})}
 
 
 def make_field(a, rank, dev):

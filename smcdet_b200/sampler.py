@@ -135,12 +135,13 @@ class SMCsampler(object):
         act = getattr(self, "_active", None)
         return None if act is None else act.reshape(self._T).to(torch.int32).contiguous()
 
-    def _keep_inactive(self, new, old):
+    def _keep_inactive(self, new, old_name):
+        """``new`` for live tiles, the current value of attribute ``old_name`` for frozen ones."""
         act = getattr(self, "_active", None)
         if act is None:
             return new
         m = act.view(self.numH, self.numW, *([1] * (new.dim() - 2)))
-        return torch.where(m, new, old.to(new.device))
+        return torch.where(m, new, getattr(self, old_name).to(new.device))
 
     def _temper_update(self, do_temper, logz, tau, tau_prev):
         T, n = self._T, self.num_catalogs
@@ -183,9 +184,9 @@ class SMCsampler(object):
         self.tempering_funcalls = calls.view(self.numH, self.numW)
         self.temperature_prev = tau_prev.view(self.numH, self.numW)
         self.temperature = tau.view(self.numH, self.numW)
-        self.weights_log_unnorm = self._keep_inactive(wlog.view(self.numH, self.numW, n), self.weights_log_unnorm)
-        self.weights = self._keep_inactive(weights.view(self.numH, self.numW, n), self.weights)
-        self.ess = self._keep_inactive(ess.view(self.numH, self.numW), self.ess)
+        self.weights_log_unnorm = self._keep_inactive(wlog.view(self.numH, self.numW, n), "weights_log_unnorm")
+        self.weights = self._keep_inactive(weights.view(self.numH, self.numW, n), "weights")
+        self.ess = self._keep_inactive(ess.view(self.numH, self.numW), "ess")
         self.log_normalizing_constant = logz.view(self.numH, self.numW)
 
     def update_weights(self):
@@ -195,9 +196,9 @@ class SMCsampler(object):
         logz = L.f32(self.log_normalizing_constant, self._device).reshape(self._T).clone()
         wlog, weights, ess, _ = self._temper_update(0, logz, tau, tau_prev)
         n = self.num_catalogs
-        self.weights_log_unnorm = self._keep_inactive(wlog.view(self.numH, self.numW, n), self.weights_log_unnorm)
-        self.weights = self._keep_inactive(weights.view(self.numH, self.numW, n), self.weights)
-        self.ess = self._keep_inactive(ess.view(self.numH, self.numW), self.ess)
+        self.weights_log_unnorm = self._keep_inactive(wlog.view(self.numH, self.numW, n), "weights_log_unnorm")
+        self.weights = self._keep_inactive(weights.view(self.numH, self.numW, n), "weights")
+        self.ess = self._keep_inactive(ess.view(self.numH, self.numW), "ess")
         self.log_normalizing_constant = logz.view(self.numH, self.numW)
 
     def resample(self, *, u=None):
@@ -243,7 +244,7 @@ class SMCsampler(object):
         self.locs = lout.view(self.numH, self.numW, n, d, 2)
         self.fluxes = fout.view(self.numH, self.numW, n, d)
         uniform = torch.full((self.numH, self.numW, n), 1.0 / n, device=dev)
-        self.weights = self._keep_inactive(uniform, self.weights)
+        self.weights = self._keep_inactive(uniform, "weights")
         if getattr(self, "_active", None) is None:
             self._loglik_key = None
         else:  # frozen tiles keep their particles, so their cached log-likelihood row stays valid

@@ -59,6 +59,7 @@ def workload_config(a):
                         "(BASELINE.json configs[1]; notebooks/smc.ipynb of the reference)",
             "tiles_per_gpu": a.tiles_per_gpu, "particles_per_tile": a.particles, "stars_per_catalog": a.stars,
             "mh_iters": a.mh_iters, "ess_threshold_prop": 0.5, "resample": "multinomial",
+            "loglik_for_tempering": "from the incrementally updated rate image (default; 7e-7 relative drift measured)",
             "step": "one full SMCsampler.run() to temperature 1 over all tiles of the rank",
             "finished_tiles": "frozen (each tile runs as in the reference's per-tile loop, experiments/m71/run_smc.py:113-124)",
             "parallelism": f"tiles sharded over {a.gpus} GPU(s), no data-path collective; final all_gather of catalogs",
@@ -329,20 +330,20 @@ def run_own(a):
     tiles_per_sec = a.gpus * T * a.steps / (elapsed_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (mh_kernel), timed live with CUDA events per launch.
-    # Units one launch processes, per live particle: 2 full renders (entry state, final refresh) of D stars and
+    # Units one launch processes, per live particle: 1 full render (entry state) of D stars and
     # num_iters sweeps that each evaluate 2 stars (the one removed and the one proposed) on the P pixels, plus
     # P pixel terms per evaluation.  Per-unit figures are SURVEY.md 8(d)'s: 4 MUFU / 12 FP32 instr per
     # (star, pixel) PSF evaluation of the M71 model, 2 MUFU / 7 FP32 instr per Normal pixel term.
     mh_ms = sum(ev0.elapsed_time(ev1) for log in mh_logs for (ev0, ev1, *_r) in log)
     n_launch = sum(len(log) for log in mh_logs)
     P = TILE * TILE
-    star_pixels = (2 * D + 2 * iters) * P
-    pixel_terms = (iters + 2) * P
+    star_pixels = (1 * D + 2 * iters) * P   # entry render + two-star sweeps (no final refresh by default)
+    pixel_terms = (iters + 1) * P
     mufu_per_particle = 4 * star_pixels + 2 * pixel_terms
     fp32_per_particle = 12 * star_pixels + 7 * pixel_terms
     # what the kernel issues: separable Gaussians (2*(8+8) ex2 per star) + 2 MUFU per star-pixel for the wing +
     # 1 for the star weight; pixel pairs share one rcp and one lg2 (1 per pixel); ~45 in the proposal step
-    exec_mufu_per_particle = (2 * D + 2 * iters) * (2 * 16 + 2 * P + 1) + pixel_terms + 45 * iters
+    exec_mufu_per_particle = (1 * D + 2 * iters) * (2 * 16 + 2 * P + 1) + pixel_terms + 45 * iters
     live_particles = live_total * N
     peaks = {}
     try:
@@ -366,7 +367,7 @@ def run_own(a):
                 "peak_source": f"derived: 148 SMs x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); "
                                "the path is SFU/FP32-bound, not HBM- or tensor-bound (SURVEY.md 8d)",
                 "definition": "algorithmic MUFU of the units a launch processes (SURVEY 8d: 4 per (star,pixel) PSF "
-                              "evaluation, 2 per pixel term; 2 full renders + num_iters two-star sweeps per particle) / "
+                              "evaluation, 2 per pixel term; 1 full render + num_iters two-star sweeps per particle) / "
                               "CUDA-event time of the launches.  It can exceed 1 because the kernel evaluates the two "
                               "Gaussian PSF terms separably (about 2.5 MUFU per star-pixel issued): executed_frac is "
                               "the MUFU actually issued / peak (ncu sm__inst_executed_pipe_xu agrees, profiles/)",

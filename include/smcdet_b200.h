@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMCDET_ABI_VERSION 1
+#define SMCDET_ABI_VERSION 2
 
 enum {
     SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
@@ -88,6 +88,9 @@ typedef struct smcdet_mh_params {
     float fluxes_stdev;
     float fluxes_min, fluxes_max;
     float locs_min[2], locs_max[2];
+    int32_t refresh_loglik; /* 1: loglik_out from a fresh full render of the final state (bit-for-bit what
+                               smcdet_loglik returns); 0: from the resident rate image that the sweeps
+                               updated incrementally (rounding drift ~1e-6 relative, one render cheaper) */
 } smcdet_mh_params;
 
 /* Injected draws for smcdet_mh_mutate (parity testing).  Entries are the draws the

@@ -2,7 +2,7 @@
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MODEL_GAUSS_POISSON, MODEL_M71_NORMAL = 0, 1
 COUNT_DISCRETE_UNIFORM, COUNT_POISSON, COUNT_NONE = 0, 1, 2
@@ -44,6 +44,7 @@ class MHParams(C.Structure):
         ("locs_stdev", C.c_float), ("fluxes_stdev", C.c_float),
         ("fluxes_min", C.c_float), ("fluxes_max", C.c_float),
         ("locs_min", C.c_float * 2), ("locs_max", C.c_float * 2),
+        ("refresh_loglik", C.c_int32),
     ]
 
 

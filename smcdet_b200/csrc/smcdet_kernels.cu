@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     //                    (the log_denom_target of kernel.py:88-96)
     //   it = 0..iters-1  one MH sweep: rate' = rate - old star + new star on the lane's pixels
     //   it = iters       fresh full render of the final state -> loglik_out (what sampler.py:100-102 recomputes)
-    const int it_end = a.mh.num_iters + (a.loglik_out != nullptr ? 1 : 0);
+    const int it_end = a.mh.num_iters + ((a.loglik_out != nullptr && a.mh.refresh_loglik) ? 1 : 0);
     for (int it = -1; it < it_end; ++it) {
         const bool full = (it < 0) || (it == a.mh.num_iters);
         int k = 0;

@@ -26,6 +26,10 @@ class SingleComponentMH(object):
         self.fluxes_max = float(fluxes_max)
         self.last_loglik = None  # log-likelihood of the state returned by the last run()
         self.last_trace = None
+        # log-likelihood handed back with the returned state: False (default) = from the rate image the sweeps
+        # updated incrementally (measured drift after 100 sweeps: 7e-7 relative, tests/test_api_gpu.py), True = from a
+        # fresh full render, bit-for-bit what ImageModel.loglikelihood returns (one render per launch dearer)
+        self.refresh_loglik = False
         self.event_log = None  # set to a list to record (start, end, active, n, iters) CUDA events per launch
 
     def _params(self):
@@ -39,6 +43,7 @@ class SingleComponentMH(object):
         hi = torch.as_tensor(self.locs_max).tolist()
         k.locs_min[0], k.locs_min[1] = lo
         k.locs_max[0], k.locs_max[1] = hi
+        k.refresh_loglik = 1 if self.refresh_loglik else 0
         return k
 
     @staticmethod

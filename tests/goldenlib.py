@@ -126,4 +126,5 @@ def abi_mh(meta, iters=None):
     k.fluxes_min, k.fluxes_max = meta["fluxes_min"], meta["fluxes_max"]
     k.locs_min[0] = k.locs_min[1] = -pad
     k.locs_max[0] = k.locs_max[1] = t + pad
+    k.refresh_loglik = 1
     return k

@@ -541,3 +541,30 @@ def test_mala_kernel_class_inside_smcsampler():
     got = np.array([float(l[:, 0].mean()), float(l[:, 1].mean()), float(f.mean())])
     assert abs(float(s.log_normalizing_constant) - float(e["exact_logz_given_count"])) < 0.35
     assert np.all(np.abs(got - mean) < 0.1 * sd)
+
+
+def test_incremental_loglik_drift_is_negligible():
+    """refresh_loglik=False hands tempering the log-likelihood of the rate image that 100 sweeps updated
+    incrementally; it must agree with a fresh render to far better than the 1e-4 budget."""
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("mh_m71")
+    meta = g.meta
+    model, prior, mh = build_objects(meta, iters=100)
+    ns, t = meta["nside"], meta["tile"]
+    image = cu(g["tiles"]).permute(0, 2, 1, 3).reshape(ns * t, ns * t).contiguous()
+    s = SMCsampler(image, t, prior, model, mh, meta["N"], 0.5, "multinomial", 0.25, 10, verbose=False)
+    torch.manual_seed(0)
+    counts, locs, fluxes = prior._sample_grid(ns, ns, None, True, 4096, seed=3)
+    tau = torch.full((ns, ns), 0.7, device=dev())
+    out = {}
+    for refresh in (True, False):
+        mh.refresh_loglik = refresh
+        lo, fo, _ = mh.run(s.tiled_image, counts, locs, fluxes, tau, s.log_target, seed=9)
+        out[refresh] = (lo, fo, mh.last_loglik.clone())
+    assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1])
+    exact = model.loglikelihood(s.tiled_image, out[True][0], out[True][1])
+    assert torch.equal(out[True][2], exact) or rel_err(out[True][2].cpu().numpy(), exact.cpu().numpy()) < 1e-6
+    drift = rel_err(out[False][2].cpu().numpy(), exact.cpu().numpy())
+    print("incremental loglik drift (max relative):", drift)
+    assert drift < 2e-5

@@ -276,14 +276,11 @@ SMC_HD float pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam
             for (int e = 0; e < 4; ++e) {
                 const float r = rr[e], xv = xx[e];
                 const float lg = lg2_fast(r) * kLn2;
-                float term;
-                if (r > m.nswitch) {
-                    const float d = xv - r;
-                    term = fmaf(-0.5f * (d * d), rcp_fast(r), fmaf(-0.5f, lg, -kLogSqrt2Pi));
-                } else {
-                    const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
-                    term = (xl - r) - gg[e];
-                }
+                // both branches are evaluated and selected: a per-pixel branch cost more than the extra rcp
+                const float d = xv - r;
+                const float normal = fmaf(-0.5f * (d * d), rcp_fast(r), fmaf(-0.5f, lg, -kLogSqrt2Pi));
+                const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
+                const float term = (r > m.nswitch) ? normal : ((xl - r) - gg[e]);
                 if (e & 1) a1 += term; else a0 += term;
             }
         }

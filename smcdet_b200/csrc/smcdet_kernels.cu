@@ -75,10 +75,12 @@ int num_sms() {
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
+// sum over the TPP lanes of a particle; neighbours first, so that with tree_sum() inside each lane the
+// additions form one balanced tree over the tile's rows for every TPP (bit-identical results)
 template <int TPP>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int o = TPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 1; o < TPP; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
@@ -166,10 +168,11 @@ __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float
     const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
     float acc[PPT];
     render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
-    const float part = pixel_loglik_sum<MODEL, PPT>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
+    float Q, S;
+    pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
         return make_float4(acc[4 * g] + m.bg, acc[4 * g + 1] + m.bg, acc[4 * g + 2] + m.bg, acc[4 * g + 3] + m.bg);
-    });
-    const float ll = group_sum<TPP>(part);
+    }, Q, S);
+    const float ll = finish_loglik<MODEL>(group_sum<TPP>(Q), group_sum<TPP>(S), HW);
     if (sub == 0 && pi < n_here) out[pbase + pi] = ll;
 }
 
@@ -816,11 +819,12 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                 acc[4 * g] = acc[4 * g + 1] = acc[4 * g + 2] = acc[4 * g + 3] = 0.0f;
             }
         }
-        const float llp = group_sum<TPP>(
-            pixel_loglik_sum<MODEL, PPT>(m, xs, lg, [&](int g) {
-                const float4 r = my_rate[g * kBT];
-                return make_float4(r.x + acc[4 * g], r.y + acc[4 * g + 1], r.z + acc[4 * g + 2], r.w + acc[4 * g + 3]);
-            }));
+        float pq, ps;
+        pixel_loglik_sum<MODEL, RPT, W>(m, xs, lg, [&](int g) {
+            const float4 r = my_rate[g * kBT];
+            return make_float4(r.x + acc[4 * g], r.y + acc[4 * g + 1], r.z + acc[4 * g + 2], r.w + acc[4 * g + 3]);
+        }, pq, ps);
+        const float llp = finish_loglik<MODEL>(group_sum<TPP>(pq), group_sum<TPP>(ps), HW);
 
         if (full) {
             ll = llp;

@@ -232,60 +232,92 @@ SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int 
 //     where rate > 50000.  lgam[p] = lgamma(x[p]+1).
 // rate_at(p) returns the expected count of the thread's p-th pixel.
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, int NPIX, class Rate4>
-SMC_HD float pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam, Rate4 rate4) {
-    // x / lgam: the lane's NPIX observed pixels (16-byte aligned); rate4(q) returns the expected counts
-    // of pixels 4q..4q+3
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-        float q0 = 0.f, q1 = 0.f, s0 = 0.f, s1 = 0.f;
+// balanced pairwise sum of N = 2^k values: ((v0+v1)+(v2+v3))+...  Together with the xor-butterfly over the lanes
+// of a particle this gives ONE summation tree over the tile's rows whatever the number of lanes per particle,
+// so results do not depend on how a launch was decomposed (and hence not on how tiles are sharded over GPUs).
+template <int N>
+SMC_HD float tree_sum(float (&v)[N]) {
 #pragma unroll
-        for (int g = 0; g < NPIX / 4; ++g) {
-            const float4 r = rate4(g);
-            const float4 xv = x4[g];
-            {
-                const float va = fmaf(m.nm, r.x, m.na), vb = fmaf(m.nm, r.y, m.na);
-                const float da = xv.x - r.x, db = xv.y - r.y;
-                const float den = va * vb;
-                const float num = fmaf(da * da, vb, (db * db) * va);
-                q0 = fmaf(num, rcp_fast(den), q0);
-                s0 += lg2_fast(den);
+    for (int s = 1; s < N; s <<= 1) {
+#pragma unroll
+        for (int i = 0; i + s < N; i += 2 * s) v[i] += v[i + s];
+    }
+    return v[0];
+}
+
+// Per-pixel log density summed over the lane's RPT rows of W pixels; returns the two partial sums (Q, S) that
+// finish_loglik combines after the reduction over the lanes of the particle:
+//   M71 (images.py:169-175): Q = sum (x-r)^2 / v, S = sum lg2 v, v = na + nm r (pixel pairs share a rcp and a lg2)
+//   Gaussian-PSF model (images.py:91-102): Q = sum of Poisson / Normal terms, S = 0
+// x / lgam: the lane's observed pixels and lgamma(x+1) (16-byte aligned); rate4(g) = expected counts of pixels 4g..4g+3.
+template <int MODEL, int RPT, int W, class Rate4>
+SMC_HD void pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam, Rate4 rate4, float& Q, float& S) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float qrow[RPT], srow[RPT];
+    if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            float q = 0.f, s = 0.f;
+#pragma unroll
+            for (int g = r * (W / 4); g < (r + 1) * (W / 4); ++g) {
+                const float4 rt = rate4(g);
+                const float4 xv = x4[g];
+                {
+                    const float va = fmaf(m.nm, rt.x, m.na), vb = fmaf(m.nm, rt.y, m.na);
+                    const float da = xv.x - rt.x, db = xv.y - rt.y;
+                    const float den = va * vb;
+                    q = fmaf(fmaf(da * da, vb, (db * db) * va), rcp_fast(den), q);
+                    s += lg2_fast(den);
+                }
+                {
+                    const float va = fmaf(m.nm, rt.z, m.na), vb = fmaf(m.nm, rt.w, m.na);
+                    const float da = xv.z - rt.z, db = xv.w - rt.w;
+                    const float den = va * vb;
+                    q = fmaf(fmaf(da * da, vb, (db * db) * va), rcp_fast(den), q);
+                    s += lg2_fast(den);
+                }
             }
-            {
-                const float va = fmaf(m.nm, r.z, m.na), vb = fmaf(m.nm, r.w, m.na);
-                const float da = xv.z - r.z, db = xv.w - r.w;
-                const float den = va * vb;
-                const float num = fmaf(da * da, vb, (db * db) * va);
-                q1 = fmaf(num, rcp_fast(den), q1);
-                s1 += lg2_fast(den);
-            }
+            qrow[r] = q; srow[r] = s;
         }
-        return fmaf(-0.5f, q0 + q1, fmaf(-0.5f * kLn2, s0 + s1, -(float)NPIX * kLogSqrt2Pi));
+        Q = tree_sum<RPT>(qrow);
+        S = tree_sum<RPT>(srow);
     } else {
         const float4* l4 = reinterpret_cast<const float4*>(lgam);
-        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int g = 0; g < NPIX / 4; ++g) {
-            const float4 r4 = rate4(g);
-            const float4 xv4 = x4[g];
-            const float4 lg4 = l4[g];
-            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-            const float xx[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
-            const float gg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+        for (int r = 0; r < RPT; ++r) {
+            float acc = 0.f;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float r = rr[e], xv = xx[e];
-                const float lg = lg2_fast(r) * kLn2;
-                // both branches are evaluated and selected: a per-pixel branch cost more than the extra rcp
-                const float d = xv - r;
-                const float normal = fmaf(-0.5f * (d * d), rcp_fast(r), fmaf(-0.5f, lg, -kLogSqrt2Pi));
-                const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
-                const float term = (r > m.nswitch) ? normal : ((xl - r) - gg[e]);
-                if (e & 1) a1 += term; else a0 += term;
+            for (int g = r * (W / 4); g < (r + 1) * (W / 4); ++g) {
+                const float4 r4 = rate4(g);
+                const float4 xv4 = x4[g];
+                const float4 lg4 = l4[g];
+                const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                const float xx[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+                const float gg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float rv = rr[e], xv = xx[e];
+                    const float lg = lg2_fast(rv) * kLn2;
+                    // both branches are evaluated and selected: a per-pixel branch cost more than the extra rcp
+                    const float d = xv - rv;
+                    const float normal = fmaf(-0.5f * (d * d), rcp_fast(rv), fmaf(-0.5f, lg, -kLogSqrt2Pi));
+                    const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
+                    acc += (rv > m.nswitch) ? normal : ((xl - rv) - gg[e]);
+                }
             }
+            qrow[r] = acc;
         }
-        return a0 + a1;
+        Q = tree_sum<RPT>(qrow);
+        S = 0.f;
     }
+}
+
+// log-likelihood of the tile from the totals of pixel_loglik_sum over all NPIX_TOTAL pixels
+template <int MODEL>
+SMC_HD float finish_loglik(float Q, float S, int npix_total) {
+    if (MODEL == SMCDET_MODEL_M71_NORMAL)
+        return fmaf(-0.5f, Q, fmaf(-0.5f * kLn2, S, -(float)npix_total * kLogSqrt2Pi));
+    return Q;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,14 +354,14 @@ SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_
 #pragma unroll
     for (int j = 0; j < W; ++j) dxs[j] = ((float)j + 0.5f) - l1;
     const float lo = floorf(l0) - m.radius, hi = floorf(l0) + m.radius;
-    sP = 0.f; s0 = 0.f; s1 = 0.f;
+    float pP[RPT], p0[RPT], p1[RPT];  // per-row partial sums, combined by the same tree as the log-likelihood
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const float fi = (float)(row0 + r);
         const float dy = (fi + 0.5f) - l0;
         const float d2 = (fi >= lo && fi <= hi) ? dy * dy : INFINITY;
         const float g1 = ex2_fast(-m.k1 * d2);
-        float rowQ0 = 0.f;  // sum_j w Q over the row (times dy afterwards)
+        float rowP = 0.f, rowQ0 = 0.f, row1 = 0.f;  // sums over the row of w P, w Q (times dy afterwards), w Q dx
         float wr[W];        // w_p = d loglik / d rate_p of the row's pixels
         w_row(r, wr);
         if (MODEL == SMCDET_MODEL_M71_NORMAL) {
@@ -344,10 +376,10 @@ SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_
                 const float Q = fmaf(pw * rcp_fast(t), m.isp, fmaf(e2, m.is2, e1 * m.is1));
                 const float wp = wr[j];
                 if (ACC) acc[r * W + j] = fmaf(acc_wgt, P, acc[r * W + j]);
-                sP = fmaf(wp, P, sP);
+                rowP = fmaf(wp, P, rowP);
                 const float wq = wp * Q;
                 rowQ0 += wq;
-                s1 = fmaf(wq, dxs[j], s1);
+                row1 = fmaf(wq, dxs[j], row1);
             }
         } else {
 #pragma unroll
@@ -355,15 +387,16 @@ SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_
                 const float P = g1 * c.e1[j];
                 const float wp = wr[j];
                 if (ACC) acc[r * W + j] = fmaf(acc_wgt, P, acc[r * W + j]);
-                sP = fmaf(wp, P, sP);
+                rowP = fmaf(wp, P, rowP);
                 const float wq = wp * (P * m.is1);
                 rowQ0 += wq;
-                s1 = fmaf(wq, dxs[j], s1);
+                row1 = fmaf(wq, dxs[j], row1);
             }
         }
         // a masked row has dy finite but every Q exactly 0
-        s0 = fmaf(rowQ0, dy, s0);
+        pP[r] = rowP; p0[r] = rowQ0 * dy; p1[r] = row1;
     }
+    sP = tree_sum<RPT>(pP); s0 = tree_sum<RPT>(p0); s1 = tree_sum<RPT>(p1);
 }
 
 // ---------------------------------------------------------------------------------------------

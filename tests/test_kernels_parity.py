@@ -398,3 +398,29 @@ def test_mala_matches_reference_with_injected_draws(backend, name):
                 assert rel_err(r["loglik"][same], O.loglik(om, tiles, r["locs"], r["fluxes"])[same]) < RTOL
     finally:
         backend.force_tpp(0)
+
+
+def test_results_do_not_depend_on_lanes_per_particle(backend):
+    """The log-likelihood and a whole MH / MALA launch are bit-identical for every threads-per-particle
+    decomposition (one summation tree over the tile's rows), so a tile's result does not depend on how many
+    tiles share its launch or its GPU."""
+    for name in ("mh_m71", "mh_gauss", "mh_m71_t16"):
+        g = Golden(name)
+        meta = g.meta
+        m, p = abi_model(meta), abi_prior(meta)
+        tiles, counts, locs, fluxes, tau = g.flat("tiles"), g.flat("counts"), g.flat("locs"), g.flat("fluxes"), g["tau"].reshape(-1)
+        ref = None
+        try:
+            for tpp in TPPS[meta["tile"]]:
+                backend.force_tpp(tpp)
+                ll = backend.loglik(m, tiles, locs, fluxes)
+                r = backend.mh_mutate(m, p, abi_mh(meta, 12), tiles, counts, locs, fluxes, tau, seed=5, offset=3)
+                q = backend.mh_mutate(m, p, abi_mh(meta, 4), tiles, counts, locs, fluxes, tau, seed=5, offset=3, mala=True)
+                cur = (ll, r["locs"], r["fluxes"], r["loglik"], r["log_alpha"], q["locs"], q["fluxes"])
+                if ref is None:
+                    ref = cur
+                else:
+                    for a, b in zip(ref, cur):
+                        assert np.array_equal(a, b, equal_nan=True), (name, tpp)
+        finally:
+            backend.force_tpp(0)

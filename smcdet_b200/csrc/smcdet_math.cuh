@@ -57,6 +57,17 @@ SMC_HD float lg2_fast(float x) {
 #endif
 }
 
+// product that the compiler may not fuse into a following add (keeps the summation tree identical for every
+// lanes-per-particle decomposition: a fused multiply-add in one instantiation would round differently)
+SMC_HD float mul_unfused(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float p = a * b;
+    return p;
+#endif
+}
+
 SMC_HD float rcp_fast(float x) {
 #if defined(__CUDA_ARCH__)
     float y;
@@ -394,7 +405,7 @@ SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_
             }
         }
         // a masked row has dy finite but every Q exactly 0
-        pP[r] = rowP; p0[r] = rowQ0 * dy; p1[r] = row1;
+        pP[r] = rowP; p0[r] = mul_unfused(rowQ0, dy); p1[r] = row1;
     }
     sP = tree_sum<RPT>(pP); s0 = tree_sum<RPT>(p0); s1 = tree_sum<RPT>(p1);
 }

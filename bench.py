@@ -175,9 +175,12 @@ class ClockSampler(threading.Thread):
             import pynvml as nv
 
             nv.nvmlInit()
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            visible = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+            entry = visible[self.index] if self.index < len(visible) else str(self.index)
+            if entry.isdigit():
+                h = nv.nvmlDeviceGetHandleByIndex(int(entry))
+            else:  # CUDA_VISIBLE_DEVICES given as UUIDs
+                h = nv.nvmlDeviceGetHandleByUUID(entry.encode() if isinstance(entry, str) else entry)
             bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
@@ -190,6 +193,30 @@ class ClockSampler(threading.Thread):
                 self._stop_flag.wait(0.2)
         except Exception as exc:  # noqa: BLE001
             self.error = repr(exc)
+            self._poll_nvidia_smi()
+
+    def _poll_nvidia_smi(self):
+        """Fallback when NVML cannot be used in-process: a polling nvidia-smi child (the recipe's clocks line)."""
+        import subprocess
+
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                     "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            for line in proc.stdout:
+                c = [x.strip() for x in line.split(",")]
+                try:
+                    self.rows.append((float(c[0]), float(c[1]), float(c[2]),
+                                      [n for n, v in zip(names, c[3:7]) if v.lower().startswith("active")]))
+                except (ValueError, IndexError):
+                    pass
+                if self._stop_flag.is_set():
+                    proc.terminate()
+                    break
+        except Exception:  # noqa: BLE001
+            pass
 
     def stop(self):
         self._stop_flag.set()

@@ -125,3 +125,33 @@ def test_gather_tiles_two_gloo_ranks(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_distribution_classes_follow_their_definitions():
+    """The thin torch classes of smcdet_b200.distributions (device-agnostic, so checkable on the CPU):
+    truncated normal draws stay in the box and its density integrates to one, bounded Pareto matches its
+    closed form, the integer uniform gives -inf outside its support."""
+    from smcdet_b200.distributions import DiscreteUniform, TruncatedDiagonalMVN, TruncatedPareto
+
+    torch.manual_seed(0)
+    mu = torch.tensor([[-3.95, 5.0], [11.9, 0.0]])
+    d = TruncatedDiagonalMVN(mu, torch.tensor(0.1), torch.tensor([-4.0, -4.0]), torch.tensor([12.0, 12.0]))
+    x = d.sample()
+    assert x.shape == mu.shape and (x >= -4).all() and (x <= 12).all()
+    grid = torch.linspace(-4.0, -3.0, 20001).unsqueeze(-1)
+    one = TruncatedDiagonalMVN(torch.tensor([-3.95]), torch.tensor(0.1), torch.tensor([-4.0]), torch.tensor([12.0]))
+    mass = torch.trapezoid(one.log_prob(grid).exp().squeeze(-1), grid.squeeze(-1))
+    assert abs(float(mass) - 1.0) < 1e-3
+    with pytest.raises(AssertionError):
+        d.log_prob(torch.full_like(mu, 13.0))
+    p = TruncatedPareto(0.2, 0.06, 1800.0)
+    f = p.sample([2000])
+    assert (f >= 0.06 * (1 - 1e-6)).all() and (f <= 1800.0 * (1 + 1e-6)).all()
+    a, lo, up = 0.2, 0.06, 1800.0
+    ref = np.log(a * lo**a / (1 - (lo / up) ** a)) - (a + 1) * np.log(7.0)
+    assert abs(float(p.log_prob(torch.tensor(7.0))) - ref) < 1e-5
+    u = DiscreteUniform(2, 5)
+    lp = u.log_prob(torch.tensor([1.0, 2.0, 5.0, 6.0]))
+    assert torch.isneginf(lp[0]) and torch.isneginf(lp[3]) and abs(float(lp[1]) + np.log(4)) < 1e-6
+    s = u.sample([100])
+    assert int(s.min()) >= 2 and int(s.max()) <= 5

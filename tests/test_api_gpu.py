@@ -565,3 +565,34 @@ def test_incremental_loglik_drift_is_negligible():
     drift = rel_err(out[False][2].cpu().numpy(), exact.cpu().numpy())
     print("incremental loglik drift (max relative):", drift)
     assert drift < 2e-5
+
+
+def test_sampler_with_16_pixel_tiles():
+    """tile_dim = 16 (the size the reference's Aggregate would merge 8x8 tiles into): a 32x32 image as 2x2 tiles."""
+    from smcdet_b200.images import M71ImageModel, generate_images
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.prior import M71Prior
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("loglik_m71_t16_d10")
+    mp, pp = g.meta["model_params"], g.meta["prior_params"]
+    torch.manual_seed(3)
+    kw = dict(background=mp["background"], psf_radius=mp["psf_radius"], adu_per_nmgy=mp["adu_per_nmgy"],
+              psf_params=mp["psf_params"], noise_additive=mp["noise_additive"], noise_multiplicative=mp["noise_multiplicative"])
+    big_model = M71ImageModel(32, 32, **kw)
+    truth = M71Prior(0, 60, pp["counts_rate"], 32, 32, flux_alpha=pp["flux_alpha"], flux_lower=0.25, flux_upper=pp["flux_upper"], pad=0)
+    image = generate_images(truth, big_model, 0.25, 0, 32, num_images=1)[-1][0]
+    assert image.shape == (32, 32)
+    model = M71ImageModel(16, 16, **kw)
+    prior = M71Prior(8, 8, pp["counts_rate"], 16, 16, flux_alpha=pp["flux_alpha"], flux_lower=pp["flux_lower"],
+                     flux_upper=pp["flux_upper"], pad=4)
+    mh = SingleComponentMH(30, 0.1, 2.5, pp["flux_lower"], pp["flux_upper"])
+    s = SMCsampler(image, 16, prior, model, mh, 2000, 0.5, "systematic", 0.25, 300, freeze_finished=True, verbose=False)
+    s.run()
+    assert s.temperature.shape == (2, 2) and float(s.temperature.min()) == 1.0
+    assert float(s.locs.min()) >= -4 and float(s.locs.max()) <= 20 and torch.isfinite(s.log_normalizing_constant).all()
+    sub = torch.randperm(2000)[:50]
+    ref = O.loglik(oracle_model(dict(g.meta)), s.tiled_image.contiguous().view(4, 16, 16).cpu().numpy(),
+                   s.locs.view(4, 2000, 8, 2)[:, sub].cpu().numpy(), s.fluxes.view(4, 2000, 8)[:, sub].cpu().numpy())
+    got = model.loglikelihood(s.tiled_image, s.locs, s.fluxes).view(4, 2000)[:, sub]
+    assert rel_err(got.cpu().numpy(), ref) < RTOL

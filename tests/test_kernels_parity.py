@@ -424,3 +424,34 @@ def test_results_do_not_depend_on_lanes_per_particle(backend):
                         assert np.array_equal(a, b, equal_nan=True), (name, tpp)
         finally:
             backend.force_tpp(0)
+
+
+def test_many_stars_and_ragged_particle_counts(backend):
+    """D = 40 (shared-memory opt-in path), D = 80 (beyond the fused kernels' limit: generic likelihood kernel,
+    MH refuses), and particle counts that do not fill a block, all against the oracle."""
+    g = Golden("loglik_m71_t8_d10")
+    meta = dict(g.meta)
+    rng = np.random.default_rng(3)
+    om = oracle_model(meta)
+    tiles = g.flat("tiles")[:2]
+    for D, N in ((40, 37), (80, 5), (3, 1), (10, 129)):
+        meta["D"] = meta["min_objects"] = D
+        locs = rng.uniform(-4, 12, (2, N, D, 2)).astype(np.float32)
+        fluxes = np.exp(rng.uniform(np.log(0.07), np.log(300.0), (2, N, D))).astype(np.float32)
+        ll = backend.loglik(abi_model(meta), tiles, locs, fluxes)
+        assert rel_err(ll, O.loglik(om, tiles, locs, fluxes)) < RTOL, (D, N)
+        counts = np.full((2, N), float(D), np.float32)
+        mh = abi_mh(dict(meta, locs_stdev=0.1, fluxes_stdev=2.5, fluxes_min=0.06291294097900389, fluxes_max=1804.6791992187502), 3)
+        tau = np.array([0.2, 0.9], np.float32)
+        comp = rng.integers(0, D, (3, 2, N)).astype(np.int32)
+        tape = dict(comp=comp, u_loc=rng.random((3, 2, N, 2), dtype=np.float32), u_flux=rng.random((3, 2, N), dtype=np.float32),
+                    u_acc=rng.random((3, 2, N), dtype=np.float32))
+        if D > 64:
+            with pytest.raises(Exception, match="too many stars"):
+                backend.mh_mutate(abi_model(meta), abi_prior(meta), mh, tiles, counts, locs, fluxes, tau, tape=tape)
+            continue
+        r = backend.mh_mutate(abi_model(meta), abi_prior(meta), mh, tiles, counts, locs, fluxes, tau, tape=tape)
+        o = O.mh_run(om, oracle_prior(meta), O.make_mh(3, 0.1, 2.5, 0.06291294097900389, 1804.6791992187502, (-4, -4), (12, 12)),
+                     tiles, counts, locs, fluxes, tau, comp, tape["u_loc"], tape["u_flux"], tape["u_acc"])
+        assert np.array_equal(r["accept"], o["accept"]), (D, N)
+        assert np.max(np.abs(r["locs"] - o["locs"])) < 1e-5 and np.max(np.abs(r["fluxes"] / o["fluxes"] - 1)) < RTOL

@@ -73,6 +73,8 @@ class SMCsampler(object):
         self._seed_uses = {}
         self._final = False
         self.iter = 0
+        self.history = []
+        self.record_history = False
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -286,17 +288,24 @@ class SMCsampler(object):
                                      L.ptr(fo), numH * numW, n, d, L.stream_for(lf)))
         return counts.view(numH, numW, n), lo.view(numH, numW, n, d, 2), fo.view(numH, numW, n, d)
 
-    def run(self):
-        """reference sampler.py:221-256"""
-        self.iter = 0
-        self._base_seed = None
-        self._seed_uses = {}
-        self._print("starting...")
-
-        self.initialize()
-        self._temper_and_update()
+    def run(self, *, resume=False, stop_after=None):
+        """reference sampler.py:221-256.  Extensions (keyword-only): ``stop_after`` = k returns after SMC
+        iteration k with ``has_run`` still False (checkpoint with ``state_dict()``); ``resume=True`` continues
+        from the loaded / current state instead of re-initialising.  A stopped-and-resumed run is bit-identical
+        to an uninterrupted one: every stage's Philox key depends on (base seed, iteration, stage) only."""
+        if not resume:
+            self.iter = 0
+            self._base_seed = None
+            self._seed_uses = {}
+            self.history = []
+            self._print("starting...")
+            self.initialize()
+            self._temper_and_update()
+            self._record()
 
         while torch.any(self.temperature < 1) and self.iter <= self.max_smc_iters:
+            if stop_after is not None and self.iter >= stop_after:
+                return
             self.iter += 1
             if self.iter % self.print_every == 0:
                 self._print(
@@ -311,6 +320,7 @@ class SMCsampler(object):
             self.resample()
             self.mutate()
             self._temper_and_update()
+            self._record()
 
         self._active = None
         self._spare = self._active_prev = None
@@ -322,6 +332,41 @@ class SMCsampler(object):
             self.MutationKernel.check_status()
         self.has_run = True
         self._print("done!\n")
+
+    def _record(self):
+        """Per-iteration record (temperature, ESS, log Z, acceptance, root-finder evaluations) kept as device
+        tensors when ``record_history`` is set; nothing is synchronised."""
+        if getattr(self, "record_history", False):
+            self.history.append(dict(iter=self.iter, temperature=self.temperature.clone(), ess=self.ess.clone(),
+                                     log_normalizing_constant=self.log_normalizing_constant.clone(),
+                                     mutation_acc_rates=self.mutation_acc_rates.clone(),
+                                     tempering_funcalls=self.tempering_funcalls.clone()))
+
+    # ---- checkpoint / resume (the reference has none; its drivers save per-batch .pt files,
+    # experiments/basic/run_smc.py:179-187) --------------------------------------------------------
+    _STATE_TENSORS = ("counts", "locs", "fluxes", "weights", "weights_log_unnorm", "loglik", "temperature",
+                      "temperature_prev", "log_normalizing_constant", "ess", "mutation_acc_rates")
+
+    def state_dict(self):
+        """Everything a shard needs to continue: particle state, weights, temperatures, log Z, iteration and
+        the Philox base seed (CPU tensors; 12 D + 20 bytes per particle)."""
+        sd = {k: getattr(self, k).detach().to("cpu", copy=True) for k in self._STATE_TENSORS}
+        sd.update(iter=int(self.iter), base_seed=int(self._base_seed), has_run=bool(self.has_run),
+                  num_catalogs=int(self.num_catalogs), grid=(int(self.numH), int(self.numW)),
+                  active=None if self._active is None else self._active.to("cpu", copy=True))
+        return sd
+
+    def load_state_dict(self, sd):
+        if tuple(sd["grid"]) != (self.numH, self.numW) or sd["num_catalogs"] != self.num_catalogs:
+            raise ValueError("checkpoint was written for a different tile grid or number of catalogs")
+        for k in self._STATE_TENSORS:
+            setattr(self, k, sd[k].to(self._device))
+        self.iter, self._base_seed, self.has_run = sd["iter"], sd["base_seed"], sd["has_run"]
+        self._seed_uses = {}
+        self._active = None if sd["active"] is None else sd["active"].to(self._device)
+        self._spare = self._active_prev = None
+        self._loglik_key = self._state_key()  # the saved log-likelihood belongs to the saved particles
+        self.history = []
 
     # ---- posterior summaries (reference sampler.py:258-298) -----------------------------------
     def posterior_mean_count(self, counts):

@@ -637,6 +637,66 @@ def case_mala():
 CASES["mala"] = case_mala
 
 
+def case_exact_counts():
+    """A faint one-star image where the evidences of "no star" and "one star" are comparable: exact log p(x | s = 0)
+    (closed form) and log p(x | s = 1) (midpoint quadrature over the whole prior box, flux axis in prior-cdf
+    coordinates) from the float64 oracle.  Known answer for count-stratified SMC (manuscript Algorithm 1): the
+    posterior over the count follows from the two evidences and the Poisson count prior.  Also reference
+    SMCsampler runs with min_objects = max_objects = 1 for comparison."""
+    from oracle import api as O
+
+    tile, pad = 8, 4
+    im, pr, meta = m71_objects(tile, 1, pad)
+    torch.manual_seed(72)
+    true_loc = torch.tensor([[[[[4.2, 3.1]]]]])
+    true_flux = torch.tensor([[[[1.4]]]])
+    image = im.sample(true_loc, true_flux)[0, 0, :, :, 0].contiguous()
+    om = O.m71_model(M71["psf_radius"], M71["psf_params"], M71["background"], M71["adu_per_nmgy"], M71["noise_additive"],
+                     M71["noise_multiplicative"], dtype=np.float64)
+    tiles = image.numpy()[None].astype(np.float64)
+    z = np.zeros((1, 1, 1, 2))
+    logz0 = float(O.loglik(om, tiles, z, z[..., 0], dtype=np.float64)[0, 0])
+    a, lo, up = M71_PRIOR["flux_alpha"], M71_PRIOR["flux_lower"], M71_PRIOR["flux_upper"]
+
+    def quad(gl, gu):
+        la = (np.arange(gl) + 0.5) / gl * (tile + 2 * pad) - pad
+        u = (np.arange(gu) + 0.5) / gu
+        f = ((up**a - u * up**a + u * lo**a) / (lo**a * up**a)) ** (-1 / a)   # distributions.py:77-79
+        L0, L1, F = np.meshgrid(la, la, f, indexing="ij")
+        th = np.stack([L0.ravel(), L1.ravel(), F.ravel()], -1)
+        ll = np.concatenate([O.loglik(om, tiles, th[i:i + 400000][None, :, None, :2], th[i:i + 400000][None, :, None, 2],
+                                      dtype=np.float64)[0] for i in range(0, th.shape[0], 400000)])
+        mx = ll.max()
+        w = np.exp(ll - mx)
+        post = w / w.sum()
+        return mx + np.log(w.mean()), (post[:, None] * th).sum(0)
+
+    coarse, _ = quad(80, 200)
+    logz1, mean1 = quad(160, 400)
+    print("logZ0", logz0, "logZ1", logz1, "(coarse grid:", coarse, ") posterior mean given one star", mean1)
+    rate = M71_PRIOR["counts_rate"] * (tile + 2 * pad) ** 2
+    lp = np.array([logz0 - rate, logz1 + np.log(rate) - rate])
+    post = np.exp(lp - lp.max())
+    post /= post.sum()
+    print("p(s | x) over s in {0, 1}:", post)
+    rows = []
+    for seed in range(4):
+        torch.manual_seed(3000 + seed)
+        mh = SingleComponentMH(25, 0.1, 2.5, pr.flux_lower, pr.flux_upper)
+        s = SMCsampler(image, tile, pr, im, mh, 2000, 0.5, "multinomial", M71_DETECTION, 200, print_every=1000)
+        s.run()
+        rows.append([float(s.log_normalizing_constant), float(s.iter)])
+        print("reference seed", seed, rows[-1])
+    meta.update(true_loc=[4.2, 3.1], true_flux=1.4, flux_threshold=M71_DETECTION, quadrature=[160, 160, 400],
+                columns=["logZ1", "smc_iters"])
+    save("exact_counts", meta, image=image, exact_logz0=np.array(logz0), exact_logz1=np.array(logz1),
+         exact_logz1_coarse=np.array(coarse), exact_count_posterior=post, exact_mean_given_one=mean1,
+         reference_runs=np.array(rows))
+
+
+CASES["exact_counts"] = case_exact_counts
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = sys.argv[1:] or list(CASES)

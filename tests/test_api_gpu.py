@@ -635,3 +635,67 @@ def test_checkpoint_resume_is_bit_identical(freeze, tmp_path):
         other = make()
         other.num_catalogs = 7
         other.load_state_dict(torch.load(tmp_path / "shard.pt"))
+
+
+def test_count_stratified_smc_against_exact_evidences():
+    """CS-SMC (manuscript Algorithm 1) on the faint-star image of the exact_counts fixture: log Z_0 is the
+    closed-form likelihood of the empty catalog, log Z_1 was integrated by quadrature over the whole prior box
+    (float64 oracle), and p(s | x) follows from both and the Poisson count prior (0.08 / 0.92: both strata
+    matter).  Also the stratified driver interface (weights_intercount -> Aggregate) and the joint draw."""
+    from smcdet_b200.aggregate import Aggregate
+    from smcdet_b200.cssmc import CountStratifiedSMC
+    from smcdet_b200.images import M71ImageModel
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.prior import M71Prior
+
+    g = Golden("exact_counts")
+    mp, pp = g.meta["model_params"], g.meta["prior_params"]
+    model = M71ImageModel(8, 8, background=mp["background"], psf_radius=mp["psf_radius"], adu_per_nmgy=mp["adu_per_nmgy"],
+                          psf_params=mp["psf_params"], noise_additive=mp["noise_additive"],
+                          noise_multiplicative=mp["noise_multiplicative"])
+    image = cu(g["image"])
+    logz0, logz1, exact = float(g["exact_logz0"]), float(g["exact_logz1"]), g["exact_count_posterior"]
+    assert abs(float(g["exact_logz1_coarse"]) - logz1) < 1e-3          # the quadrature has converged
+    assert abs(g["reference_runs"][:, 0].mean() - logz1) < 0.5         # and the reference agrees with it
+
+    def run(max_objects, method, seed, n=20000):
+        torch.manual_seed(seed)
+        prior = M71Prior(0, max_objects, pp["counts_rate"], 8, 8, flux_alpha=pp["flux_alpha"], flux_lower=pp["flux_lower"],
+                         flux_upper=pp["flux_upper"], pad=g.meta["pad"])
+        mh = SingleComponentMH(25, 0.1, 2.5, pp["flux_lower"], pp["flux_upper"])
+        cs = CountStratifiedSMC(image, 8, prior, model, mh, n, 0.5, method, g.meta["flux_threshold"], 200, verbose=False)
+        cs.run()
+        return cs, prior, mh
+
+    cs, prior, mh = run(1, "multinomial", 0)
+    lz = cs.log_normalizing_constant[0, 0].cpu().numpy()
+    assert abs(lz[0] / logz0 - 1) < 1e-5 and abs(lz[1] - logz1) < 0.15, (lz, logz0, logz1)
+    post = cs.posterior_count_probs[0, 0].cpu().numpy()
+    assert np.allclose(post, exact, atol=0.015), (post, exact)
+    assert int(cs.iters[1]) >= 1                                       # the one-star stratum really tempers
+    assert abs(float(cs.weights_intercount.sum()) - 1) < 1e-5 and cs.counts.shape[-1] == 2 * 20000
+    # the joint draw follows p(s | x); one-star catalogs reproduce the exact posterior mean given one star
+    frac1 = float((cs.joint_counts == 1).float().mean())
+    assert abs(frac1 - post[1]) < 0.01
+    assert cs.joint_locs.shape == (1, 1, 20000, 1, 2) and int(cs.pruned_counts.max()) <= 1
+    one = cs.locs[0, 0, 20000:, 0]
+    assert np.allclose(one.mean(0).cpu().numpy(), g["exact_mean_given_one"][:2], atol=0.15)
+
+    # three strata, systematic: same evidences for s = 0, 1; probabilities normalised; catalogs carry s stars
+    cs3, _, _ = run(2, "systematic", 1, n=6000)
+    lz3 = cs3.log_normalizing_constant[0, 0].cpu().numpy()
+    assert abs(lz3[0] / logz0 - 1) < 1e-5 and abs(lz3[1] - logz1) < 0.25
+    p3 = cs3.posterior_count_probs[0, 0].cpu().numpy()
+    assert abs(p3.sum() - 1) < 1e-5 and abs(p3[1] / p3[0] - exact[1] / exact[0]) < 0.3 * exact[1] / exact[0]
+    nz = (cs3.fluxes[0, 0] > 0).sum(-1).float()
+    assert torch.equal(nz, cs3.counts[0, 0])
+    assert cs3.joint_counts.shape == (1, 1, 6000) and cs3.posterior_mean_count().shape == (1, 1)
+    assert abs(float((cs3.joint_counts == 2).float().mean()) - p3[2]) < 0.02
+
+    # the reference drivers' flow: stratified population + inter-count weights into the 1x1 Aggregate sink
+    agg = Aggregate(prior, model, mh, cs.tiled_image, cs.counts, cs.locs, cs.fluxes, cs.weights_intercount,
+                    cs.log_normalizing_constant, g.meta["flux_threshold"], "multinomial", 0.5)
+    agg.run()
+    assert agg.has_run and abs(float((agg.counts == 1).float().mean()) - post[1]) < 0.01
+    with pytest.raises(ValueError):
+        CountStratifiedSMC(image, 8, prior, model, mh, 10, 0.5, "stratified")

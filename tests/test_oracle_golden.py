@@ -103,3 +103,31 @@ def test_oracle_resample_gather_prune():
     c, l, f = O.prune(g.flat("locs"), g.flat("fluxes"), g.meta["tile"], g.meta["tile"], g.meta["flux_threshold"])
     assert np.array_equal(c, g.flat("pruned_counts")) and np.array_equal(l, g.flat("pruned_locs"))
     assert np.array_equal(f, g.flat("pruned_fluxes"))
+
+
+def test_exact_count_evidences_fixture_is_consistent():
+    """exact_counts.npz: log p(x | s = 0) is the oracle's likelihood of the empty catalog, a coarse re-integration
+    of log p(x | s = 1) over the prior box agrees with the stored quadrature, and the stored p(s | x) follows."""
+    import numpy as np
+
+    from goldenlib import Golden, O, oracle_model
+
+    g = Golden("exact_counts")
+    om = oracle_model(g.meta, dtype=np.float64, psf_norm=None)
+    tiles = g["image"][None].astype(np.float64)
+    z = np.zeros((1, 1, 1, 2))
+    assert abs(float(O.loglik(om, tiles, z, z[..., 0], dtype=np.float64)[0, 0]) - float(g["exact_logz0"])) < 1e-6
+    pp, pad = g.meta["prior_params"], g.meta["pad"]
+    a, lo, up = pp["flux_alpha"], pp["flux_lower"], pp["flux_upper"]
+    la = (np.arange(48) + 0.5) / 48 * (8 + 2 * pad) - pad
+    u = (np.arange(96) + 0.5) / 96
+    f = ((up**a - u * up**a + u * lo**a) / (lo**a * up**a)) ** (-1 / a)
+    L0, L1, F = np.meshgrid(la, la, f, indexing="ij")
+    ll = O.loglik(om, tiles, np.stack([L0.ravel(), L1.ravel()], -1)[None, :, None, :], F.ravel()[None, :, None],
+                  dtype=np.float64)[0]
+    logz1 = ll.max() + np.log(np.exp(ll - ll.max()).mean())
+    assert abs(logz1 - float(g["exact_logz1"])) < 5e-3
+    rate = pp["counts_rate"] * (8 + 2 * pad) ** 2
+    lp = np.array([float(g["exact_logz0"]) - rate, float(g["exact_logz1"]) + np.log(rate) - rate])
+    post = np.exp(lp - lp.max())
+    assert np.allclose(post / post.sum(), g["exact_count_posterior"], atol=1e-9)

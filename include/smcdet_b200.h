@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMCDET_ABI_VERSION 2
+#define SMCDET_ABI_VERSION 3
 
 enum {
     SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
@@ -208,6 +208,19 @@ int smcdet_mala_mutate(const smcdet_model_params *model, const smcdet_prior_para
 int smcdet_prune(const float *locs, const float *fluxes, float tile_h, float tile_w,
                  float flux_threshold, int64_t *counts_out, float *locs_out, float *fluxes_out,
                  int T, int N, int D, void *stream);
+
+/* match_catalogs (smcdet/metrics.py:8-84): for tile t and each of the n catalogs index[t, k] (the draw at
+ * metrics.py:40) match true and estimated stars with scipy's linear_sum_assignment algorithm on
+ * location distance (pairs farther than locs_tol, or differing by more than mags_tol in magnitude, carry the
+ * 1e20 penalty and never count as matches); outputs [T, n, B] float32: stars per magnitude bin (torch.bucketize
+ * on mag_bins) in the true catalog, matched true stars, stars in the estimated catalog, matched estimated
+ * stars.  Counts are float32 ([T] and [T, M]); at most 96 stars per side, else bit 4 of *status is set
+ * (status may be NULL) and that problem's outputs stay zero. */
+int smcdet_match_catalogs(const float *true_counts, const float *true_locs, const float *true_fluxes,
+                          const float *est_counts, const float *est_locs, const float *est_fluxes,
+                          const int64_t *index, const float *mag_bins, float locs_tol, float mags_tol,
+                          float *true_total, float *true_match, float *est_total, float *est_match,
+                          int32_t *status, int T, int n, int M, int Dt, int De, int B, void *stream);
 
 #ifdef __cplusplus
 }

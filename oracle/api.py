@@ -356,6 +356,33 @@ def prune(locs, fluxes, tile_h, tile_w, flux_threshold):
     return counts, lo, fo
 
 
+def lsap(cost):
+    """scipy.optimize.linear_sum_assignment restated: (row_ind, col_ind) of the assigned pairs, rows ascending."""
+    cost = _arr(cost, np.float64)
+    nr, nc = cost.shape
+    col = np.full(max(nr, 1), -1, dtype=np.int32)
+    rc = lib().oracle_lsap(_p(cost), nr, nc, _p(col))
+    if rc != 0:
+        raise ValueError("cost matrix is infeasible")
+    rows = np.nonzero(col[:nr] >= 0)[0]
+    return rows, col[rows].astype(np.int64)
+
+
+def match_catalogs(true_counts, true_locs, true_fluxes, est_counts, est_locs, est_fluxes, index, locs_tol, mags_tol,
+                   mag_bins):
+    """smcdet/metrics.py:8-84 with the drawn catalog indices (metrics.py:40) supplied: four [T, n, B] arrays."""
+    tc, tl, tf = _arr(true_counts, np.float32), _arr(true_locs, np.float32), _arr(true_fluxes, np.float32)
+    ec, el, ef = _arr(est_counts, np.float32), _arr(est_locs, np.float32), _arr(est_fluxes, np.float32)
+    index, bins = _arr(index, np.int64), _arr(mag_bins, np.float32)
+    T, Dt = tf.shape
+    _, M, De = ef.shape
+    n, B = index.shape[1], bins.shape[0]
+    out = [np.zeros((T, n, B), dtype=np.float32) for _ in range(4)]
+    lib().oracle_match_catalogs(_p(tc), _p(tl), _p(tf), _p(ec), _p(el), _p(ef), _p(index), _p(bins), C.c_float(locs_tol),
+                                C.c_float(mags_tol), T, n, M, Dt, De, B, *[_p(o) for o in out])
+    return out
+
+
 def num_threads():
     return int(lib().oracle_num_threads())
 

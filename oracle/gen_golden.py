@@ -697,6 +697,64 @@ def case_exact_counts():
 CASES["exact_counts"] = case_exact_counts
 
 
+def case_match():
+    """metrics.match_catalogs / compute_precision_recall_f1 (smcdet/metrics.py) run unmodified on synthetic true and
+    estimated catalogs; the catalogs it draws with torch.randint (metrics.py:40) are recorded."""
+    from smcdet import metrics as M
+
+    torch.manual_seed(91)
+    T, Dt, Mc, De, n = 7, 14, 24, 16, 9
+    true_counts = torch.tensor([5, 0, 12, 3, 8, 14, 1]).float()
+    true_locs = torch.zeros(T, Dt, 2)
+    true_fluxes = torch.zeros(T, Dt)
+    est_counts = torch.zeros(T, Mc)
+    est_locs = torch.zeros(T, Mc, De, 2)
+    est_fluxes = torch.zeros(T, Mc, De)
+    for t in range(T):
+        c = int(true_counts[t])
+        true_locs[t, :c] = REAL_RAND(c, 2) * 8
+        true_fluxes[t, :c] = 10 ** (REAL_RAND(c) * 2.5 - 0.3)
+        for m in range(Mc):
+            keep = REAL_RAND(c) < 0.8
+            l = true_locs[t, :c][keep] + 0.25 * torch.randn(int(keep.sum()), 2)
+            f = true_fluxes[t, :c][keep] * torch.exp(0.25 * torch.randn(int(keep.sum())))
+            extra = int(torch.randint(0, 4, (1,)))
+            l = torch.cat([l, REAL_RAND(extra, 2) * 8])
+            f = torch.cat([f, 10 ** (REAL_RAND(extra) * 2.5 - 0.3)])
+            if m % 5 == 4 and c > 1:      # crowded: several estimates on top of one true star, and the reverse
+                l[: min(3, l.shape[0])] = true_locs[t, 0] + 0.1 * torch.randn(min(3, l.shape[0]), 2)
+            k = min(l.shape[0], De)
+            perm = torch.randperm(l.shape[0])[:k]
+            est_counts[t, m] = k
+            est_locs[t, m, :k] = l[perm]
+            est_fluxes[t, m, :k] = f[perm]
+    est_counts[3, 0] = 0
+    mag_bins = torch.arange(16.0, 23.5, 1.5)
+    drawn = []
+    real_randint = torch.randint
+
+    def recording_randint(*a, **k):
+        out = real_randint(*a, **k)
+        drawn.append(out.clone())
+        return out
+
+    torch.randint = recording_randint
+    try:
+        res = M.match_catalogs(true_counts, true_locs, true_fluxes, est_counts, est_locs, est_fluxes, n, 0.5, 0.5, mag_bins)
+    finally:
+        torch.randint = real_randint
+    index = torch.stack(drawn)
+    prf = M.compute_precision_recall_f1(*res)
+    meta = dict(T=T, Dt=Dt, M=Mc, De=De, n=n, locs_tol=0.5, mags_tol=0.5)
+    print("matches", res[1].sum().item(), "of", res[0].sum().item(), "precision", prf[0], "recall", prf[1])
+    save("match_catalogs", meta, true_counts=true_counts, true_locs=true_locs, true_fluxes=true_fluxes, est_counts=est_counts,
+         est_locs=est_locs, est_fluxes=est_fluxes, index=index, mag_bins=mag_bins, true_total=res[0], true_match=res[1],
+         est_total=res[2], est_match=res[3], precision=prf[0], recall=prf[1], f1=prf[2])
+
+
+CASES["match"] = case_match
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = sys.argv[1:] or list(CASES)

@@ -254,3 +254,135 @@ void oracle_prune_f32(const float *locs, const float *fluxes, int T, int N, int 
         counts[pn] = k;
     }
 }
+
+/* ---- catalog matching (smcdet/metrics.py:8-84) ---------------------------------------------
+ * metrics.py:61 hands the [true x est] cost matrix to scipy.optimize.linear_sum_assignment (scipy 1.17.0 in
+ * the reference's uv.lock; third-party, not under /root/reference).  oracle_lsap restates scipy's published
+ * algorithm -- the shortest-augmenting-path method of Crouse, "On implementing 2D rectangular assignment
+ * algorithms" (IEEE TAES 2016), as in scipy/optimize/rectangular_lsap -- with the same float64 operation
+ * order, so that assignments agree even where the 1e20 out-of-bounds penalty (metrics.py:60) absorbs the
+ * distances; tests/test_oracle_golden.py checks it against scipy itself and against reference runs. */
+static int lsap_augment(int nc, const double *cost, const double *u, const double *v, int *path,
+                        const int *row4col, double *spc, int i, char *SR, char *SC, int *remaining,
+                        double *p_min) {
+    double min_val = 0.0;
+    int num_remaining = nc, sink = -1;
+    for (int it = 0; it < nc; ++it) remaining[it] = nc - it - 1;
+    memset(SR, 0, (size_t)nc + 1);
+    memset(SC, 0, (size_t)nc + 1);
+    for (int j = 0; j < nc; ++j) spc[j] = INFINITY;
+    while (sink == -1) {
+        int index = -1;
+        double lowest = INFINITY;
+        SR[i] = 1;
+        for (int it = 0; it < num_remaining; ++it) {
+            int j = remaining[it];
+            double r = min_val + cost[(size_t)i * nc + j] - u[i] - v[j];
+            if (r < spc[j]) { path[j] = i; spc[j] = r; }
+            if (spc[j] < lowest || (spc[j] == lowest && row4col[j] == -1)) { lowest = spc[j]; index = it; }
+        }
+        min_val = lowest;
+        if (min_val == INFINITY) return -1;
+        int j = remaining[index];
+        if (row4col[j] == -1) sink = j; else i = row4col[j];
+        SC[j] = 1;
+        remaining[index] = remaining[--num_remaining];
+    }
+    *p_min = min_val;
+    return sink;
+}
+
+/* cost [nr, nc] row-major; col_of_row[nr] receives the assigned column or -1 (only min(nr, nc) rows get one) */
+int oracle_lsap(const double *cost_in, int nr, int nc, int *col_of_row) {
+    for (int i = 0; i < nr; ++i) col_of_row[i] = -1;
+    if (nr <= 0 || nc <= 0 || nr > (1 << 20) || nc > (1 << 20)) return 0;
+    const int transpose = nc < nr;
+    double *cost = (double *)malloc(sizeof(double) * nr * nc);
+    int R = nr, Cn = nc;
+    if (transpose) {
+        for (int i = 0; i < nr; ++i) for (int j = 0; j < nc; ++j) cost[(size_t)j * nr + i] = cost_in[(size_t)i * nc + j];
+        R = nc; Cn = nr;
+    } else memcpy(cost, cost_in, sizeof(double) * nr * nc);
+    double *u = calloc(R, sizeof(double)), *v = calloc(Cn, sizeof(double)), *spc = malloc(sizeof(double) * Cn);
+    int *path = malloc(sizeof(int) * Cn), *col4row = malloc(sizeof(int) * R), *row4col = malloc(sizeof(int) * Cn);
+    int *remaining = malloc(sizeof(int) * Cn);
+    char *SR = malloc((size_t)Cn + 1), *SC = malloc((size_t)Cn + 1);
+    for (int j = 0; j < Cn; ++j) { path[j] = -1; row4col[j] = -1; }
+    for (int i = 0; i < R; ++i) col4row[i] = -1;
+    int rc = 0;
+    for (int cur = 0; cur < R && rc == 0; ++cur) {
+        double min_val;
+        int sink = lsap_augment(Cn, cost, u, v, path, row4col, spc, cur, SR, SC, remaining, &min_val);
+        if (sink < 0) { rc = -1; break; }
+        u[cur] += min_val;
+        for (int i = 0; i < R; ++i) if (SR[i] && i != cur) u[i] += min_val - spc[col4row[i]];
+        for (int j = 0; j < Cn; ++j) if (SC[j]) v[j] -= min_val - spc[j];
+        int j = sink;
+        while (1) {
+            int i = path[j];
+            row4col[j] = i;
+            int t = col4row[i]; col4row[i] = j; j = t;
+            if (i == cur) break;
+        }
+    }
+    if (rc == 0) {
+        if (transpose) { for (int i = 0; i < R; ++i) col_of_row[col4row[i]] = i; }
+        else for (int i = 0; i < R; ++i) col_of_row[i] = col4row[i];
+    }
+    free(cost); free(u); free(v); free(spc); free(path); free(col4row); free(row4col); free(remaining); free(SR); free(SC);
+    return rc;
+}
+
+/* torch.bucketize(x, bins) with right=False: number of boundaries strictly below x */
+static int bucket_of(float x, const float *bins, int B) {
+    int k = 0;
+    while (k < B && bins[k] < x) ++k;
+    return k;
+}
+
+/* metrics.py:8-84.  true_* [T, Dt(,2)], est_* [T, M, De(,2)], index [T, n] = the catalogs metrics.py:40 draws
+ * with torch.randint; outputs [T, n, B] float32 each. */
+void oracle_match_catalogs(const float *true_counts, const float *true_locs, const float *true_fluxes,
+                           const float *est_counts, const float *est_locs, const float *est_fluxes,
+                           const int64_t *index, const float *mag_bins, float locs_tol, float mags_tol, int T,
+                           int n, int M, int Dt, int De, int B, float *true_total, float *true_match,
+                           float *est_total, float *est_match) {
+    for (int t = 0; t < T; ++t) {
+        const int nt = (int)true_counts[t];                                   /* metrics.py:37 */
+        const float *tl = true_locs + (size_t)t * Dt * 2, *tf = true_fluxes + (size_t)t * Dt;
+        for (int k = 0; k < n; ++k) {
+            const size_t cat = (size_t)t * M + (size_t)index[(size_t)t * n + k];
+            const int ne = (int)est_counts[cat];                              /* metrics.py:43,46 */
+            const float *el = est_locs + cat * De * 2, *ef = est_fluxes + cat * De;
+            float *o_tt = true_total + ((size_t)t * n + k) * B, *o_tm = true_match + ((size_t)t * n + k) * B;
+            float *o_et = est_total + ((size_t)t * n + k) * B, *o_em = est_match + ((size_t)t * n + k) * B;
+            for (int b = 0; b < B; ++b) o_tt[b] = o_tm[b] = o_et[b] = o_em[b] = 0.f;
+            double *cost = malloc(sizeof(double) * (nt * ne + 1));
+            char *oob = malloc((size_t)nt * ne + 1);
+            float *tm = malloc(sizeof(float) * (nt + 1)), *em = malloc(sizeof(float) * (ne + 1));
+            int *col = malloc(sizeof(int) * (nt + 1));
+            for (int i = 0; i < nt; ++i) tm[i] = 22.5f - 2.5f * log10f(tf[i]);  /* utils/sdss.py:8-9 */
+            for (int j = 0; j < ne; ++j) em[j] = 22.5f - 2.5f * log10f(ef[j]);
+            for (int i = 0; i < nt; ++i)
+                for (int j = 0; j < ne; ++j) {
+                    float dx = tl[2 * i] - el[2 * j], dy = tl[2 * i + 1] - el[2 * j + 1];
+                    float dist = sqrtf(dx * dx + dy * dy);                      /* metrics.py:49-52 */
+                    int o = dist > locs_tol || fabsf(tm[i] - em[j]) > mags_tol; /* metrics.py:53-58 */
+                    oob[i * ne + j] = (char)o;
+                    cost[i * ne + j] = o ? (double)(dist + 1e20f) : (double)dist; /* metrics.py:60, float32 sum */
+                }
+            oracle_lsap(cost, nt, ne, col);
+            for (int i = 0; i < nt; ++i) {
+                int b = bucket_of(tm[i], mag_bins, B);
+                if (b < B) o_tt[b] += 1.f;
+                if (col[i] >= 0 && !oob[i * ne + col[i]]) {
+                    if (b < B) o_tm[b] += 1.f;
+                    int be = bucket_of(em[col[i]], mag_bins, B);
+                    if (be < B) o_em[be] += 1.f;
+                }
+            }
+            for (int j = 0; j < ne; ++j) { int b = bucket_of(em[j], mag_bins, B); if (b < B) o_et[b] += 1.f; }
+            free(cost); free(oob); free(tm); free(em); free(col);
+        }
+    }
+}

@@ -150,6 +150,18 @@ void oracle_prune_f32(const float *locs, const float *fluxes, int T, int N, int 
                       float tile_w, float flux_threshold, int64_t *counts, float *locs_out,
                       float *fluxes_out);
 
+/* scipy.optimize.linear_sum_assignment restated (Crouse 2016 shortest augmenting path, float64);
+ * col_of_row[nr] = assigned column or -1.  Returns 0, or -1 if infeasible. */
+int oracle_lsap(const double *cost, int nr, int nc, int *col_of_row);
+
+/* smcdet/metrics.py:8-84 (match_catalogs): per (tile, drawn catalog) Hungarian matching of true and estimated
+ * stars on location distance with location / magnitude tolerances, counted per magnitude bin */
+void oracle_match_catalogs(const float *true_counts, const float *true_locs, const float *true_fluxes,
+                           const float *est_counts, const float *est_locs, const float *est_fluxes,
+                           const int64_t *index, const float *mag_bins, float locs_tol, float mags_tol, int T,
+                           int n, int M, int Dt, int De, int B, float *true_total, float *true_match,
+                           float *est_total, float *est_match);
+
 int oracle_num_threads(void);
 void oracle_set_num_threads(int n);
 

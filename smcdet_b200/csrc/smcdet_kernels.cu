@@ -952,6 +952,112 @@ __global__ void prune_kernel(const float* __restrict__ locs, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// match_catalogs (metrics.py:8-84): one thread per (tile, drawn catalog) solves the rectangular
+// assignment problem of true vs estimated stars with scipy's algorithm (Crouse 2016 shortest
+// augmenting path, float64, same operation order -- see oracle/smcdet_oracle.c: oracle_lsap) and
+// counts total / matched stars per magnitude bin.  Evaluation utility, not a hot kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxMatch = 96;  // stars per side of one matching problem (local-memory arrays)
+
+__device__ __forceinline__ int bucket_of(float x, const float* __restrict__ bins, int B) {
+    int k = 0;  // torch.bucketize(right=False): boundaries strictly below x
+    while (k < B && bins[k] < x) ++k;
+    return k;
+}
+
+__global__ void match_kernel(const float* __restrict__ true_counts, const float* __restrict__ true_locs,
+                             const float* __restrict__ true_fluxes, const float* __restrict__ est_counts,
+                             const float* __restrict__ est_locs, const float* __restrict__ est_fluxes,
+                             const int64_t* __restrict__ index, const float* __restrict__ mag_bins, float locs_tol,
+                             float mags_tol, float* __restrict__ true_total, float* __restrict__ true_match,
+                             float* __restrict__ est_total, float* __restrict__ est_match, int32_t* status, int T,
+                             int n, int M, int Dt, int De, int B) {
+    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob >= T * n) return;
+    const int t = prob / n;
+    const size_t cat = (size_t)t * M + (size_t)index[prob];
+    float* o_tt = true_total + (size_t)prob * B;
+    float* o_tm = true_match + (size_t)prob * B;
+    float* o_et = est_total + (size_t)prob * B;
+    float* o_em = est_match + (size_t)prob * B;
+    for (int b = 0; b < B; ++b) { o_tt[b] = 0.f; o_tm[b] = 0.f; o_et[b] = 0.f; o_em[b] = 0.f; }
+    const int nt = (int)true_counts[t], ne = (int)est_counts[cat];
+    if (nt < 0 || ne < 0 || nt > kMaxMatch || ne > kMaxMatch || nt > Dt || ne > De) {
+        if (status) atomicOr(status, 4);
+        return;
+    }
+    const float* tl = true_locs + (size_t)t * Dt * 2;
+    const float* el = est_locs + cat * De * 2;
+    float tm[kMaxMatch], em[kMaxMatch];
+    for (int i = 0; i < nt; ++i) tm[i] = 22.5f - mul_unfused(2.5f, log10f(true_fluxes[(size_t)t * Dt + i]));
+    for (int j = 0; j < ne; ++j) em[j] = 22.5f - mul_unfused(2.5f, log10f(est_fluxes[cat * De + j]));
+    for (int i = 0; i < nt; ++i) { const int b = bucket_of(tm[i], mag_bins, B); if (b < B) o_tt[b] += 1.f; }
+    for (int j = 0; j < ne; ++j) { const int b = bucket_of(em[j], mag_bins, B); if (b < B) o_et[b] += 1.f; }
+    if (nt == 0 || ne == 0) return;
+
+    // rows = the smaller side (scipy transposes when there are more rows than columns)
+    const bool tr = ne < nt;
+    const int R = tr ? ne : nt, Cn = tr ? nt : ne;
+    auto pair_cost = [&](int r, int c, bool& oob) -> double {
+        const int i = tr ? c : r, j = tr ? r : c;   // i: true star, j: estimated star
+        const float dx = tl[2 * i] - el[2 * j], dy = tl[2 * i + 1] - el[2 * j + 1];
+        const float dist = sqrtf(mul_unfused(dx, dx) + mul_unfused(dy, dy));
+        oob = dist > locs_tol || fabsf(tm[i] - em[j]) > mags_tol;
+        return oob ? (double)(dist + 1e20f) : (double)dist;   // metrics.py:60 adds the penalty in float32
+    };
+    double u[kMaxMatch], v[kMaxMatch], spc[kMaxMatch];
+    int path[kMaxMatch], col4row[kMaxMatch], row4col[kMaxMatch], remaining[kMaxMatch];
+    bool SR[kMaxMatch], SC[kMaxMatch];
+    for (int i = 0; i < R; ++i) { u[i] = 0.0; col4row[i] = -1; }
+    for (int j = 0; j < Cn; ++j) { v[j] = 0.0; path[j] = -1; row4col[j] = -1; }
+    const double inf = (double)INFINITY;
+    for (int cur = 0; cur < R; ++cur) {
+        double min_val = 0.0;
+        int num_remaining = Cn, sink = -1, i = cur;
+        for (int it = 0; it < Cn; ++it) { remaining[it] = Cn - it - 1; SC[it] = false; spc[it] = inf; }
+        for (int r = 0; r < R; ++r) SR[r] = false;
+        while (sink == -1) {
+            int idx = -1;
+            double lowest = inf;
+            SR[i] = true;
+            for (int it = 0; it < num_remaining; ++it) {
+                const int j = remaining[it];
+                bool o;
+                const double r = min_val + pair_cost(i, j, o) - u[i] - v[j];
+                if (r < spc[j]) { path[j] = i; spc[j] = r; }
+                if (spc[j] < lowest || (spc[j] == lowest && row4col[j] == -1)) { lowest = spc[j]; idx = it; }
+            }
+            min_val = lowest;
+            const int j = remaining[idx];
+            if (row4col[j] == -1) sink = j; else i = row4col[j];
+            SC[j] = true;
+            remaining[idx] = remaining[--num_remaining];
+        }
+        u[cur] += min_val;
+        for (int r = 0; r < R; ++r) if (SR[r] && r != cur) u[r] += min_val - spc[col4row[r]];
+        for (int j = 0; j < Cn; ++j) if (SC[j]) v[j] -= min_val - spc[j];
+        int j = sink;
+        while (true) {
+            const int r = path[j];
+            row4col[j] = r;
+            const int old = col4row[r];
+            col4row[r] = j;
+            j = old;
+            if (r == cur) break;
+        }
+    }
+    for (int r = 0; r < R; ++r) {
+        bool o;
+        pair_cost(r, col4row[r], o);
+        if (o) continue;
+        const int i = tr ? col4row[r] : r, j = tr ? r : col4row[r];
+        const int bt = bucket_of(tm[i], mag_bins, B), be = bucket_of(em[j], mag_bins, B);
+        if (bt < B) o_tm[bt] += 1.f;
+        if (be < B) o_em[be] += 1.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dispatch over (model, tile, threads-per-particle)
 // ---------------------------------------------------------------------------------------------
 // smallest TPP whose grid fills the machine, within what is instantiated for the tile size
@@ -1241,6 +1347,25 @@ int smcdet_prune(const float* locs, const float* fluxes, float tile_h, float til
                                                                                   flux_threshold, counts_out, locs_out,
                                                                                   fluxes_out, TN, D);
     return launch_status("prune_kernel");
+}
+
+int smcdet_match_catalogs(const float* true_counts, const float* true_locs, const float* true_fluxes,
+                          const float* est_counts, const float* est_locs, const float* est_fluxes, const int64_t* index,
+                          const float* mag_bins, float locs_tol, float mags_tol, float* true_total, float* true_match,
+                          float* est_total, float* est_match, int32_t* status, int T, int n, int M, int Dt, int De,
+                          int B, void* stream) {
+    SMC_REQUIRE(true_counts && true_locs && true_fluxes && est_counts && est_locs && est_fluxes && index && mag_bins,
+                SMCDET_E_INVALID, "smcdet_match_catalogs: null input pointer");
+    SMC_REQUIRE(true_total && true_match && est_total && est_match, SMCDET_E_INVALID,
+                "smcdet_match_catalogs: null output pointer");
+    SMC_REQUIRE(T > 0 && n > 0 && M > 0 && Dt > 0 && De > 0 && B > 0, SMCDET_E_INVALID,
+                "smcdet_match_catalogs: non-positive size");
+    const long long probs = (long long)T * n;
+    SMC_REQUIRE(probs < (1LL << 31), SMCDET_E_INVALID, "smcdet_match_catalogs: too many matching problems");
+    SMC_LAUNCH(match_kernel, (unsigned)((probs + 63) / 64), 64, 0, (cudaStream_t)stream, true_counts, true_locs,
+               true_fluxes, est_counts, est_locs, est_fluxes, index, mag_bins, locs_tol, mags_tol, true_total,
+               true_match, est_total, est_match, status, T, n, M, Dt, De, B);
+    return launch_status("match_kernel");
 }
 
 }  // extern "C"

@@ -196,3 +196,17 @@ class GpuBackend:
         self._check(self.lib.smcdet_prune(self._p(locs), self._p(fluxes), tile_h, tile_w, thr, self._p(counts),
                                           self._p(lo), self._p(fo), T, N, D, self._stream()))
         return counts.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
+
+    def match_catalogs(self, true_counts, true_locs, true_fluxes, est_counts, est_locs, est_fluxes, index, locs_tol,
+                       mags_tol, mag_bins):
+        t = self.torch
+        tc, tl, tf, ec, el, ef = (self._d(a) for a in (true_counts, true_locs, true_fluxes, est_counts, est_locs, est_fluxes))
+        index, bins = self._d(index, np.int64), self._d(mag_bins)
+        (T, Dt), (_, M, De), n, B = tf.shape, ef.shape, index.shape[1], bins.shape[0]
+        out = [self._z((T, n, B), t.float32) for _ in range(4)]
+        status = self._z((1,), t.int32)
+        self._check(self.lib.smcdet_match_catalogs(self._p(tc), self._p(tl), self._p(tf), self._p(ec), self._p(el),
+                                                   self._p(ef), self._p(index), self._p(bins), locs_tol, mags_tol,
+                                                   *[self._p(o) for o in out], self._p(status), T, n, M, Dt, De, B,
+                                                   self._stream()))
+        return [o.cpu().numpy() for o in out] + [int(status.item())]

@@ -183,3 +183,15 @@ def prune(locs, fluxes, tile_h, tile_w, thr):
     lo, fo = np.zeros_like(locs), np.zeros_like(fluxes)
     check(lib().smcdet_prune(_p(locs), _p(fluxes), tile_h, tile_w, thr, _p(counts), _p(lo), _p(fo), T, N, D, None))
     return counts, lo, fo
+
+
+def match_catalogs(true_counts, true_locs, true_fluxes, est_counts, est_locs, est_fluxes, index, locs_tol, mags_tol,
+                   mag_bins):
+    tc, tl, tf, ec, el, ef = (_f(a) for a in (true_counts, true_locs, true_fluxes, est_counts, est_locs, est_fluxes))
+    index, bins = np.ascontiguousarray(index, dtype=np.int64), _f(mag_bins)
+    (T, Dt), (_, M, De), n, B = tf.shape, ef.shape, index.shape[1], bins.shape[0]
+    out = [np.zeros((T, n, B), np.float32) for _ in range(4)]
+    status = np.zeros(1, np.int32)
+    check(lib().smcdet_match_catalogs(_p(tc), _p(tl), _p(tf), _p(ec), _p(el), _p(ef), _p(index), _p(bins), locs_tol,
+                                      mags_tol, *[_p(o) for o in out], _p(status), T, n, M, Dt, De, B, None))
+    return out + [int(status[0])]

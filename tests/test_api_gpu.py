@@ -699,3 +699,32 @@ def test_count_stratified_smc_against_exact_evidences():
     assert agg.has_run and abs(float((agg.counts == 1).float().mean()) - post[1]) < 0.01
     with pytest.raises(ValueError):
         CountStratifiedSMC(image, 8, prior, model, mh, 10, 0.5, "stratified")
+
+
+def test_metrics_module_matches_reference():
+    """smcdet_b200.metrics.match_catalogs / compute_precision_recall_f1 against the reference's outputs on the same
+    drawn catalogs (metrics.py:8-92)."""
+    from smcdet_b200 import metrics
+
+    g = Golden("match_catalogs")
+    m = g.meta
+    res = metrics.match_catalogs(cu(g["true_counts"]), cu(g["true_locs"]), cu(g["true_fluxes"]), cu(g["est_counts"]),
+                                 cu(g["est_locs"]), cu(g["est_fluxes"]), m["n"], m["locs_tol"], m["mags_tol"],
+                                 torch.from_numpy(g["mag_bins"]), index=cu(g["index"]))
+    for got, name in zip(res, ["true_total", "true_match", "est_total", "est_match"]):
+        assert got.is_cuda and np.array_equal(got.cpu().numpy(), g[name]), name
+    p, r, f1 = metrics.compute_precision_recall_f1(*res)
+    assert np.allclose(p.cpu().numpy(), g["precision"]) and np.allclose(r.cpu().numpy(), g["recall"])
+    assert np.allclose(f1.cpu().numpy(), g["f1"])
+    # own draw of the catalogs, int64 counts as SMCsampler.pruned_counts has them
+    torch.manual_seed(0)
+    res2 = metrics.match_catalogs(cu(g["true_counts"]), cu(g["true_locs"]), cu(g["true_fluxes"]),
+                                  cu(g["est_counts"]).long(), cu(g["est_locs"]), cu(g["est_fluxes"]), 5, 0.5, 0.5,
+                                  torch.from_numpy(g["mag_bins"]))
+    assert res2[0].shape == (m["T"], 5, len(g["mag_bins"])) and float(res2[1].sum()) > 0
+    assert torch.equal(res2[0][:, 0], res[0][:, 0])          # true totals do not depend on the draw
+    with pytest.raises(ValueError):
+        big = cu(g["true_counts"]).clone()
+        big[0] = 1000
+        metrics.match_catalogs(big, cu(g["true_locs"]), cu(g["true_fluxes"]), cu(g["est_counts"]), cu(g["est_locs"]),
+                               cu(g["est_fluxes"]), 2, 0.5, 0.5, torch.from_numpy(g["mag_bins"]))

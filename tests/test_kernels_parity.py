@@ -455,3 +455,43 @@ def test_many_stars_and_ragged_particle_counts(backend):
                      tiles, counts, locs, fluxes, tau, comp, tape["u_loc"], tape["u_flux"], tape["u_acc"])
         assert np.array_equal(r["accept"], o["accept"]), (D, N)
         assert np.max(np.abs(r["locs"] - o["locs"])) < 1e-5 and np.max(np.abs(r["fluxes"] / o["fluxes"] - 1)) < RTOL
+
+
+def test_match_catalogs_equals_the_reference(backend):
+    """smcdet_match_catalogs against metrics.match_catalogs of the reference (scipy's linear_sum_assignment on
+    every (tile, catalog) problem) on the catalogs the reference drew: per-bin totals and matches identical."""
+    g = Golden("match_catalogs")
+    m = g.meta
+    out = backend.match_catalogs(g["true_counts"], g["true_locs"], g["true_fluxes"], g["est_counts"], g["est_locs"],
+                                 g["est_fluxes"], g["index"], m["locs_tol"], m["mags_tol"], g["mag_bins"])
+    assert out[4] == 0
+    for got, name in zip(out[:4], ["true_total", "true_match", "est_total", "est_match"]):
+        assert np.array_equal(got, g[name]), name
+    assert g["true_match"].sum() > 100 and g["true_match"].sum() < g["true_total"].sum()
+    # more stars than the tensors hold: flagged, not read out of bounds
+    bad = g["true_counts"].copy()
+    bad[0] = 500
+    assert backend.match_catalogs(bad, g["true_locs"], g["true_fluxes"], g["est_counts"], g["est_locs"], g["est_fluxes"],
+                                  g["index"], m["locs_tol"], m["mags_tol"], g["mag_bins"])[4] == 4
+
+
+def test_match_catalogs_many_random_problems_against_oracle(backend):
+    """Crowded random catalogs (ties in the penalised costs included): the kernel's assignment counts equal the
+    oracle's, whose solver is checked against scipy itself in test_oracle_golden.py."""
+    rng = np.random.default_rng(5)
+    T, Dt, M, De, n = 40, 24, 6, 24, 6
+    tc = rng.integers(0, Dt + 1, T).astype(np.float32)
+    ec = rng.integers(0, De + 1, (T, M)).astype(np.float32)
+    tl = (rng.random((T, Dt, 2)) * 4).astype(np.float32)
+    el = (rng.random((T, M, De, 2)) * 4).astype(np.float32)
+    el[:, 0] = np.round(el[:, 0] * 2) / 2       # exact ties
+    tl[::2] = np.round(tl[::2] * 2) / 2
+    tf = (10 ** (rng.random((T, Dt)) * 2)).astype(np.float32)
+    ef = (10 ** (rng.random((T, M, De)) * 2)).astype(np.float32)
+    index = rng.integers(0, M, (T, n))
+    bins = np.arange(17.0, 23.0, 1.0, dtype=np.float32)
+    want = O.match_catalogs(tc, tl, tf, ec, el, ef, index, 0.8, 1.0, bins)
+    got = backend.match_catalogs(tc, tl, tf, ec, el, ef, index, 0.8, 1.0, bins)
+    for w, g_ in zip(want, got[:4]):
+        assert np.array_equal(w, g_)
+    assert want[1].sum() > 500

@@ -131,3 +131,37 @@ def test_exact_count_evidences_fixture_is_consistent():
     lp = np.array([float(g["exact_logz0"]) - rate, float(g["exact_logz1"]) + np.log(rate) - rate])
     post = np.exp(lp - lp.max())
     assert np.allclose(post / post.sum(), g["exact_count_posterior"], atol=1e-9)
+
+
+def test_oracle_lsap_is_scipy_linear_sum_assignment():
+    """The assignment solver restated in oracle/smcdet_oracle.c returns scipy's assignment exactly, also where the
+    float32 1e20 penalty of metrics.py:60 absorbs the distances and where costs tie."""
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+
+    from goldenlib import O
+
+    rng = np.random.default_rng(0)
+    for trial in range(3000):
+        nr, nc = rng.integers(0, 10), rng.integers(0, 10)
+        d = rng.random((nr, nc)).astype(np.float32) * 3
+        oob = rng.random((nr, nc)) < rng.random()
+        cost = (d + oob.astype(np.float32) * np.float32(1e20)).astype(np.float32)
+        if trial % 3 == 0:
+            cost = np.round(cost, 1)
+        r, c = linear_sum_assignment(cost)
+        r2, c2 = O.lsap(cost.astype(np.float64))
+        assert np.array_equal(r, r2) and np.array_equal(c, c2)
+
+
+def test_oracle_match_catalogs_reproduces_reference():
+    import numpy as np
+
+    from goldenlib import Golden, O
+
+    g = Golden("match_catalogs")
+    m = g.meta
+    out = O.match_catalogs(g["true_counts"], g["true_locs"], g["true_fluxes"], g["est_counts"], g["est_locs"],
+                           g["est_fluxes"], g["index"], m["locs_tol"], m["mags_tol"], g["mag_bins"])
+    for got, name in zip(out, ["true_total", "true_match", "est_total", "est_match"]):
+        assert np.array_equal(got, g[name]), name

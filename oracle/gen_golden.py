@@ -755,6 +755,161 @@ def case_match():
 CASES["match"] = case_match
 
 
+class AggregateMH(SingleComponentMH):
+    """REPAIR of the reference for the tree merge: ``Aggregate.mutate`` calls
+    ``MutationKernel.run`` with nine arguments (aggregate.py:176-187) but no kernel at the reference's HEAD accepts
+    them.  This is the reference's single-site random-walk sweep (kernel.py:26-130: same truncated-normal proposals,
+    same ratio, same arithmetic blend of the cached target) with the two changes the merge needs: the target is
+    ``Aggregate.log_target`` evaluated through ``Aggregate.unjoin`` (aggregate.py:105-128, :267-324), and the updated
+    component is drawn among the catalog's live stars (j < count) -- merged catalogs have varying counts, and moving
+    an empty slot would create a star the prior never sees."""
+
+    def run(self, data, counts, locs, fluxes, temperature, log_target, unjoin, axis, ChildImageModel):
+        D = fluxes.shape[-1]
+
+        def target(l, f):
+            cd, _, cl, cf = unjoin(axis, data, l, f)
+            return log_target(axis, ChildImageModel, cd, cl, cf, data, counts, l, f, temperature)
+
+        live = (torch.arange(D) < counts.unsqueeze(-1)).float()
+        any_live = live.sum(-1) > 0
+        probs = live + (~any_live).unsqueeze(-1).float()          # empty catalogs: any slot, the move is masked out
+        locs_prev, fluxes_prev = locs, fluxes
+        for it in range(self.num_iters):
+            comp = torch.multinomial(probs.flatten(0, 2), 1).view(counts.shape)
+            mask = torch.nn.functional.one_hot(comp, D).float() * live
+            lp = locs_prev * (1 - mask.unsqueeze(-1)) + (
+                TruncatedDiagonalMVN(locs_prev, self.locs_stdev, self.locs_min, self.locs_max).sample() * mask.unsqueeze(-1))
+            fp = fluxes_prev * (1 - mask) + (
+                TruncatedDiagonalMVN(fluxes_prev, self.fluxes_stdev, self.fluxes_min, self.fluxes_max).sample() * mask)
+            num = target(lp, fp)
+            fl_prev = fluxes_prev.clamp(self.fluxes_min, self.fluxes_max)   # empty slots (flux 0) are masked out below
+            fl_prop = fp.clamp(self.fluxes_min, self.fluxes_max)
+            nq = (TruncatedDiagonalMVN(lp, self.locs_stdev, self.locs_min, self.locs_max).log_prob(locs_prev)
+                  * mask.unsqueeze(-1)).sum([-2, -1]) + (
+                TruncatedDiagonalMVN(fl_prop, self.fluxes_stdev, self.fluxes_min, self.fluxes_max).log_prob(fl_prev) * mask).sum(-1)
+            if it == 0:
+                den = target(locs_prev, fluxes_prev)
+            dq = (TruncatedDiagonalMVN(locs_prev, self.locs_stdev, self.locs_min, self.locs_max).log_prob(lp)
+                  * mask.unsqueeze(-1)).sum([-2, -1]) + (
+                TruncatedDiagonalMVN(fl_prev, self.fluxes_stdev, self.fluxes_min, self.fluxes_max).log_prob(fl_prop) * mask).sum(-1)
+            alpha = ((num + nq) - (den + dq)).exp().clamp(max=1)
+            accept = torch.rand_like(alpha) <= alpha
+            a_l, a_f = accept.unsqueeze(-1).unsqueeze(-1), accept.unsqueeze(-1)
+            locs_prev = lp * a_l + locs_prev * (~a_l)
+            fluxes_prev = fp * a_f + fluxes_prev * (~a_f)
+            den = num * accept + den * (~accept)
+        return [locs_prev, fluxes_prev, accept.float().mean(-1)]
+
+
+def case_aggregate():
+    """The divide-and-conquer tree merge (aggregate.py:523-593) on a 2 x 2 grid of 8 x 8 tiles, recorded stage by
+    stage with every random draw.  The reference's own Aggregate runs with two repairs:
+    a no-op ``ImageModel.update_psf_grid`` (aggregate.py:241 calls a method that no longer exists; the PSF is
+    evaluated on the fly from image_height/width) and the nine-argument mutation kernel above."""
+    from smcdet.aggregate import Aggregate
+
+    torch.manual_seed(97)
+    tile, D, pad, nside, N, iters = 8, 3, 2, 2, 128, 4
+    im, pr, meta = m71_objects(tile, D, pad)
+    big_im, big_pr, _ = m71_objects(tile * nside, 6, pad)
+    c, l, f = big_pr.sample(num_tiles_per_side=1, stratify_by_count=True, num_catalogs_per_count=1)
+    f = f.clamp(min=4 * M71_DETECTION)
+    image = big_im.sample(l, f)[0, 0, :, :, 0].contiguous()
+    mh = SingleComponentMH(8, 0.1, 2.5, pr.flux_lower, pr.flux_upper)
+    smp = SMCsampler(image, tile, pr, im, mh, N, 0.5, "multinomial", M71_DETECTION, 100, print_every=1000)
+    smp.run()
+    type(im).update_psf_grid = lambda self: None
+    aggmh = AggregateMH(iters, 0.1, 2.5, pr.flux_lower, pr.flux_upper)
+    agg = Aggregate(smp.Prior, smp.ImageModel, aggmh, smp.tiled_image, smp.counts, smp.locs, smp.fluxes, smp.weights,
+                    smp.log_normalizing_constant, M71_DETECTION, "multinomial", 0.5, print_every=10**9)
+    arrays = dict(image=image, leaf_counts=smp.counts, leaf_locs=smp.locs, leaf_fluxes=smp.fluxes,
+                  leaf_weights=smp.weights, leaf_logz=smp.log_normalizing_constant)
+    events, draws, stage = [], [], ["init"]
+
+    def lnc_array(lnc):
+        J = max(len(torch.as_tensor(x).reshape(-1)) for row in lnc for x in row)
+        out = torch.full((len(lnc), len(lnc[0]), J), float("nan"))
+        for a, row in enumerate(lnc):
+            for b, x in enumerate(row):
+                x = torch.as_tensor(x).reshape(-1)
+                out[a, b, : x.shape[0]] = x
+        return out
+
+    def strata_array(npc):
+        J = max(len(x) for row in npc for x in row)
+        out = torch.zeros(len(npc), len(npc[0]), J, dtype=torch.int64)
+        for a, row in enumerate(npc):
+            for b, x in enumerate(row):
+                out[a, b, : len(x)] = torch.tensor(x)
+        return out
+
+    def snap(name, **extra):
+        k = len(events)
+        events.append(name)
+        rec = dict(counts=agg.counts, locs=agg.locs, fluxes=agg.fluxes, weights=agg.weights, data=agg.data,
+                   temperature=agg.temperature, temperature_prev=agg.temperature_prev,
+                   logz=lnc_array(agg.log_normalizing_constant), **extra)
+        if agg.num_catalogs_per_count[0][0] is not None and len(agg.num_catalogs_per_count) == agg.numH:
+            rec["strata"] = strata_array(agg.num_catalogs_per_count)
+        if agg.weights_intracount is not None:
+            rec["weights_intracount"] = agg.weights_intracount
+        if hasattr(agg, "loglik_diff"):
+            rec["loglik_diff"] = agg.loglik_diff
+        if agg.mutation_acc_rates is not None:
+            rec["acc"] = agg.mutation_acc_rates
+        for key, v in rec.items():
+            arrays[f"e{k:03d}_{key}"] = v.clone() if isinstance(v, torch.Tensor) else v
+        mine = [d for d in draws if d[0] == k]
+        for kind in ("rand", "rand_like", "multinomial"):
+            sel = [d[2] for d in mine if d[1] == kind]
+            if sel:
+                if all(x.shape == sel[0].shape for x in sel):
+                    arrays[f"e{k:03d}_draw_{kind}"] = torch.stack(sel)
+                else:
+                    arrays[f"e{k:03d}_draw_{kind}_cat"] = torch.cat([x.reshape(-1) for x in sel])
+
+    def wrap(name):
+        orig = getattr(agg, name)
+
+        def wrapped(*a, **kw):
+            stage[0] = name
+            out = orig(*a, **kw)
+            snap(name)
+            return out
+
+        setattr(agg, name, wrapped)
+
+    for name in ("merge", "sort_by_count", "temper", "update_weights", "resample_intracount", "mutate"):
+        wrap(name)
+    real = dict(rand=torch.rand, rand_like=torch.rand_like, multinomial=torch.multinomial, tmn=torch.Tensor.multinomial)
+
+    def rec_call(kind, fn):
+        def call(*a, **kw):
+            out = fn(*a, **kw)
+            draws.append((len(events), kind, out.clone()))
+            return out
+        return call
+
+    torch.rand = rec_call("rand", real["rand"])
+    torch.rand_like = rec_call("rand_like", real["rand_like"])
+    torch.multinomial = rec_call("multinomial", real["multinomial"])
+    torch.Tensor.multinomial = rec_call("multinomial", real["tmn"])
+    try:
+        agg.run()
+    finally:
+        torch.rand, torch.rand_like, torch.multinomial = real["rand"], real["rand_like"], real["multinomial"]
+        torch.Tensor.multinomial = real["tmn"]
+    snap("final", pruned_counts=agg.pruned_counts, pruned_locs=agg.pruned_locs, pruned_fluxes=agg.pruned_fluxes)
+    print("events:", len(events), "final counts", agg.counts.unique(return_counts=True), "D", agg.locs.shape)
+    meta.update(nside=nside, N=N, iters=iters, events=events, flux_threshold=M71_DETECTION, locs_stdev=0.1,
+                fluxes_stdev=2.5, fluxes_min=float(pr.flux_lower), fluxes_max=float(pr.flux_upper), ess_prop=0.5)
+    save("aggregate_m71", meta, **arrays)
+
+
+CASES["aggregate"] = case_aggregate
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = sys.argv[1:] or list(CASES)

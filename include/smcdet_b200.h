@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMCDET_ABI_VERSION 3
+#define SMCDET_ABI_VERSION 4
 
 enum {
     SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
@@ -221,6 +221,37 @@ int smcdet_match_catalogs(const float *true_counts, const float *true_locs, cons
                           const int64_t *index, const float *mag_bins, float locs_tol, float mags_tol,
                           float *true_total, float *true_match, float *est_total, float *est_match,
                           int32_t *status, int T, int n, int M, int Dt, int De, int B, void *stream);
+
+/* ---- Aggregate tree merge (smcdet/aggregate.py) -------------------------------------------------
+ * smcdet_agg_join: drop_sources_from_overlap + join (aggregate.py:189-265) for a [nH, nW] grid of child tiles
+ * with M star slots each, merging neighbours along `axis` (0: rows, 1: columns); `dim` = the child tile's size
+ * along that axis.  Outputs on the parent grid ([nH/2, nW] or [nH, nW/2]) with 2*M slots: counts_out [.., N]
+ * (float32, kept stars), locs_out [.., N, 2M, 2], fluxes_out [.., N, 2M]; the caller truncates to the largest
+ * count as the reference does (aggregate.py:236-252). */
+int smcdet_agg_join(const float *locs, const float *fluxes, int axis, float dim, float *counts_out,
+                    float *locs_out, float *fluxes_out, int nH, int nW, int N, int M, void *stream);
+
+/* smcdet_agg_unjoin: Aggregate.unjoin (aggregate.py:267-324) of [T, N, D] parent catalogs at loc_axis <= half;
+ * children parent-major: counts_out [T, 2, N], locs_out [T, 2, N, D, 2], fluxes_out [T, 2, N, D]. */
+int smcdet_agg_unjoin(const float *locs, const float *fluxes, int axis, float half, float *counts_out,
+                      float *locs_out, float *fluxes_out, int T, int N, int D, void *stream);
+
+/* smcdet_agg_mutate: the mutation step of the merge (Aggregate.mutate, aggregate.py:176-187) under
+ * Aggregate.log_target (aggregate.py:105-128):
+ *     log prior(parent) + (1 - tau) * [loglik(child 1) + loglik(child 2)] + tau * loglik(parent).
+ * Single-site random-walk sweeps as in smcdet_mh_mutate (kernel.py:26-130) with the updated star drawn among
+ * the catalog's live stars (j < count); no kernel of the reference's HEAD takes the nine arguments
+ * aggregate.py passes, see DESIGN.md section 8.  tiles [T, h, w] are the PARENT tiles (h x w = 16x8, 16x16,
+ * 32x16 or 32x32; axis 0 for h = 2w, axis 1 for h = w); `prior` / `mh` carry the parent's location box.
+ * num_iters = 0 only evaluates: loglik_diff_out [T, N] = loglik(parent) - sum of the children's
+ * (aggregate.py:539-541); parent_loglik_out / child_loglik_out / log_target_out are optional [T, N]. */
+int smcdet_agg_mutate(const smcdet_model_params *model, const smcdet_prior_params *prior,
+                      const smcdet_mh_params *mh, int axis, const float *tiles, const float *counts,
+                      float *locs, float *fluxes, const float *tau, float *loglik_diff_out,
+                      float *parent_loglik_out, float *child_loglik_out, float *log_target_out,
+                      float *acc_rate, const smcdet_draw_tape *tape, const smcdet_mh_trace *trace,
+                      uint64_t seed, uint64_t offset, const int64_t *tile_ids, const int32_t *active,
+                      int T, int N, int D, int h, int w, void *stream);
 
 #ifdef __cplusplus
 }

@@ -803,14 +803,16 @@ class AggregateMH(SingleComponentMH):
 
 
 def case_aggregate():
-    """The divide-and-conquer tree merge (aggregate.py:523-593) on a 2 x 2 grid of 8 x 8 tiles, recorded stage by
-    stage with every random draw.  The reference's own Aggregate runs with two repairs:
-    a no-op ``ImageModel.update_psf_grid`` (aggregate.py:241 calls a method that no longer exists; the PSF is
-    evaluated on the fly from image_height/width) and the nine-argument mutation kernel above."""
+    """Building blocks of the divide-and-conquer tree merge (aggregate.py:189-324, :105-128, :533-541) on a 2 x 2 grid
+    of 8 x 8 tiles, both merge axes: the reference's own drop_sources_from_overlap / join / unjoin / log_target, and
+    the repaired nine-argument mutation kernel above with every draw recorded.  Aggregate.run() itself cannot be
+    recorded end to end: besides the two repairs (a no-op ImageModel.update_psf_grid for aggregate.py:241, the
+    kernel) its per-count evidence bookkeeping turns into -3.4e38 / nan for the one-stratum tiles SMCsampler
+    produces at HEAD (aggregate.py:372-399 compares counts AFTER the in-place drop with the strata before it)."""
     from smcdet.aggregate import Aggregate
 
     torch.manual_seed(97)
-    tile, D, pad, nside, N, iters = 8, 3, 2, 2, 128, 4
+    tile, D, pad, nside, N, iters = 8, 3, 2, 2, 96, 5
     im, pr, meta = m71_objects(tile, D, pad)
     big_im, big_pr, _ = m71_objects(tile * nside, 6, pad)
     c, l, f = big_pr.sample(num_tiles_per_side=1, stratify_by_count=True, num_catalogs_per_count=1)
@@ -823,87 +825,74 @@ def case_aggregate():
     aggmh = AggregateMH(iters, 0.1, 2.5, pr.flux_lower, pr.flux_upper)
     agg = Aggregate(smp.Prior, smp.ImageModel, aggmh, smp.tiled_image, smp.counts, smp.locs, smp.fluxes, smp.weights,
                     smp.log_normalizing_constant, M71_DETECTION, "multinomial", 0.5, print_every=10**9)
-    arrays = dict(image=image, leaf_counts=smp.counts, leaf_locs=smp.locs, leaf_fluxes=smp.fluxes,
-                  leaf_weights=smp.weights, leaf_logz=smp.log_normalizing_constant)
-    events, draws, stage = [], [], ["init"]
+    arrays = dict(image=image, leaf_data=smp.tiled_image.contiguous(), leaf_counts=smp.counts, leaf_locs=smp.locs,
+                  leaf_fluxes=smp.fluxes)
+    from copy import deepcopy
 
-    def lnc_array(lnc):
-        J = max(len(torch.as_tensor(x).reshape(-1)) for row in lnc for x in row)
-        out = torch.full((len(lnc), len(lnc[0]), J), float("nan"))
-        for a, row in enumerate(lnc):
-            for b, x in enumerate(row):
-                x = torch.as_tensor(x).reshape(-1)
-                out[a, b, : x.shape[0]] = x
-        return out
+    data, counts, locs, fluxes = agg.data, smp.counts.clone(), smp.locs.clone(), smp.fluxes.clone()
+    # a few hand-placed stars on the decision boundaries of drop / unjoin
+    locs[0, 0, 0, 0, 0] = 8.0          # exactly on the shared edge of an even tile: dropped (needs loc < dim)
+    locs[1, 0, 1, 1, 0] = 1e-3         # just inside an odd tile: kept
+    locs[0, 1, 2, 2, 1] = -0.5         # in the padding of an odd-column tile (level 1): dropped there
+    for level in range(2):
+        axis = level % 2
+        child_model = deepcopy(agg.ImageModel)
+        cs, ls, fs = agg.drop_sources_from_overlap(axis, counts.clone(), locs.clone(), fluxes.clone())
+        arrays[f"L{level}_in_counts"], arrays[f"L{level}_in_locs"], arrays[f"L{level}_in_fluxes"] = counts, locs, fluxes
+        arrays[f"L{level}_drop_counts"], arrays[f"L{level}_drop_locs"], arrays[f"L{level}_drop_fluxes"] = cs, ls, fs
+        data, counts, locs, fluxes = agg.join(axis, data, cs.clone(), ls.clone(), fs.clone())
+        data = data.contiguous()
+        agg.data, agg.counts, agg.locs, agg.fluxes = data, counts, locs, fluxes
+        arrays[f"L{level}_data"], arrays[f"L{level}_counts"] = data, counts
+        arrays[f"L{level}_locs"], arrays[f"L{level}_fluxes"] = locs, fluxes
+        cd, cc, cl, cf = agg.unjoin(axis, data, locs, fluxes)
+        arrays[f"L{level}_child_data"], arrays[f"L{level}_child_counts"] = cd.contiguous(), cc
+        arrays[f"L{level}_child_locs"], arrays[f"L{level}_child_fluxes"] = cl, cf
+        child_ll = child_model.loglikelihood(cd, cl, cf)
+        parent_ll = agg.ImageModel.loglikelihood(data, locs, fluxes)
+        arrays[f"L{level}_child_loglik"], arrays[f"L{level}_parent_loglik"] = child_ll, parent_ll
+        arrays[f"L{level}_loglik_diff"] = parent_ll - child_ll.unfold(axis, 2, 2).sum(-1)   # aggregate.py:539-541
+        tau = torch.linspace(0.15, 0.85, agg.numH * agg.numW).reshape(agg.numH, agg.numW)
+        arrays[f"L{level}_tau"] = tau
+        arrays[f"L{level}_log_target"] = agg.log_target(axis, child_model, cd, cl, cf, data, counts, locs, fluxes, tau)
+        arrays[f"L{level}_logprior"] = agg.Prior.log_prob(counts, locs, fluxes)
+        # the repaired mutation kernel, with its draws recorded: after 1..iters sweeps from the same start
+        agg.temperature = tau
+        tape_rand, tape_mn, tape_like = [], [], []
+        real = dict(rand=torch.rand, rand_like=torch.rand_like, multinomial=torch.multinomial)
 
-    def strata_array(npc):
-        J = max(len(x) for row in npc for x in row)
-        out = torch.zeros(len(npc), len(npc[0]), J, dtype=torch.int64)
-        for a, row in enumerate(npc):
-            for b, x in enumerate(row):
-                out[a, b, : len(x)] = torch.tensor(x)
-        return out
+        def rec(store, fn):
+            def call(*a, **kw):
+                out = fn(*a, **kw)
+                store.append(out.clone())
+                return out
+            return call
 
-    def snap(name, **extra):
-        k = len(events)
-        events.append(name)
-        rec = dict(counts=agg.counts, locs=agg.locs, fluxes=agg.fluxes, weights=agg.weights, data=agg.data,
-                   temperature=agg.temperature, temperature_prev=agg.temperature_prev,
-                   logz=lnc_array(agg.log_normalizing_constant), **extra)
-        if agg.num_catalogs_per_count[0][0] is not None and len(agg.num_catalogs_per_count) == agg.numH:
-            rec["strata"] = strata_array(agg.num_catalogs_per_count)
-        if agg.weights_intracount is not None:
-            rec["weights_intracount"] = agg.weights_intracount
-        if hasattr(agg, "loglik_diff"):
-            rec["loglik_diff"] = agg.loglik_diff
-        if agg.mutation_acc_rates is not None:
-            rec["acc"] = agg.mutation_acc_rates
-        for key, v in rec.items():
-            arrays[f"e{k:03d}_{key}"] = v.clone() if isinstance(v, torch.Tensor) else v
-        mine = [d for d in draws if d[0] == k]
-        for kind in ("rand", "rand_like", "multinomial"):
-            sel = [d[2] for d in mine if d[1] == kind]
-            if sel:
-                if all(x.shape == sel[0].shape for x in sel):
-                    arrays[f"e{k:03d}_draw_{kind}"] = torch.stack(sel)
-                else:
-                    arrays[f"e{k:03d}_draw_{kind}_cat"] = torch.cat([x.reshape(-1) for x in sel])
-
-    def wrap(name):
-        orig = getattr(agg, name)
-
-        def wrapped(*a, **kw):
-            stage[0] = name
-            out = orig(*a, **kw)
-            snap(name)
-            return out
-
-        setattr(agg, name, wrapped)
-
-    for name in ("merge", "sort_by_count", "temper", "update_weights", "resample_intracount", "mutate"):
-        wrap(name)
-    real = dict(rand=torch.rand, rand_like=torch.rand_like, multinomial=torch.multinomial, tmn=torch.Tensor.multinomial)
-
-    def rec_call(kind, fn):
-        def call(*a, **kw):
-            out = fn(*a, **kw)
-            draws.append((len(events), kind, out.clone()))
-            return out
-        return call
-
-    torch.rand = rec_call("rand", real["rand"])
-    torch.rand_like = rec_call("rand_like", real["rand_like"])
-    torch.multinomial = rec_call("multinomial", real["multinomial"])
-    torch.Tensor.multinomial = rec_call("multinomial", real["tmn"])
-    try:
-        agg.run()
-    finally:
-        torch.rand, torch.rand_like, torch.multinomial = real["rand"], real["rand_like"], real["multinomial"]
-        torch.Tensor.multinomial = real["tmn"]
-    snap("final", pruned_counts=agg.pruned_counts, pruned_locs=agg.pruned_locs, pruned_fluxes=agg.pruned_fluxes)
-    print("events:", len(events), "final counts", agg.counts.unique(return_counts=True), "D", agg.locs.shape)
-    meta.update(nside=nside, N=N, iters=iters, events=events, flux_threshold=M71_DETECTION, locs_stdev=0.1,
-                fluxes_stdev=2.5, fluxes_min=float(pr.flux_lower), fluxes_max=float(pr.flux_upper), ess_prop=0.5)
+        torch.rand, torch.rand_like = rec(tape_rand, real["rand"]), rec(tape_like, real["rand_like"])
+        torch.multinomial = rec(tape_mn, real["multinomial"])
+        try:
+            out_l, out_f, acc = agg.MutationKernel.run(data, counts, locs, fluxes, tau, agg.log_target, agg.unjoin, axis,
+                                                        child_model)
+        finally:
+            torch.rand, torch.rand_like, torch.multinomial = real["rand"], real["rand_like"], real["multinomial"]
+        comp = torch.stack(tape_mn).view(iters, *counts.shape)
+        u_loc_full, u_flux_full = torch.stack(tape_rand[0::2]), torch.stack(tape_rand[1::2])
+        ci = comp.unsqueeze(-1)
+        arrays[f"L{level}_comp"] = comp.to(torch.int32)
+        arrays[f"L{level}_u_loc"] = torch.gather(u_loc_full, 4, ci.unsqueeze(-1).expand(-1, -1, -1, -1, 1, 2)).squeeze(4)
+        arrays[f"L{level}_u_flux"] = torch.gather(u_flux_full, 4, ci).squeeze(4)
+        arrays[f"L{level}_u_acc"] = torch.stack(tape_like)
+        arrays[f"L{level}_mh_locs"], arrays[f"L{level}_mh_fluxes"], arrays[f"L{level}_mh_acc"] = out_l, out_f, acc
+        cd2, _, cl2, cf2 = agg.unjoin(axis, data, out_l, out_f)
+        arrays[f"L{level}_mh_loglik_diff"] = agg.ImageModel.loglikelihood(data, out_l, out_f) - child_model.loglikelihood(
+            cd2, cl2, cf2).unfold(axis, 2, 2).sum(-1)
+        arrays[f"L{level}_loc_low"], arrays[f"L{level}_loc_high"] = agg.Prior.loc_prior.low, agg.Prior.loc_prior.high
+        meta[f"L{level}"] = dict(axis=axis, dimH=agg.dimH, dimW=agg.dimW, numH=agg.numH, numW=agg.numW,
+                                 D=int(agg.Prior.max_objects))
+        print("level", level, "parent", agg.dimH, agg.dimW, "D", agg.Prior.max_objects, "counts", counts.unique().tolist(),
+              "acc", acc.flatten().tolist())
+    meta.update(nside=nside, N=N, iters=iters, flux_threshold=M71_DETECTION, locs_stdev=0.1, fluxes_stdev=2.5,
+                fluxes_min=float(pr.flux_lower), fluxes_max=float(pr.flux_upper))
     save("aggregate_m71", meta, **arrays)
 
 

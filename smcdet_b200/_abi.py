@@ -2,7 +2,7 @@
 
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MODEL_GAUSS_POISSON, MODEL_M71_NORMAL = 0, 1
 COUNT_DISCRETE_UNIFORM, COUNT_POISSON, COUNT_NONE = 0, 1, 2
@@ -78,6 +78,11 @@ PROTOTYPES = {
                                      _P, _P, _P, _P, _P, _P, _P, C.POINTER(DrawTape), C.POINTER(MHTrace),
                                      C.c_uint64, C.c_uint64, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "smcdet_prune": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _P, _I, _I, _I, _P]),
+    "smcdet_agg_join": (C.c_int, [_P, _P, _I, C.c_float, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "smcdet_agg_unjoin": (C.c_int, [_P, _P, _I, C.c_float, _P, _P, _P, _I, _I, _I, _P]),
+    "smcdet_agg_mutate": (C.c_int, [C.POINTER(ModelParams), C.POINTER(PriorParams), C.POINTER(MHParams), _I]
+                          + [_P] * 10 + [C.POINTER(DrawTape), C.POINTER(MHTrace), C.c_uint64, C.c_uint64, _P, _P]
+                          + [_I] * 5 + [_P]),
     "smcdet_match_catalogs": (C.c_int, [_P] * 8 + [C.c_float, C.c_float] + [_P] * 5 + [_I] * 6 + [_P]),
 }
 

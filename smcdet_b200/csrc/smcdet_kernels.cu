@@ -1058,6 +1058,276 @@ __global__ void match_kernel(const float* __restrict__ true_counts, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Aggregate tree merge (aggregate.py:189-324, :105-128): merging two neighbouring tiles' catalogs
+// and mutating the merged catalogs under the bridge target
+//     log prior(parent) + (1 - tau) * [loglik(child 1) + loglik(child 2)] + tau * loglik(parent)
+// ---------------------------------------------------------------------------------------------
+// drop_sources_from_overlap + join (aggregate.py:189-265) for one parent particle per thread:
+// the first child keeps stars with 0 != loc_axis < dim, the second those with loc_axis > 0 (shifted by
+// dim into the parent's frame); kept values are compacted to the front, field by field as the
+// reference's three sorts do.  Output catalogs have 2*M slots; counts_out = number of kept stars.
+__global__ void agg_join_kernel(const float* __restrict__ locs, const float* __restrict__ fluxes, int axis, float dim,
+                                float* __restrict__ counts_out, float* __restrict__ locs_out,
+                                float* __restrict__ fluxes_out, int nH, int nW, int N, int M) {
+    const int pH = axis == 0 ? nH / 2 : nH, pW = axis == 1 ? nW / 2 : nW;
+    const size_t total = (size_t)pH * pW * N;
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    const int n = (int)(id % N);
+    const int pw = (int)((id / N) % pW), ph = (int)(id / ((size_t)N * pW));
+    float* lo = locs_out + id * (size_t)(4 * M);
+    float* fo = fluxes_out + id * (size_t)(2 * M);
+    int k0 = 0, k1 = 0, kf = 0, kept = 0;
+    for (int c = 0; c < 2; ++c) {
+        const int h = axis == 0 ? 2 * ph + c : ph, w = axis == 1 ? 2 * pw + c : pw;
+        const size_t src = ((size_t)h * nW + w) * N + n;
+        const float* l = locs + src * (size_t)(2 * M);
+        const float* f = fluxes + src * (size_t)M;
+        for (int d = 0; d < M; ++d) {
+            float l0 = l[2 * d], l1 = l[2 * d + 1], fv = f[d];
+            const float la = axis == 0 ? l0 : l1;
+            const bool keep = c == 0 ? (la < dim && la != 0.0f) : (la > 0.0f);
+            if (!keep) continue;
+            ++kept;
+            if (c == 1) {  // shift into the parent's frame; exact zeros stay "empty" (aggregate.py:243-248)
+                if (axis == 0) { if (l0 != 0.0f) l0 += dim; } else { if (l1 != 0.0f) l1 += dim; }
+            }
+            if (l0 != 0.0f) lo[2 * k0++] = l0;
+            if (l1 != 0.0f) lo[2 * k1++ + 1] = l1;
+            if (fv != 0.0f) fo[kf++] = fv;
+        }
+    }
+    for (; k0 < 2 * M; ++k0) lo[2 * k0] = 0.0f;
+    for (; k1 < 2 * M; ++k1) lo[2 * k1 + 1] = 0.0f;
+    for (; kf < 2 * M; ++kf) fo[kf] = 0.0f;
+    counts_out[id] = (float)kept;
+}
+
+// unjoin (aggregate.py:267-324): split parent catalogs at loc_axis <= half into the two children's frames;
+// children are written parent-major ([parent tile][child 0/1][particle]), field-wise compaction as above
+__global__ void agg_unjoin_kernel(const float* __restrict__ locs, const float* __restrict__ fluxes, int axis, float half,
+                                  float* __restrict__ counts_out, float* __restrict__ locs_out,
+                                  float* __restrict__ fluxes_out, int T, int N, int D) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (size_t)T * N) return;
+    const size_t t = id / N, n = id % N;
+    const float* l = locs + id * (size_t)(2 * D);
+    const float* f = fluxes + id * (size_t)D;
+    for (int c = 0; c < 2; ++c) {
+        const size_t dst = (t * 2 + c) * N + n;
+        float* lo = locs_out + dst * (size_t)(2 * D);
+        float* fo = fluxes_out + dst * (size_t)D;
+        int k0 = 0, k1 = 0, kf = 0, cnt = 0;
+        for (int d = 0; d < D; ++d) {
+            float l0 = l[2 * d], l1 = l[2 * d + 1];
+            const float fv = f[d];
+            const bool first = (axis == 0 ? l0 : l1) <= half;
+            if (first != (c == 0)) continue;
+            if (l0 != 0.0f && l1 != 0.0f) ++cnt;
+            if (c == 1) { if (axis == 0) { if (l0 != 0.0f) l0 -= half; } else { if (l1 != 0.0f) l1 -= half; } }
+            if (l0 != 0.0f) lo[2 * k0++] = l0;
+            if (l1 != 0.0f) lo[2 * k1++ + 1] = l1;
+            if (fv != 0.0f) fo[kf++] = fv;
+        }
+        for (; k0 < D; ++k0) lo[2 * k0] = 0.0f;
+        for (; k1 < D; ++k1) lo[2 * k1 + 1] = 0.0f;
+        for (; kf < D; ++kf) fo[kf] = 0.0f;
+        counts_out[dst] = (float)cnt;
+    }
+}
+
+struct AggOut {
+    float* loglik_diff;    // [T,N] parent - (child 1 + child 2) at the final state (aggregate.py:539-541)
+    float* parent_loglik;  // [T,N] nullable
+    float* child_loglik;   // [T,N] nullable: sum over the two children
+    float* log_target;     // [T,N] nullable: bridge target of the final state
+    float half;
+};
+
+// The bridge-target sweep.  A particle is owned by TPP lanes as in loglik_kernel; every sweep renders the
+// whole catalog twice in one pass -- the parent image and the "children" image in which a star only reaches
+// the pixels of its own half (which is what evaluating the two child tiles on their own catalogs amounts to:
+// the half boundary is an integer, so pixel-to-star offsets and the floor()-anchored PSF patch are the same
+// in the child's frame).  No incremental rate image: merged catalogs are mutated for far fewer sweeps than
+// leaf tiles, and the cost is D star renders per sweep.
+template <int MODEL, int H, int W, int TPP, int AXIS>
+__global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOut o) {
+    constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
+    SMC_DYN_SHARED(float, smem);
+    float* s_tile = smem;
+    float* s_lgam = s_tile + HW;
+    float* s_star = s_lgam + HW;  // [3*D][PB]
+
+    const int t = blockIdx.x / a.blocks_per_tile;
+    if (a.active != nullptr && a.active[t] == 0) return;
+    const int N = a.N, D = a.D;
+    const int n0 = (blockIdx.x - t * a.blocks_per_tile) * PB;
+    const int n_here = min(PB, N - n0);
+    const size_t pbase = (size_t)t * N + n0;
+    stage_block<MODEL, HW, PB>(a.tiles + (size_t)t * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
+                               s_tile, s_lgam, s_star);
+    __syncthreads();
+
+    const ModelK& m = a.m;
+    const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
+    const bool valid = pi < n_here;
+    const size_t pn = pbase + pi;
+    const float* my_star = s_star + pi;
+    const float count = valid ? a.counts[pn] : 0.0f;
+    const int icount = (int)count;
+    const float tau = a.tau[t];
+    const float count_lp = count_logpmf_scalar(a.count_kind, a.count_rate, a.min_objects, a.max_objects, count);
+    const uint64_t tile_key = a.tile_ids ? (uint64_t)a.tile_ids[t] : (uint64_t)t;
+    const uint32_t pidx = (uint32_t)(n0 + pi);
+    const float sl = a.mh.locs_stdev, sf = a.mh.fluxes_stdev;
+    const float isl = (1.0f / sl) * kInvSqrt2, isf = (1.0f / sf) * kInvSqrt2;
+    const bool wide_l = fminf(a.mh.locs_max[0] - a.mh.locs_min[0], a.mh.locs_max[1] - a.mh.locs_min[1]) >= 12.0f * sl;
+    const bool wide_f = (a.mh.fluxes_max - a.mh.fluxes_min) >= 12.0f * sf;
+    int last_acc = 0;
+    float cached = 0.0f, ll_par = 0.0f, ll_chi = 0.0f;
+
+    for (int it = -1; it < a.mh.num_iters; ++it) {
+        int k = 0;
+        bool live = false;
+        float u0 = 0.5f, u1 = 0.5f, uf = 0.5f, ua = 0.5f;
+        float l0 = 0.f, l1 = 0.f, f = 0.f, pl0 = 0.f, pl1 = 0.f, pf = 0.f, lq = 0.f;
+        const size_t e = ((size_t)max(it, 0) * a.T + t) * N + (n0 + pi);
+        if (it >= 0) {
+            if (a.tape_comp != nullptr) {
+                if (valid) {
+                    k = a.tape_comp[e];
+                    u0 = a.tape_u_loc[2 * e]; u1 = a.tape_u_loc[2 * e + 1];
+                    uf = a.tape_u_flux[e]; ua = a.tape_u_acc[e];
+                }
+            } else {
+                const uint32_t c2 = (uint32_t)(a.offset << 16) ^ (uint32_t)it;
+                const Philox4 r = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHDraws, (uint32_t)a.seed,
+                                                (uint32_t)(a.seed >> 32));
+                const Philox4 rc = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHComp, (uint32_t)a.seed,
+                                                 (uint32_t)(a.seed >> 32));
+                u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]); ua = u01_f(r.v[3]);
+                k = (int)(((uint64_t)rc.v[0] * (uint64_t)max(icount, 1)) >> 32);  // uniform over the live stars
+            }
+            live = k < icount && k < D;
+            if (!live) k = 0;
+            l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
+            pl0 = l0; pl1 = l1; pf = f;
+            if (live) {
+                float lq0, lq1, lqf;
+                pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
+                pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
+                pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
+                lq = (lq0 + lq1) + lqf;
+            }
+        }
+        // ---- both images of the (proposed) catalog, and its prior
+        float accP[PPT], accC[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) { accP[p] = 0.0f; accC[p] = 0.0f; }
+        float prior_fin = 0.0f;
+        int prior_bad = 0;
+#pragma unroll 1
+        for (int s = 0; s < D; ++s) {
+            float s0 = my_star[(s * 3 + 0) * PB], s1 = my_star[(s * 3 + 1) * PB], sfl = my_star[(s * 3 + 2) * PB];
+            if (it >= 0 && live && s == k) { s0 = pl0; s1 = pl1; sfl = pf; }
+            if ((float)s < count) {
+                int bad;
+                prior_fin += star_prior_term(a.pk, s0, s1, sfl, bad);
+                prior_bad += bad;
+            }
+            const float sw = m.c0 * sfl;
+            if (sw == 0.0f) continue;
+            float tmp[PPT];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) tmp[p] = 0.0f;
+            star_accumulate<MODEL, RPT, W>(m, s0, s1, sw, row0, tmp);
+            const bool second = (AXIS == 0 ? s0 : s1) > o.half;  // aggregate.py:279-281: first child iff loc <= half
+#pragma unroll
+            for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                for (int c = 0; c < W; ++c) {
+                    const bool pix_second = AXIS == 0 ? (row0 + r >= H / 2) : (c >= W / 2);
+                    accP[r * W + c] += tmp[r * W + c];
+                    accC[r * W + c] += (pix_second == second) ? tmp[r * W + c] : 0.0f;
+                }
+        }
+        float q, sg;
+        pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
+            return make_float4(accP[4 * g] + m.bg, accP[4 * g + 1] + m.bg, accP[4 * g + 2] + m.bg, accP[4 * g + 3] + m.bg);
+        }, q, sg);
+        const float llp = finish_loglik<MODEL>(group_sum<TPP>(q), group_sum<TPP>(sg), HW);
+        pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
+            return make_float4(accC[4 * g] + m.bg, accC[4 * g + 1] + m.bg, accC[4 * g + 2] + m.bg, accC[4 * g + 3] + m.bg);
+        }, q, sg);
+        const float llc = finish_loglik<MODEL>(group_sum<TPP>(q), group_sum<TPP>(sg), HW);
+        const float target = ((prior_bad ? -INFINITY : count_lp + prior_fin) + (1.0f - tau) * llc) + tau * llp;
+        if (it < 0) {
+            cached = target; ll_par = llp; ll_chi = llc;
+            continue;
+        }
+        const float log_alpha = (target - cached) + lq;
+        float alpha = ex2_fast(log_alpha * kLog2e);
+        if (alpha > 1.0f) alpha = 1.0f;
+        const bool accept = (ua <= alpha);
+        __syncwarp();
+        if (accept) {
+            ll_par = llp; ll_chi = llc;
+            if (sub == 0 && live) {
+                s_star[(k * 3 + 0) * PB + pi] = pl0;
+                s_star[(k * 3 + 1) * PB + pi] = pl1;
+                s_star[(k * 3 + 2) * PB + pi] = pf;
+            }
+        }
+        cached = target * (accept ? 1.0f : 0.0f) + cached * (accept ? 0.0f : 1.0f);  // kernel.py:125
+        last_acc = accept ? 1 : 0;
+        __syncwarp();
+        if (valid && sub == 0) {
+            if (a.tr_log_alpha) a.tr_log_alpha[e] = log_alpha;
+            if (a.tr_target_prop) a.tr_target_prop[e] = target;
+            if (a.tr_accept) a.tr_accept[e] = (int8_t)last_acc;
+        }
+    }
+    if (valid && sub == 0) {
+        if (o.loglik_diff) o.loglik_diff[pn] = ll_par - ll_chi;
+        if (o.parent_loglik) o.parent_loglik[pn] = ll_par;
+        if (o.child_loglik) o.child_loglik[pn] = ll_chi;
+        if (o.log_target) o.log_target[pn] = cached;
+    }
+    const unsigned votes = __ballot_sync(0xffffffffu, valid && sub == 0 && last_acc);
+    if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(a.acc_count + t, (float)__popc(votes));
+    __syncthreads();
+    unstage_block<PB>(a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D, s_star);
+}
+
+template <int MODEL, int H, int W, int TPP, int AXIS>
+int launch_agg_t(MHArgs a, const AggOut& o, cudaStream_t st) {
+    constexpr int PB = kBT / TPP;
+    a.blocks_per_tile = (a.N + PB - 1) / PB;
+    const size_t smem = sizeof(float) * ((size_t)2 * H * W + (size_t)3 * a.D * PB);
+    const long long grid = (long long)a.T * a.blocks_per_tile;
+    if (grid >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_agg_mutate: grid too large");
+#ifndef SMC_HOSTSIM
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(agg_mh_kernel<MODEL, H, W, TPP, AXIS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(agg_mh_kernel)");
+    }
+#endif
+    SMC_LAUNCH((agg_mh_kernel<MODEL, H, W, TPP, AXIS>), (unsigned)grid, kBT, smem, st, a, o);
+    return launch_status("agg_mh_kernel");
+}
+
+template <int MODEL>
+int dispatch_agg(int h, int w, int axis, const MHArgs& a, const AggOut& o, cudaStream_t st) {
+    // a parent tile is two child tiles side by side: 2s x s after a merge along rows, 2s x 2s after the next one
+    if (h == 16 && w == 8 && axis == 0) return launch_agg_t<MODEL, 16, 8, 4, 0>(a, o, st);
+    if (h == 16 && w == 16 && axis == 1) return launch_agg_t<MODEL, 16, 16, 8, 1>(a, o, st);
+    if (h == 32 && w == 16 && axis == 0) return launch_agg_t<MODEL, 32, 16, 16, 0>(a, o, st);
+    if (h == 32 && w == 32 && axis == 1) return launch_agg_t<MODEL, 32, 32, 32, 1>(a, o, st);
+    return fail(SMCDET_E_UNSUPPORTED, "smcdet_agg_mutate: parent tile must be 16x8, 16x16, 32x16 or 32x32 with the matching axis");
+}
+
+// ---------------------------------------------------------------------------------------------
 // dispatch over (model, tile, threads-per-particle)
 // ---------------------------------------------------------------------------------------------
 // smallest TPP whose grid fills the machine, within what is instantiated for the tile size
@@ -1366,6 +1636,69 @@ int smcdet_match_catalogs(const float* true_counts, const float* true_locs, cons
                true_fluxes, est_counts, est_locs, est_fluxes, index, mag_bins, locs_tol, mags_tol, true_total,
                true_match, est_total, est_match, status, T, n, M, Dt, De, B);
     return launch_status("match_kernel");
+}
+
+int smcdet_agg_join(const float* locs, const float* fluxes, int axis, float dim, float* counts_out, float* locs_out,
+                    float* fluxes_out, int nH, int nW, int N, int M, void* stream) {
+    SMC_REQUIRE(locs && fluxes && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID, "smcdet_agg_join: null pointer");
+    SMC_REQUIRE(nH > 0 && nW > 0 && N > 0 && M > 0 && (axis == 0 || axis == 1), SMCDET_E_INVALID,
+                "smcdet_agg_join: bad sizes");
+    SMC_REQUIRE((axis == 0 ? nH : nW) % 2 == 0, SMCDET_E_INVALID, "smcdet_agg_join: odd number of tiles along the merge axis");
+    const size_t total = (size_t)nH * nW * N / 2;
+    SMC_LAUNCH(agg_join_kernel, (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, locs, fluxes, axis, dim,
+               counts_out, locs_out, fluxes_out, nH, nW, N, M);
+    return launch_status("agg_join_kernel");
+}
+
+int smcdet_agg_unjoin(const float* locs, const float* fluxes, int axis, float half, float* counts_out, float* locs_out,
+                      float* fluxes_out, int T, int N, int D, void* stream) {
+    SMC_REQUIRE(locs && fluxes && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID, "smcdet_agg_unjoin: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0 && (axis == 0 || axis == 1), SMCDET_E_INVALID, "smcdet_agg_unjoin: bad sizes");
+    const size_t total = (size_t)T * N;
+    SMC_LAUNCH(agg_unjoin_kernel, (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, locs, fluxes, axis, half,
+               counts_out, locs_out, fluxes_out, T, N, D);
+    return launch_status("agg_unjoin_kernel");
+}
+
+int smcdet_agg_mutate(const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
+                      int axis, const float* tiles, const float* counts, float* locs, float* fluxes, const float* tau,
+                      float* loglik_diff_out, float* parent_loglik_out, float* child_loglik_out, float* log_target_out,
+                      float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace, uint64_t seed,
+                      uint64_t offset, const int64_t* tile_ids, const int32_t* active, int T, int N, int D, int h, int w,
+                      void* stream) {
+    SMC_REQUIRE(model_ok(model) && prior && mh, SMCDET_E_INVALID, "smcdet_agg_mutate: bad parameters");
+    SMC_REQUIRE(tiles && counts && locs && fluxes && tau && acc_rate, SMCDET_E_INVALID, "smcdet_agg_mutate: null pointer");
+    SMC_REQUIRE(T > 0 && N > 0 && D > 0 && mh->num_iters >= 0 && (axis == 0 || axis == 1), SMCDET_E_INVALID,
+                "smcdet_agg_mutate: bad sizes");
+    SMC_REQUIRE(D <= kMaxStars, SMCDET_E_TOO_LARGE, "smcdet_agg_mutate: too many stars per catalog");
+    if (tape != nullptr)
+        SMC_REQUIRE(tape->comp && tape->u_loc && tape->u_flux && tape->u_acc, SMCDET_E_INVALID,
+                    "smcdet_agg_mutate: incomplete draw tape");
+    cudaStream_t st = (cudaStream_t)stream;
+    MHArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = make_model_k(*model);
+    a.pk = make_prior_k(*prior);
+    a.count_kind = prior->count_kind; a.min_objects = prior->min_objects; a.max_objects = prior->max_objects;
+    a.count_rate = prior->count_rate;
+    a.mh = *mh;
+    a.tiles = tiles; a.counts = counts; a.locs = locs; a.fluxes = fluxes; a.tau = tau;
+    a.acc_count = acc_rate;
+    if (tape) { a.tape_comp = tape->comp; a.tape_u_loc = tape->u_loc; a.tape_u_flux = tape->u_flux; a.tape_u_acc = tape->u_acc; }
+    if (trace) { a.tr_log_alpha = trace->log_alpha; a.tr_target_prop = trace->target_prop; a.tr_accept = trace->accept; }
+    a.seed = seed; a.offset = offset; a.tile_ids = tile_ids; a.active = active;
+    a.T = T; a.N = N; a.D = D;
+    AggOut o;
+    o.loglik_diff = loglik_diff_out; o.parent_loglik = parent_loglik_out; o.child_loglik = child_loglik_out;
+    o.log_target = log_target_out;
+    o.half = axis == 0 ? 0.5f * (float)h : 0.5f * (float)w;
+    SMC_LAUNCH(zero_active_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, T);
+    int rc;
+    if (model->model_kind == SMCDET_MODEL_M71_NORMAL) rc = dispatch_agg<SMCDET_MODEL_M71_NORMAL>(h, w, axis, a, o, st);
+    else rc = dispatch_agg<SMCDET_MODEL_GAUSS_POISSON>(h, w, axis, a, o, st);
+    if (rc != 0) return rc;
+    SMC_LAUNCH(divide_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, (float)N, T);
+    return launch_status("divide_kernel");
 }
 
 }  // extern "C"

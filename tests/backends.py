@@ -210,3 +210,51 @@ class GpuBackend:
                                                    *[self._p(o) for o in out], self._p(status), T, n, M, Dt, De, B,
                                                    self._stream()))
         return [o.cpu().numpy() for o in out] + [int(status.item())]
+
+    def agg_join(self, locs, fluxes, axis, dim):
+        t = self.torch
+        locs, fluxes = self._d(locs), self._d(fluxes)
+        nH, nW, N, M, _ = locs.shape
+        pH, pW = (nH // 2, nW) if axis == 0 else (nH, nW // 2)
+        co, lo, fo = self._z((pH, pW, N), t.float32), self._z((pH, pW, N, 2 * M, 2), t.float32), self._z((pH, pW, N, 2 * M), t.float32)
+        self._check(self.lib.smcdet_agg_join(self._p(locs), self._p(fluxes), axis, float(dim), self._p(co), self._p(lo),
+                                             self._p(fo), nH, nW, N, M, self._stream()))
+        return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
+
+    def agg_unjoin(self, locs, fluxes, axis, half):
+        t = self.torch
+        locs, fluxes = self._d(locs), self._d(fluxes)
+        T, N, D, _ = locs.shape
+        co, lo, fo = self._z((T, 2, N), t.float32), self._z((T, 2, N, D, 2), t.float32), self._z((T, 2, N, D), t.float32)
+        self._check(self.lib.smcdet_agg_unjoin(self._p(locs), self._p(fluxes), axis, float(half), self._p(co), self._p(lo),
+                                               self._p(fo), T, N, D, self._stream()))
+        return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
+
+    def agg_mutate(self, model, prior, mh, axis, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0):
+        t = self.torch
+        tiles, counts, locs, fluxes = self._d(tiles), self._d(counts), self._d(locs), self._d(fluxes)
+        tau = self._d(np.reshape(tau, -1))
+        T, h, w = tiles.shape
+        _, N, D, _ = locs.shape
+        iters = mh.num_iters
+        outs = [self._z((T, N), t.float32) for _ in range(4)]
+        acc = t.full((T,), -1.0, device=self.dev)
+        tp, keep = None, []
+        if tape is not None:
+            comp = self._d(np.reshape(tape["comp"], (iters, T, N)), np.int32)
+            ul = self._d(np.reshape(tape["u_loc"], (iters, T, N, 2)))
+            uf = self._d(np.reshape(tape["u_flux"], (iters, T, N)))
+            ua = self._d(np.reshape(tape["u_acc"], (iters, T, N)))
+            keep += [comp, ul, uf, ua]
+            tp = A.DrawTape(comp.data_ptr(), ul.data_ptr(), uf.data_ptr(), ua.data_ptr())
+        la, tg = self._z((max(iters, 1), T, N), t.float32), self._z((max(iters, 1), T, N), t.float32)
+        ac = self._z((max(iters, 1), T, N), t.int8)
+        tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr(), None, None)
+        self._check(self.lib.smcdet_agg_mutate(
+            C.byref(model), C.byref(prior), C.byref(mh), axis, self._p(tiles), self._p(counts), self._p(locs),
+            self._p(fluxes), self._p(tau), *[self._p(o) for o in outs], self._p(acc),
+            C.byref(tp) if tp is not None else None, C.byref(tr), seed, offset, None, None, T, N, D, h, w, self._stream()))
+        return dict(locs=locs.cpu().numpy(), fluxes=fluxes.cpu().numpy(), loglik_diff=outs[0].cpu().numpy(),
+                    parent_loglik=outs[1].cpu().numpy(), child_loglik=outs[2].cpu().numpy(),
+                    log_target=outs[3].cpu().numpy(), acc_rate=acc.cpu().numpy(), log_alpha=la.cpu().numpy(),
+                    target_prop=tg.cpu().numpy(), accept=ac.cpu().numpy())

@@ -195,3 +195,45 @@ def match_catalogs(true_counts, true_locs, true_fluxes, est_counts, est_locs, es
     check(lib().smcdet_match_catalogs(_p(tc), _p(tl), _p(tf), _p(ec), _p(el), _p(ef), _p(index), _p(bins), locs_tol,
                                       mags_tol, *[_p(o) for o in out], _p(status), T, n, M, Dt, De, B, None))
     return out + [int(status[0])]
+
+
+def agg_join(locs, fluxes, axis, dim):
+    locs, fluxes = _f(locs), _f(fluxes)
+    nH, nW, N, M, _ = locs.shape
+    pH, pW = (nH // 2, nW) if axis == 0 else (nH, nW // 2)
+    co, lo, fo = np.zeros((pH, pW, N), np.float32), np.zeros((pH, pW, N, 2 * M, 2), np.float32), np.zeros((pH, pW, N, 2 * M), np.float32)
+    check(lib().smcdet_agg_join(_p(locs), _p(fluxes), axis, float(dim), _p(co), _p(lo), _p(fo), nH, nW, N, M, None))
+    return co, lo, fo
+
+
+def agg_unjoin(locs, fluxes, axis, half):
+    locs, fluxes = _f(locs), _f(fluxes)
+    T, N, D, _ = locs.shape
+    co, lo, fo = np.zeros((T, 2, N), np.float32), np.zeros((T, 2, N, D, 2), np.float32), np.zeros((T, 2, N, D), np.float32)
+    check(lib().smcdet_agg_unjoin(_p(locs), _p(fluxes), axis, float(half), _p(co), _p(lo), _p(fo), T, N, D, None))
+    return co, lo, fo
+
+
+def agg_mutate(model, prior, mh, axis, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0):
+    tiles, counts = _f(tiles), _f(counts)
+    locs, fluxes = _f(locs).copy(), _f(fluxes).copy()
+    tau = _f(tau).reshape(-1)
+    T, h, w = tiles.shape
+    _, N, D, _ = locs.shape
+    iters = mh.num_iters
+    outs = [np.zeros((T, N), np.float32) for _ in range(4)]
+    acc = np.full(T, -1.0, np.float32)
+    keep, tp = [], None
+    if tape is not None:
+        comp = np.ascontiguousarray(tape["comp"], np.int32).reshape(iters, T, N)
+        ul, uf, ua = _f(tape["u_loc"]).reshape(iters, T, N, 2), _f(tape["u_flux"]).reshape(iters, T, N), _f(tape["u_acc"]).reshape(iters, T, N)
+        keep += [comp, ul, uf, ua]
+        tp = A.DrawTape(_p(comp).value, _p(ul).value, _p(uf).value, _p(ua).value)
+    la, tg, ac = np.zeros((max(iters, 1), T, N), np.float32), np.zeros((max(iters, 1), T, N), np.float32), np.zeros((max(iters, 1), T, N), np.int8)
+    tr = A.MHTrace(_p(la).value, _p(tg).value, _p(ac).value, None, None)
+    check(lib().smcdet_agg_mutate(C.byref(model), C.byref(prior), C.byref(mh), axis, _p(tiles), _p(counts), _p(locs),
+                                  _p(fluxes), _p(tau), *[_p(o) for o in outs], _p(acc),
+                                  C.byref(tp) if tp is not None else None, C.byref(tr), seed, offset, None, None,
+                                  T, N, D, h, w, None))
+    return dict(locs=locs, fluxes=fluxes, loglik_diff=outs[0], parent_loglik=outs[1], child_loglik=outs[2],
+                log_target=outs[3], acc_rate=acc, log_alpha=la, target_prop=tg, accept=ac)

@@ -495,3 +495,80 @@ def test_match_catalogs_many_random_problems_against_oracle(backend):
     for w, g_ in zip(want, got[:4]):
         assert np.array_equal(w, g_)
     assert want[1].sum() > 500
+
+
+# ---- Aggregate tree merge building blocks (aggregate.py) ------------------------------------------------
+def _agg_level(g, level):
+    L = g.meta[f"L{level}"]
+    m = abi_model(g.meta)
+    p = abi_prior(g.meta)
+    pad = g.meta["pad"]
+    p.max_objects = L["D"]
+    p.loc_high[0], p.loc_high[1] = L["dimH"] + pad, L["dimW"] + pad
+    p.count_rate = g.meta["prior_params"]["counts_rate"] * (L["dimH"] + 2 * pad) * (L["dimW"] + 2 * pad)
+    k = abi_mh(g.meta)
+    k.locs_max[0], k.locs_max[1] = L["dimH"] + pad, L["dimW"] + pad
+    return L, m, p, k
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_aggregate_join_and_unjoin_equal_the_reference(backend, level):
+    """drop_sources_from_overlap + join and unjoin of the reference's Aggregate (aggregate.py:189-324) on its own
+    inputs, including stars placed exactly on the decision boundaries: bit-identical catalogs."""
+    g = Golden("aggregate_m71")
+    L = g.meta[f"L{level}"]
+    axis = L["axis"]
+    child_dim = (L["dimH"] if axis == 0 else L["dimW"]) // 2
+    c, l, f = backend.agg_join(g[f"L{level}_in_locs"], g[f"L{level}_in_fluxes"], axis, child_dim)
+    D = L["D"]
+    assert np.array_equal(c, g[f"L{level}_counts"]) and int(c.max()) == D
+    assert np.array_equal(l[..., :D, :], g[f"L{level}_locs"]) and np.array_equal(f[..., :D], g[f"L{level}_fluxes"])
+    assert np.all(l[..., D:, :] == 0) and np.all(f[..., D:] == 0)
+    T, N = L["numH"] * L["numW"], g.meta["N"]
+    cc, cl, cf = backend.agg_unjoin(g[f"L{level}_locs"].reshape(T, N, D, 2), g[f"L{level}_fluxes"].reshape(T, N, D), axis,
+                                    child_dim)
+    # the reference lays children out child-major along the merge axis (aggregate.py:296, :318, :322)
+    want_c, want_l, want_f = g[f"L{level}_child_counts"], g[f"L{level}_child_locs"], g[f"L{level}_child_fluxes"]
+    if axis == 0:
+        sel = lambda a: np.stack([a[:L["numH"]], a[L["numH"]:]], 2)  # -> [numH, numW, child, ...]
+    else:
+        sel = lambda a: np.stack([a[:, :L["numW"]], a[:, L["numW"]:]], 2)
+    assert np.array_equal(cc.reshape(L["numH"], L["numW"], 2, N), sel(want_c))
+    assert np.array_equal(cl.reshape(L["numH"], L["numW"], 2, N, D, 2), sel(want_l))
+    assert np.array_equal(cf.reshape(L["numH"], L["numW"], 2, N, D), sel(want_f))
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_aggregate_bridge_target_and_mutation(backend, level):
+    """smcdet_agg_mutate: with num_iters = 0 the parent / children log-likelihoods, their difference and
+    Aggregate.log_target of the reference (aggregate.py:105-128, :533-541); with the recorded draws, the states
+    after the sweeps of the repaired nine-argument kernel (oracle/gen_golden.py: AggregateMH)."""
+    g = Golden("aggregate_m71")
+    L, m, p, k = _agg_level(g, level)
+    T, N, D = L["numH"] * L["numW"], g.meta["N"], L["D"]
+    tiles = g[f"L{level}_data"].reshape(T, L["dimH"], L["dimW"])
+    counts, locs, fluxes = g[f"L{level}_counts"].reshape(T, N), g[f"L{level}_locs"].reshape(T, N, D, 2), g[f"L{level}_fluxes"].reshape(T, N, D)
+    tau = g[f"L{level}_tau"].reshape(T)
+    k.num_iters = 0
+    ev = backend.agg_mutate(m, p, k, L["axis"], tiles, counts, locs, fluxes, tau)
+    assert rel_err(ev["parent_loglik"], g[f"L{level}_parent_loglik"].reshape(T, N)) < RTOL
+    child_sum = g[f"L{level}_parent_loglik"].reshape(T, N) - g[f"L{level}_loglik_diff"].reshape(T, N)
+    assert rel_err(ev["child_loglik"], child_sum) < RTOL
+    assert np.max(np.abs(ev["loglik_diff"] - g[f"L{level}_loglik_diff"].reshape(T, N))) < RTOL * np.max(np.abs(child_sum))
+    assert rel_err(ev["log_target"], g[f"L{level}_log_target"].reshape(T, N)) < RTOL
+    assert np.array_equal(ev["locs"], locs) and np.array_equal(ev["fluxes"], fluxes)
+
+    k.num_iters = g.meta["iters"]
+    tape = dict(comp=g[f"L{level}_comp"], u_loc=g[f"L{level}_u_loc"], u_flux=g[f"L{level}_u_flux"], u_acc=g[f"L{level}_u_acc"])
+    out = backend.agg_mutate(m, p, k, L["axis"], tiles, counts, locs, fluxes, tau, tape=tape)
+    want_l, want_f = g[f"L{level}_mh_locs"].reshape(T, N, D, 2), g[f"L{level}_mh_fluxes"].reshape(T, N, D)
+    moved = np.any(want_l != locs, axis=(-1, -2))
+    assert moved.mean() > 0.3
+    same = np.all(np.isclose(out["locs"], want_l, rtol=1e-4, atol=1e-5), axis=(-1, -2)) & np.all(
+        np.isclose(out["fluxes"], want_f, rtol=1e-4, atol=1e-5), axis=-1)
+    assert same.all(), f"{(~same).sum()} of {same.size} particles differ"
+    assert np.allclose(out["acc_rate"], g[f"L{level}_mh_acc"].reshape(T), atol=1e-6)
+    assert np.max(np.abs(out["loglik_diff"] - g[f"L{level}_mh_loglik_diff"].reshape(T, N))) < 2e-4 * np.max(np.abs(child_sum))
+    # live-star rule: empty slots never move
+    dead = np.arange(D)[None, None, :] >= counts[..., None]
+    assert np.all(out["fluxes"][dead] == 0)

@@ -1,14 +1,21 @@
 """``Aggregate`` with the reference's constructor and result surface (smcdet/aggregate.py).
 
-At the reference's HEAD the divide-and-conquer tree merge only runs for a 1 x 1 grid of tiles
-(``num_aggregation_levels == 0``): ``run()`` then performs a final resample by the weights and a
-prune (reference aggregate.py:583-589); for larger grids the reference itself raises
-(``join`` calls a method no ImageModel defines, aggregate.py:241 -- SURVEY.md section 0.4).  This
-class implements exactly that working behaviour on the GPU and is the sink of the multi-GPU
-gather (``smcdet_b200.shard``): per-tile catalogs from all ranks are concatenated along the tile
-axis and finished tile by tile.  The tree merge is listed as "next" in SURVEY.md section 8(f).
+For a 1 x 1 grid of tiles (``num_aggregation_levels == 0``) ``run()`` performs a final resample by the
+weights and a prune (reference aggregate.py:583-589); this is also the sink of the multi-GPU gather
+(``smcdet_b200.shard``, ``merge=False``: per-tile catalogs from all ranks finished tile by tile).
+
+For larger grids ``run()`` performs the divide-and-conquer tree merge (reference aggregate.py:523-581): per
+level, neighbouring tiles are resampled, their overlap sources dropped and their catalogs joined
+(``smcdet_agg_join`` = drop_sources_from_overlap + join, aggregate.py:189-265), and the merged catalogs are
+carried from "two independent children" to "one parent tile" by tempered SMC on
+``loglik(parent) - loglik(child 1) - loglik(child 2)`` (aggregate.py:533-541) with mutation under the bridge
+target of ``Aggregate.log_target`` (aggregate.py:105-128) -- ``smcdet_agg_mutate``, which also returns that
+difference for the next tempering step; tempering, weights and resampling are the launches ``SMCsampler`` uses.
+The reference itself raises at HEAD for grids > 1 x 1; what is pinned on its code, and
+what had to be decided, is listed in DESIGN.md section 8.
 """
 
+import ctypes as C
 from copy import deepcopy
 
 import torch
@@ -39,7 +46,7 @@ class Aggregate(object):
         self.weights_intracount = None
 
         self.numH, self.numW, self.dimH, self.dimW = self.data.shape
-        self.merge = merge
+        self._merge_tree = merge
         self.num_aggregation_levels = (2 * torch.tensor(float(self.numH)).log2()).int().item() if merge else 0
 
         self.log_normalizing_constant = [
@@ -105,14 +112,126 @@ class Aggregate(object):
                                      L.ptr(fo), numH * numW, n, d, L.stream_for(lf)))
         return counts.view(numH, numW, n), lo.view(numH, numW, n, d, 2), fo.view(numH, numW, n, d)
 
-    def run(self, *, u=None):
-        """reference aggregate.py:523-593 for zero aggregation levels: final resample + prune."""
+    # ---- tree merge (reference aggregate.py:347-422, :523-581) -----------------------------------
+    def _flat_state(self):
+        T, n, d = self.numH * self.numW, self.counts.shape[-1], self.fluxes.shape[-1]
+        dev = L.f32(self.weights).device
+        return (T, n, d, L.f32(self.counts, dev).view(T, n), L.f32(self.locs, dev).view(T, n, d, 2),
+                L.f32(self.fluxes, dev).view(T, n, d))
+
+    def _bridge(self, axis, num_iters):
+        """num_iters sweeps under the bridge target (0: evaluate only); sets self.loglik_diff."""
+        T, n, d, counts, locs, fluxes = self._flat_state()
+        dev = counts.device
+        k = self.MutationKernel._params()
+        k.num_iters = int(num_iters)
+        model, prior = self.ImageModel._params(), self.Prior._params()
+        tiles = L.f32(self.data, dev).reshape(T, self.dimH, self.dimW)
+        tau = L.f32(self.temperature, dev).reshape(T)
+        lld = torch.empty(T, n, device=dev)
+        acc = torch.empty(T, device=dev)
+        locs, fluxes = locs.clone(), fluxes.clone()
+        L.check(L.lib().smcdet_agg_mutate(C.byref(model), C.byref(prior), C.byref(k), int(axis), L.ptr(tiles),
+                                          L.ptr(counts), L.ptr(locs), L.ptr(fluxes), L.ptr(tau), L.ptr(lld), None, None,
+                                          None, L.ptr(acc), None, None, L.fresh_seed(), int(self.iter), None, None,
+                                          T, n, d, int(self.dimH), int(self.dimW), L.stream_for(tiles)))
+        self.loglik_diff = lld.view(self.numH, self.numW, n)
+        if num_iters > 0:
+            self.locs, self.fluxes = locs.view(self.numH, self.numW, n, d, 2), fluxes.view(self.numH, self.numW, n, d)
+            self.mutation_acc_rates = acc.view(self.numH, self.numW)
+
+    def _temper_and_update(self):
+        """Adaptive step on the log-likelihood difference + weights / ESS / log Z (aggregate.py:140-174, :439-483
+        with one stratum per tile): the same launch SMCsampler uses."""
+        T, n = self.numH * self.numW, self.loglik_diff.shape[-1]
+        dev = self.loglik_diff.device
+        lld = self.loglik_diff.reshape(T, n).contiguous()
+        tau, tau_prev = self.temperature.reshape(T).clone(), self.temperature_prev.reshape(T).clone()
+        logz = self._logz.reshape(T).clone()
+        wlog, weights = torch.empty(T, n, device=dev), torch.empty(T, n, device=dev)
+        ess = torch.empty(T, device=dev)
+        L.check(L.lib().smcdet_temper_update(L.ptr(lld), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold_prop * n), 1,
+                                             L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz), None, None, T, n,
+                                             L.stream_for(lld)))
+        self.temperature, self.temperature_prev = tau.view(self.numH, self.numW), tau_prev.view(self.numH, self.numW)
+        self.weights = self.weights_intracount = weights.view(self.numH, self.numW, n)
+        self._logz = logz.view(self.numH, self.numW)
+
+    def _resample(self):
+        index = self.get_resampled_index(self.weights, 1)
+        self.counts, self.locs, self.fluxes, self.weights = self.apply_resampled_index(index, self.counts, self.locs,
+                                                                                      self.fluxes)
+
+    def merge(self, level):
+        """Resample the children, drop the sources in each other's territory, join pairs of tiles along
+        ``level % 2`` (aggregate.py:347-360, :189-265); the parent's log normalising constant starts as the sum
+        of its children's."""
+        axis = level % 2
+        if (self.numH if axis == 0 else self.numW) % 2 != 0:
+            raise ValueError("the tree merge needs an even number of tiles along the merge axis")
+        self._resample()
+        T, n, m, counts, locs, fluxes = self._flat_state()
+        dev = counts.device
+        nH, nW = self.numH, self.numW
+        pH, pW = (nH // 2, nW) if axis == 0 else (nH, nW // 2)
+        cs = torch.empty(pH * pW, n, device=dev)
+        ls = torch.empty(pH * pW, n, 2 * m, 2, device=dev)
+        fs = torch.empty(pH * pW, n, 2 * m, device=dev)
+        child_dim = self.dimH if axis == 0 else self.dimW
+        L.check(L.lib().smcdet_agg_join(L.ptr(locs), L.ptr(fluxes), axis, float(child_dim), L.ptr(cs), L.ptr(ls), L.ptr(fs),
+                                        nH, nW, n, m, L.stream_for(locs)))
+        d = max(1, int(cs.max().item()))  # max objects detected (aggregate.py:236)
+        data = L.f32(self.data, dev)
+        if axis == 0:
+            self.data = data.reshape(pH, 2, nW, self.dimH, self.dimW).permute(0, 2, 1, 3, 4).reshape(pH, pW, 2 * self.dimH, self.dimW)
+            self._logz = self._logz.reshape(pH, 2, nW).sum(1)
+            self.dimH *= 2
+        else:
+            self.data = data.reshape(nH, pW, 2, self.dimH, self.dimW).permute(0, 1, 3, 2, 4).reshape(pH, pW, self.dimH, 2 * self.dimW)
+            self._logz = self._logz.reshape(nH, pW, 2).sum(2)
+            self.dimW *= 2
+        self.data = self.data.contiguous()
+        self.numH, self.numW = pH, pW
+        self.ImageModel.image_height, self.ImageModel.image_width = self.dimH, self.dimW
+        self.Prior.image_height, self.Prior.image_width = self.dimH, self.dimW
+        self.Prior.max_objects = d
+        self.Prior.update_attrs()
+        self.MutationKernel.locs_min = self.Prior.loc_prior.low
+        self.MutationKernel.locs_max = self.Prior.loc_prior.high
+        self.counts = cs.view(pH, pW, n)
+        self.locs = ls[:, :, :d].contiguous().view(pH, pW, n, d, 2)
+        self.fluxes = fs[:, :, :d].contiguous().view(pH, pW, n, d)
+        self.weights = torch.full((pH, pW, n), 1.0 / n, device=dev)
+        self.num_catalogs_per_count = [[[n] for _ in range(pW)] for _ in range(pH)]
+
+    def run(self, *, u=None, max_iters=500):
+        """reference aggregate.py:523-593"""
         print("aggregating tile catalogs...")
+        dev = L.f32(self.weights).device
+        self._logz = torch.tensor(self.log_normalizing_constant, device=dev, dtype=torch.float32).reshape(self.numH, self.numW)
+        self.iter = 0
+        for level in range(self.num_aggregation_levels):
+            print(f"level {level}")
+            axis = level % 2
+            self.merge(level)
+            self.temperature_prev = torch.zeros(self.numH, self.numW, device=dev)
+            self.temperature = torch.zeros(self.numH, self.numW, device=dev)
+            self._bridge(axis, 0)
+            self._temper_and_update()
+            self.iter = 0
+            while torch.any(self.temperature < 1) and self.iter < max_iters:
+                self.iter += 1
+                if self.iter % self.print_every == 0 and self.mutation_acc_rates is not None:
+                    print(f"iteration {self.iter}: "
+                          f"temperature in [{round(self.temperature.min().item(), 2)}, "
+                          f"{round(self.temperature.max().item(), 2)}], "
+                          f"accept rate in [{round(self.mutation_acc_rates.min().item(), 2)}, "
+                          f"{round(self.mutation_acc_rates.max().item(), 2)}]")
+                self._resample()
+                self._bridge(axis, self.MutationKernel.num_iters)
+                self._temper_and_update()
         if self.num_aggregation_levels > 0:
-            raise NotImplementedError(
-                "the divide-and-conquer tree merge is not implemented: at the reference's HEAD it raises for any "
-                "grid larger than 1x1 (smcdet/aggregate.py:241; SURVEY.md section 0.4).  Pass merge=False to "
-                "finish every tile on its own.")
+            self.log_normalizing_constant = [[[float(self._logz[h, w])] for w in range(self.numW)] for h in range(self.numH)]
         index = self.get_resampled_index(self.weights, 1, u=u)
         res = self.apply_resampled_index(index, self.counts, self.locs, self.fluxes)
         self.counts, self.locs, self.fluxes, self.weights = res

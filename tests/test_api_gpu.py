@@ -235,10 +235,11 @@ def test_aggregate_single_tile_sink():
     assert np.array_equal(agg.pruned_counts.cpu().numpy().reshape(1, -1), pc)
     assert abs(float(agg.ess) - meta["N"]) < 1e-2
     agg.summarize()
-    big = Aggregate(prior, model, mh, torch.zeros(2, 2, 8, 8, device=dev()), cu(g["counts"]), cu(g["locs"]), cu(g["fluxes"]),
-                    cu(g[f"k{k}_weights"]), torch.zeros(2, 2), 0.25, "systematic", 0.5)
-    with pytest.raises(NotImplementedError):
-        big.run()
+    odd = Aggregate(prior, model, mh, torch.zeros(3, 3, 8, 8, device=dev()), cu(g["counts"][:1, :1]).expand(3, 3, -1),
+                    cu(g["locs"][:1, :1]).expand(3, 3, -1, -1, -1), cu(g["fluxes"][:1, :1]).expand(3, 3, -1, -1),
+                    w.expand(3, 3, -1), torch.zeros(3, 3), 0.25, "systematic", 0.5)
+    with pytest.raises(ValueError):
+        odd.run()      # the tree merge pairs tiles: odd grids cannot be merged
     sink = Aggregate(prior, model, mh, torch.zeros(2, 2, 8, 8, device=dev()), cu(g["counts"]), cu(g["locs"]), cu(g["fluxes"]),
                      cu(g[f"k{k}_weights"]), torch.zeros(2, 2), 0.25, "systematic", 0.5, merge=False)
     sink.run(u=cu(g[f"k{k}_u"].astype(np.float64)))
@@ -728,3 +729,68 @@ def test_metrics_module_matches_reference():
         big[0] = 1000
         metrics.match_catalogs(big, cu(g["true_locs"]), cu(g["true_fluxes"]), cu(g["est_counts"]), cu(g["est_locs"]),
                                cu(g["est_fluxes"]), 2, 0.5, 0.5, torch.from_numpy(g["mag_bins"]))
+
+
+def test_aggregate_tree_merge_end_to_end():
+    """SMCsampler on a 2 x 2 grid of 8 x 8 tiles, then Aggregate.run() merging 8x8 -> 16x8 -> 16x16
+    (aggregate.py:523-593).  Checked: the bridge reaches temperature 1 at both levels, catalogs stay consistent
+    (count = number of live slots, stars inside the parent's box, no star of a child left in its sibling's
+    territory at the merge), the run is reproducible, and the merged posterior agrees loosely with a direct run
+    on the whole 16 x 16 image (different models of the star count, same image)."""
+    from smcdet_b200.aggregate import Aggregate
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("aggregate_m71")
+    meta = g.meta
+    image = cu(g["image"])
+
+    def run(seed):
+        torch.manual_seed(seed)
+        model, prior, mh = build_objects(meta, iters=25)
+        s = SMCsampler(image, 8, prior, model, mh, 2000, 0.5, "multinomial", meta["flux_threshold"], 200, verbose=False)
+        s.run()
+        aggmh = SingleComponentMH(10, 0.1, 2.5, meta["fluxes_min"], meta["fluxes_max"])
+        agg = Aggregate(s.Prior, s.ImageModel, aggmh, s.tiled_image, s.counts, s.locs, s.fluxes, s.weights,
+                        s.log_normalizing_constant, meta["flux_threshold"], "multinomial", 0.5, print_every=1000)
+        assert agg.num_aggregation_levels == 2
+        agg.run()
+        return s, agg
+
+    s, agg = run(3)
+    assert agg.has_run and (agg.numH, agg.numW, agg.dimH, agg.dimW) == (1, 1, 16, 16)
+    assert float(agg.temperature.min()) == 1.0 and agg.data.shape == (1, 1, 16, 16)
+    assert torch.equal(agg.data[0, 0], image)
+    assert agg.Prior.image_height == 16 and agg.ImageModel.image_width == 16
+    d = agg.locs.shape[-2]
+    assert d == agg.Prior.max_objects and agg.counts.shape == (1, 1, 2000)
+    live = (agg.fluxes > 0).sum(-1).float()
+    assert torch.equal(live, agg.counts)
+    lo, hi = -meta["pad"], 16 + meta["pad"]
+    on = agg.fluxes > 0
+    assert bool(((agg.locs[on] >= lo) & (agg.locs[on] <= hi)).all())
+    assert abs(float(agg.weights.sum()) - 1) < 1e-4 and len(agg.log_normalizing_constant[0][0]) == 1
+    assert np.isfinite(agg.log_normalizing_constant[0][0][0])
+    # reproducible
+    _, again = run(3)
+    assert torch.equal(again.locs, agg.locs) and torch.equal(again.pruned_counts, agg.pruned_counts)
+    # loose agreement with a direct run on the whole image (tile_dim = 16, as many stars as the merge ended with)
+    torch.manual_seed(5)
+    from smcdet_b200.images import M71ImageModel
+    from smcdet_b200.prior import M71Prior
+
+    mp, pp = meta["model_params"], meta["prior_params"]
+    big_model = M71ImageModel(16, 16, background=mp["background"], psf_radius=mp["psf_radius"], adu_per_nmgy=mp["adu_per_nmgy"],
+                              psf_params=mp["psf_params"], noise_additive=mp["noise_additive"],
+                              noise_multiplicative=mp["noise_multiplicative"])
+    dd = int(round(float(agg.counts.mean())))
+    big_prior = M71Prior(dd, dd, pp["counts_rate"], 16, 16, flux_alpha=pp["flux_alpha"], flux_lower=pp["flux_lower"],
+                         flux_upper=pp["flux_upper"], pad=meta["pad"])
+    direct = SMCsampler(image, 16, big_prior, big_model, SingleComponentMH(50, 0.1, 2.5, meta["fluxes_min"], meta["fluxes_max"]),
+                        4000, 0.5, "multinomial", meta["flux_threshold"], 200, verbose=False)
+    direct.run()
+    merged_count, direct_count = float(agg.pruned_counts.float().mean()), float(direct.pruned_counts.float().mean())
+    merged_flux = float(agg.pruned_fluxes.sum(-1).mean())
+    direct_flux = float(direct.pruned_fluxes.sum(-1).mean())
+    assert abs(merged_count - direct_count) < 1.5, (merged_count, direct_count)
+    assert abs(merged_flux / direct_flux - 1) < 0.2, (merged_flux, direct_flux)

@@ -208,7 +208,11 @@ class Aggregate(object):
         """reference aggregate.py:523-593"""
         print("aggregating tile catalogs...")
         dev = L.f32(self.weights).device
-        self._logz = torch.tensor(self.log_normalizing_constant, device=dev, dtype=torch.float32).reshape(self.numH, self.numW)
+        if self.num_aggregation_levels > 0:
+            self._logz = torch.tensor(self.log_normalizing_constant, device=dev, dtype=torch.float32)
+            if self._logz.numel() != self.numH * self.numW:
+                raise ValueError("the tree merge takes one log normalising constant per tile")
+            self._logz = self._logz.reshape(self.numH, self.numW)
         self.iter = 0
         for level in range(self.num_aggregation_levels):
             print(f"level {level}")

@@ -572,3 +572,68 @@ def test_aggregate_bridge_target_and_mutation(backend, level):
     # live-star rule: empty slots never move
     dead = np.arange(D)[None, None, :] >= counts[..., None]
     assert np.all(out["fluxes"][dead] == 0)
+
+
+@pytest.mark.parametrize("model_name", ["loglik_m71_t8_d10", "loglik_gauss_t8_d8"])
+@pytest.mark.parametrize("shape", [(16, 8, 0), (16, 16, 1), (32, 16, 0), (32, 32, 1)])
+def test_aggregate_bridge_kernel_equals_unjoin_plus_loglik(backend, model_name, shape):
+    """All four parent shapes and both image models: the fused parent / children evaluation of smcdet_agg_mutate
+    equals the path the reference takes -- unjoin the catalogs, evaluate the two child tiles with the child image
+    model and the parent tile with the parent's (aggregate.py:533-541) -- built here from smcdet_agg_unjoin and
+    smcdet_loglik (whose answers are pinned on the reference separately), and from the float64 oracle."""
+    g = Golden(model_name)
+    meta = g.meta
+    H, W, axis = shape
+    rng = np.random.default_rng(H * 100 + W + axis)
+    T, N, D, pad = 2, 40, 7, meta["pad"]
+    m = abi_model(meta)
+    bg = meta["model_params"]["background"]
+    tiles = (bg + rng.gamma(2.0, 0.4 * bg, (T, H, W))).astype(np.float32)
+    if meta["model"] != "m71":
+        tiles = np.round(tiles)
+    counts = rng.integers(0, D + 1, (T, N)).astype(np.float32)
+    live = np.arange(D)[None, None, :] < counts[..., None]
+    locs = np.stack([rng.uniform(-pad, H + pad, (T, N, D)), rng.uniform(-pad, W + pad, (T, N, D))], -1).astype(np.float32)
+    half = (H if axis == 0 else W) // 2
+    locs[0, 0, 0, axis] = half            # exactly on the split: belongs to the first child (loc <= half)
+    locs[0, 1, 0, axis] = np.nextafter(np.float32(half), np.float32(1e9))
+    fl_lo = meta["prior_params"].get("flux_lower", meta["prior_params"].get("flux_scale"))
+    fluxes = (fl_lo * (1 + rng.pareto(1.0, (T, N, D)))).astype(np.float32)
+    locs, fluxes = locs * live[..., None], fluxes * live
+    p = abi_prior(meta)
+    p.min_objects, p.max_objects = 0, D
+    p.loc_high[0], p.loc_high[1] = H + pad, W + pad
+    if meta["model"] == "m71":
+        p.count_rate = meta["prior_params"]["counts_rate"] * (H + 2 * pad) * (W + 2 * pad)
+    k = A.MHParams()
+    k.num_iters, k.locs_stdev, k.fluxes_stdev = 0, 0.1, 2.5
+    k.fluxes_min, k.fluxes_max = float(fl_lo), 1e6
+    k.locs_min[0] = k.locs_min[1] = -pad
+    k.locs_max[0], k.locs_max[1] = H + pad, W + pad
+    tau = np.array([0.3, 0.8], np.float32)
+    ev = backend.agg_mutate(m, p, k, axis, tiles, counts, locs, fluxes, tau)
+    cc, cl, cf = backend.agg_unjoin(locs, fluxes, axis, half)
+    assert np.array_equal(cc.sum(1), counts)
+    if axis == 0:
+        child_tiles = np.stack([tiles[:, :half], tiles[:, half:]], 1)
+    else:
+        child_tiles = np.stack([tiles[:, :, :half], tiles[:, :, half:]], 1)
+    ch, cw = child_tiles.shape[-2:]
+    child_ll = backend.loglik(m, child_tiles.reshape(2 * T, ch, cw), cl.reshape(2 * T, N, D, 2), cf.reshape(2 * T, N, D))
+    child_sum = child_ll.reshape(T, 2, N).sum(1)
+    parent_ll = backend.loglik(m, tiles, locs, fluxes)
+    assert rel_err(ev["parent_loglik"], parent_ll) < RTOL and rel_err(ev["child_loglik"], child_sum) < RTOL
+    om = oracle_model(meta)
+    ref_child = O.loglik(om, child_tiles.reshape(2 * T, ch, cw), cl.reshape(2 * T, N, D, 2), cf.reshape(2 * T, N, D)).reshape(T, 2, N).sum(1)
+    ref_parent = O.loglik(om, tiles, locs, fluxes)
+    assert rel_err(ev["parent_loglik"], ref_parent) < RTOL and rel_err(ev["child_loglik"], ref_child) < RTOL
+    scale = np.max(np.abs(ref_child))
+    assert np.max(np.abs(ev["loglik_diff"] - (ref_parent - ref_child))) < RTOL * scale
+    lp = backend.prior_logprob(p, counts, locs, fluxes)
+    want = lp + (1 - tau)[:, None] * ref_child + tau[:, None] * ref_parent
+    ok = np.isfinite(want)
+    assert ok.mean() > 0.5 and rel_err(ev["log_target"][ok], want[ok]) < RTOL
+    assert np.all(np.isneginf(ev["log_target"][~ok]) | np.isnan(ev["log_target"][~ok]))
+    # wrong axis for the shape / unsupported shape
+    with pytest.raises(Exception):
+        backend.agg_mutate(m, p, k, 1 - axis, tiles, counts, locs, fluxes, tau)

@@ -1144,19 +1144,34 @@ struct AggOut {
     float half;
 };
 
-// The bridge-target sweep.  A particle is owned by TPP lanes as in loglik_kernel; every sweep renders the
-// whole catalog twice in one pass -- the parent image and the "children" image in which a star only reaches
-// the pixels of its own half (which is what evaluating the two child tiles on their own catalogs amounts to:
-// the half boundary is an integer, so pixel-to-star offsets and the floor()-anchored PSF patch are the same
-// in the child's frame).  No incremental rate image: merged catalogs are mutated for far fewer sweeps than
-// leaf tiles, and the cost is D star renders per sweep.
+// The bridge-target sweep.  A particle is owned by TPP lanes as in loglik_kernel and mh_kernel.  Two rate
+// images live in shared memory for the whole launch: the parent image and the "children" image, in which a star
+// only reaches the pixels of its own half -- which is what evaluating the two child tiles on their own catalogs
+// amounts to: the half boundary is an integer, so pixel-to-star offsets and the floor()-anchored PSF patch are
+// the same in the child's frame.  A sweep renders the old and the new star once each (star_accumulate) and
+// updates both images' lane pixels incrementally, like mh_kernel; it = -1 is the full render of the entry state.
+template <int RPT, int W, int H, int AXIS>
+__device__ __forceinline__ void agg_split_add(const float (&tmp)[RPT * W], bool second, int row0, float (&accP)[RPT * W],
+                                              float (&accC)[RPT * W]) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+            const bool pix_second = AXIS == 0 ? (row0 + r >= H / 2) : (c >= W / 2);
+            accP[r * W + c] += tmp[r * W + c];
+            accC[r * W + c] += (pix_second == second) ? tmp[r * W + c] : 0.0f;
+        }
+}
+
 template <int MODEL, int H, int W, int TPP, int AXIS>
 __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOut o) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
     float* s_tile = smem;
     float* s_lgam = s_tile + HW;
-    float* s_star = s_lgam + HW;  // [3*D][PB]
+    float* s_star = s_lgam + HW;               // [3*D][PB]
+    float* s_rateP = s_star + 3 * a.D * PB;    // [PPT][kBT]
+    float* s_rateC = s_rateP + PPT * kBT;      // [PPT][kBT]
 
     const int t = blockIdx.x / a.blocks_per_tile;
     if (a.active != nullptr && a.active[t] == 0) return;
@@ -1173,6 +1188,10 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
     const bool valid = pi < n_here;
     const size_t pn = pbase + pi;
     const float* my_star = s_star + pi;
+    float4* rateP = reinterpret_cast<float4*>(s_rateP) + threadIdx.x;  // [PPT/4][kBT] float4
+    float4* rateC = reinterpret_cast<float4*>(s_rateC) + threadIdx.x;
+    const float* xs = s_tile + row0 * W;
+    const float* lg = s_lgam + row0 * W;
     const float count = valid ? a.counts[pn] : 0.0f;
     const int icount = (int)count;
     const float tau = a.tau[t];
@@ -1183,16 +1202,27 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
     const float isl = (1.0f / sl) * kInvSqrt2, isf = (1.0f / sf) * kInvSqrt2;
     const bool wide_l = fminf(a.mh.locs_max[0] - a.mh.locs_min[0], a.mh.locs_max[1] - a.mh.locs_min[1]) >= 12.0f * sl;
     const bool wide_f = (a.mh.fluxes_max - a.mh.fluxes_min) >= 12.0f * sf;
+    // log prior kept as in mh_kernel: finite part + number of live stars outside the support
+    float prior_fin = 0.0f;
+    int prior_bad = 0;
+    for (int d = 0; d < D; ++d)
+        if ((float)d < count) {
+            int bad;
+            prior_fin += star_prior_term(a.pk, my_star[(d * 3 + 0) * PB], my_star[(d * 3 + 1) * PB],
+                                         my_star[(d * 3 + 2) * PB], bad);
+            prior_bad += bad;
+        }
     int last_acc = 0;
     float cached = 0.0f, ll_par = 0.0f, ll_chi = 0.0f;
 
     for (int it = -1; it < a.mh.num_iters; ++it) {
+        const bool full = it < 0;
         int k = 0;
         bool live = false;
         float u0 = 0.5f, u1 = 0.5f, uf = 0.5f, ua = 0.5f;
         float l0 = 0.f, l1 = 0.f, f = 0.f, pl0 = 0.f, pl1 = 0.f, pf = 0.f, lq = 0.f;
         const size_t e = ((size_t)max(it, 0) * a.T + t) * N + (n0 + pi);
-        if (it >= 0) {
+        if (!full) {
             if (a.tape_comp != nullptr) {
                 if (valid) {
                     k = a.tape_comp[e];
@@ -1220,48 +1250,60 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
                 lq = (lq0 + lq1) + lqf;
             }
         }
-        // ---- both images of the (proposed) catalog, and its prior
+        // ---- changes of both images on the lane's pixels: all D stars (entry) or -old star +new star (sweep)
         float accP[PPT], accC[PPT];
 #pragma unroll
         for (int p = 0; p < PPT; ++p) { accP[p] = 0.0f; accC[p] = 0.0f; }
-        float prior_fin = 0.0f;
-        int prior_bad = 0;
+        const int ns = full ? D : (live ? 2 : 0);
 #pragma unroll 1
-        for (int s = 0; s < D; ++s) {
-            float s0 = my_star[(s * 3 + 0) * PB], s1 = my_star[(s * 3 + 1) * PB], sfl = my_star[(s * 3 + 2) * PB];
-            if (it >= 0 && live && s == k) { s0 = pl0; s1 = pl1; sfl = pf; }
-            if ((float)s < count) {
-                int bad;
-                prior_fin += star_prior_term(a.pk, s0, s1, sfl, bad);
-                prior_bad += bad;
+        for (int s = 0; s < ns; ++s) {
+            float s0, s1, sw;
+            if (full) {
+                s0 = my_star[(s * 3 + 0) * PB]; s1 = my_star[(s * 3 + 1) * PB]; sw = m.c0 * my_star[(s * 3 + 2) * PB];
+            } else if (s == 0) {
+                s0 = l0; s1 = l1; sw = -(m.c0 * f);
+            } else {
+                s0 = pl0; s1 = pl1; sw = m.c0 * pf;
             }
-            const float sw = m.c0 * sfl;
             if (sw == 0.0f) continue;
             float tmp[PPT];
 #pragma unroll
             for (int p = 0; p < PPT; ++p) tmp[p] = 0.0f;
             star_accumulate<MODEL, RPT, W>(m, s0, s1, sw, row0, tmp);
-            const bool second = (AXIS == 0 ? s0 : s1) > o.half;  // aggregate.py:279-281: first child iff loc <= half
+            // aggregate.py:279-281: a star belongs to the first child iff loc_axis <= half
+            agg_split_add<RPT, W, H, AXIS>(tmp, (AXIS == 0 ? s0 : s1) > o.half, row0, accP, accC);
+        }
+        if (full) {
 #pragma unroll
-            for (int r = 0; r < RPT; ++r)
-#pragma unroll
-                for (int c = 0; c < W; ++c) {
-                    const bool pix_second = AXIS == 0 ? (row0 + r >= H / 2) : (c >= W / 2);
-                    accP[r * W + c] += tmp[r * W + c];
-                    accC[r * W + c] += (pix_second == second) ? tmp[r * W + c] : 0.0f;
-                }
+            for (int g = 0; g < PPT / 4; ++g) {
+                rateP[g * kBT] = make_float4(accP[4 * g] + m.bg, accP[4 * g + 1] + m.bg, accP[4 * g + 2] + m.bg, accP[4 * g + 3] + m.bg);
+                rateC[g * kBT] = make_float4(accC[4 * g] + m.bg, accC[4 * g + 1] + m.bg, accC[4 * g + 2] + m.bg, accC[4 * g + 3] + m.bg);
+                accP[4 * g] = accP[4 * g + 1] = accP[4 * g + 2] = accP[4 * g + 3] = 0.0f;
+                accC[4 * g] = accC[4 * g + 1] = accC[4 * g + 2] = accC[4 * g + 3] = 0.0f;
+            }
         }
         float q, sg;
-        pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
-            return make_float4(accP[4 * g] + m.bg, accP[4 * g + 1] + m.bg, accP[4 * g + 2] + m.bg, accP[4 * g + 3] + m.bg);
+        pixel_loglik_sum<MODEL, RPT, W>(m, xs, lg, [&](int g) {
+            const float4 r = rateP[g * kBT];
+            return make_float4(r.x + accP[4 * g], r.y + accP[4 * g + 1], r.z + accP[4 * g + 2], r.w + accP[4 * g + 3]);
         }, q, sg);
         const float llp = finish_loglik<MODEL>(group_sum<TPP>(q), group_sum<TPP>(sg), HW);
-        pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
-            return make_float4(accC[4 * g] + m.bg, accC[4 * g + 1] + m.bg, accC[4 * g + 2] + m.bg, accC[4 * g + 3] + m.bg);
+        pixel_loglik_sum<MODEL, RPT, W>(m, xs, lg, [&](int g) {
+            const float4 r = rateC[g * kBT];
+            return make_float4(r.x + accC[4 * g], r.y + accC[4 * g + 1], r.z + accC[4 * g + 2], r.w + accC[4 * g + 3]);
         }, q, sg);
         const float llc = finish_loglik<MODEL>(group_sum<TPP>(q), group_sum<TPP>(sg), HW);
-        const float target = ((prior_bad ? -INFINITY : count_lp + prior_fin) + (1.0f - tau) * llc) + tau * llp;
-        if (it < 0) {
+        float fin_p = prior_fin;
+        int bad_p = prior_bad;
+        if (!full && live) {
+            int bad_old, bad_new;
+            const float t_old = star_prior_term(a.pk, l0, l1, f, bad_old);
+            const float t_new = star_prior_term(a.pk, pl0, pl1, pf, bad_new);
+            fin_p = (prior_fin - t_old) + t_new;
+            bad_p = prior_bad - bad_old + bad_new;
+        }
+        const float target = ((bad_p ? -INFINITY : count_lp + fin_p) + (1.0f - tau) * llc) + tau * llp;
+        if (full) {
             cached = target; ll_par = llp; ll_chi = llc;
             continue;
         }
@@ -1269,9 +1311,19 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
         float alpha = ex2_fast(log_alpha * kLog2e);
         if (alpha > 1.0f) alpha = 1.0f;
         const bool accept = (ua <= alpha);
-        __syncwarp();
+        __syncwarp();  // every lane of the particle has read the old star
         if (accept) {
+#pragma unroll
+            for (int g = 0; g < PPT / 4; ++g) {
+                float4 r = rateP[g * kBT];
+                r.x += accP[4 * g]; r.y += accP[4 * g + 1]; r.z += accP[4 * g + 2]; r.w += accP[4 * g + 3];
+                rateP[g * kBT] = r;
+                float4 c = rateC[g * kBT];
+                c.x += accC[4 * g]; c.y += accC[4 * g + 1]; c.z += accC[4 * g + 2]; c.w += accC[4 * g + 3];
+                rateC[g * kBT] = c;
+            }
             ll_par = llp; ll_chi = llc;
+            prior_fin = fin_p; prior_bad = bad_p;
             if (sub == 0 && live) {
                 s_star[(k * 3 + 0) * PB + pi] = pl0;
                 s_star[(k * 3 + 1) * PB + pi] = pl1;
@@ -1303,7 +1355,8 @@ template <int MODEL, int H, int W, int TPP, int AXIS>
 int launch_agg_t(MHArgs a, const AggOut& o, cudaStream_t st) {
     constexpr int PB = kBT / TPP;
     a.blocks_per_tile = (a.N + PB - 1) / PB;
-    const size_t smem = sizeof(float) * ((size_t)2 * H * W + (size_t)3 * a.D * PB);
+    constexpr int PPT = (H / TPP) * W;
+    const size_t smem = sizeof(float) * ((size_t)2 * H * W + (size_t)3 * a.D * PB + (size_t)2 * PPT * kBT);
     const long long grid = (long long)a.T * a.blocks_per_tile;
     if (grid >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_agg_mutate: grid too large");
 #ifndef SMC_HOSTSIM

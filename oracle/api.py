@@ -383,6 +383,78 @@ def match_catalogs(true_counts, true_locs, true_fluxes, est_counts, est_locs, es
     return out
 
 
+# ---- Aggregate tree merge (smcdet/aggregate.py), numpy restatement ------------------------------------------
+def _compact_nonzero(v, width):
+    """Stable "nonzero entries first" along the last axis, cut / zero-padded to ``width`` -- what
+    torch.sort(mask, descending=True) + gather does in aggregate.py:252-262 (equal keys keep their order)."""
+    out = np.zeros(v.shape[:-1] + (width,), dtype=v.dtype)
+    flat, oflat = v.reshape(-1, v.shape[-1]), out.reshape(-1, width)
+    for i in range(flat.shape[0]):
+        nz = flat[i][flat[i] != 0][:width]
+        oflat[i, : nz.shape[0]] = nz
+    return out
+
+
+def agg_join(counts, locs, fluxes, axis, dim):
+    """drop_sources_from_overlap + join (aggregate.py:189-265) on a [nH, nW] grid of child tiles; returns the parent
+    grid's counts [.., N], locs [.., N, 2M, 2], fluxes [.., N, 2M] (the reference then cuts to the largest count)."""
+    locs, fluxes = _arr(locs, np.float32).copy(), _arr(fluxes, np.float32).copy()
+    nH, nW, N, M, _ = locs.shape
+    sl_even = (slice(0, None, 2), slice(None)) if axis == 0 else (slice(None), slice(0, None, 2))
+    sl_odd = (slice(1, None, 2), slice(None)) if axis == 0 else (slice(None), slice(1, None, 2))
+    keep = np.zeros((nH, nW, N, M), dtype=bool)
+    la = locs[..., axis]
+    keep[sl_even] = (la[sl_even] < dim) & (la[sl_even] != 0)          # aggregate.py:191-193 / :206-208
+    keep[sl_odd] = la[sl_odd] > 0                                      # aggregate.py:198 / :213
+    cnt = keep.sum(-1).astype(np.float32)
+    locs, fluxes = locs * keep[..., None], fluxes * keep
+    shifted = locs.copy()
+    odd_axis = shifted[sl_odd][..., axis]
+    shifted[sl_odd + (Ellipsis, axis)] = np.where(odd_axis != 0, odd_axis + np.float32(dim), 0)   # aggregate.py:243-248
+    a, b = shifted[sl_even], shifted[sl_odd]
+    both_l = np.concatenate([a, b], axis=-2)                           # "(t M)": first child's slots, then the second's
+    both_f = np.concatenate([fluxes[sl_even], fluxes[sl_odd]], axis=-1)
+    out_l = np.stack([_compact_nonzero(both_l[..., 0], 2 * M), _compact_nonzero(both_l[..., 1], 2 * M)], -1)
+    return cnt[sl_even] + cnt[sl_odd], out_l, _compact_nonzero(both_f, 2 * M)
+
+
+def agg_unjoin(locs, fluxes, axis, half):
+    """unjoin (aggregate.py:267-324) of [T, N, D] parent catalogs; children parent-major: [T, 2, N, ...]."""
+    locs, fluxes = _arr(locs, np.float32), _arr(fluxes, np.float32)
+    T, N, D, _ = locs.shape
+    first = locs[..., axis] <= half                                     # aggregate.py:279-281
+    cl, cf, cc = [], [], []
+    for c, m in enumerate([first, ~first]):
+        l = locs * m[..., None]
+        if c == 1:
+            l = l.copy()
+            l[..., axis] = np.where(l[..., axis] != 0, l[..., axis] - np.float32(half), 0)   # aggregate.py:295-299
+        cl.append(np.stack([_compact_nonzero(l[..., 0], D), _compact_nonzero(l[..., 1], D)], -1))
+        cf.append(_compact_nonzero(fluxes * m, D))
+        cc.append((m & (locs != 0).all(-1)).sum(-1).astype(np.float32))  # aggregate.py:320-322
+    return np.stack(cc, 1), np.stack(cl, 1), np.stack(cf, 1)
+
+
+def agg_logliks(model, tiles, locs, fluxes, axis, dtype=np.float32):
+    """(parent loglik, sum of the two children's) as Aggregate.run computes them (aggregate.py:533-541)."""
+    tiles = _arr(tiles, dtype)
+    T, H, W = tiles.shape
+    half = (H if axis == 0 else W) // 2
+    _, cl, cf = agg_unjoin(locs, fluxes, axis, half)
+    kids = np.stack([tiles[:, :half], tiles[:, half:]], 1) if axis == 0 else np.stack([tiles[:, :, :half], tiles[:, :, half:]], 1)
+    N, D = cl.shape[2], cl.shape[3]
+    child = loglik(model, kids.reshape(2 * T, *kids.shape[2:]), cl.reshape(2 * T, N, D, 2), cf.reshape(2 * T, N, D), dtype=dtype)
+    return loglik(model, tiles, locs, fluxes, dtype=dtype), child.reshape(T, 2, N).sum(1)
+
+
+def agg_log_target(model, prior, tiles, counts, locs, fluxes, tau, axis, dtype=np.float32):
+    """Aggregate.log_target (aggregate.py:105-128)."""
+    par, kid = agg_logliks(model, tiles, locs, fluxes, axis, dtype=dtype)
+    lp = prior_logprob(prior, counts, locs, fluxes, dtype=dtype)
+    tau = np.asarray(tau, dtype=dtype).reshape(-1, 1)
+    return lp + (1 - tau) * kid + tau * par
+
+
 def num_threads():
     return int(lib().oracle_num_threads())
 

@@ -637,3 +637,28 @@ def test_aggregate_bridge_kernel_equals_unjoin_plus_loglik(backend, model_name, 
     # wrong axis for the shape / unsupported shape
     with pytest.raises(Exception):
         backend.agg_mutate(m, p, k, 1 - axis, tiles, counts, locs, fluxes, tau)
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+def test_aggregate_join_on_larger_grids_against_oracle(backend, axis):
+    """4 x 2 / 2 x 4 grids (several parents per row and column, where the pairing of children matters) with empty
+    slots, stars in the sibling's territory and exact zeros: kernel == numpy restatement, bit for bit."""
+    rng = np.random.default_rng(11 + axis)
+    nH, nW = (4, 2) if axis == 0 else (2, 4)
+    N, M, dim, pad = 33, 5, 8, 2
+    counts = rng.integers(0, M + 1, (nH, nW, N))
+    live = np.arange(M)[None, None, None, :] < counts[..., None]
+    locs = rng.uniform(-pad, dim + pad, (nH, nW, N, M, 2)).astype(np.float32) * live[..., None]
+    fluxes = rng.uniform(0.1, 50, (nH, nW, N, M)).astype(np.float32) * live
+    locs[0, 0, 0, 0, axis] = dim
+    locs[-1, -1, 1, 0, axis] = 0.0
+    want = O.agg_join(counts.astype(np.float32), locs, fluxes, axis, dim)
+    got = backend.agg_join(locs, fluxes, axis, dim)
+    for w, g_ in zip(want, got):
+        assert np.array_equal(w, g_)
+    assert want[0].shape == ((2, 2, N))
+    T = 4
+    D = 2 * M
+    cu_, lu, fu = backend.agg_unjoin(got[1].reshape(T, N, D, 2), got[2].reshape(T, N, D), axis, dim)
+    wc, wl, wf = O.agg_unjoin(got[1].reshape(T, N, D, 2), got[2].reshape(T, N, D), axis, dim)
+    assert np.array_equal(cu_, wc) and np.array_equal(lu, wl) and np.array_equal(fu, wf)

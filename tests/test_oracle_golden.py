@@ -165,3 +165,38 @@ def test_oracle_match_catalogs_reproduces_reference():
                            g["est_fluxes"], g["index"], m["locs_tol"], m["mags_tol"], g["mag_bins"])
     for got, name in zip(out, ["true_total", "true_match", "est_total", "est_match"]):
         assert np.array_equal(got, g[name]), name
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_oracle_aggregate_building_blocks_reproduce_reference(level):
+    """numpy restatement of drop_sources_from_overlap + join, unjoin and Aggregate.log_target against the
+    reference's own methods (aggregate_m71.npz)."""
+    import numpy as np
+
+    from goldenlib import Golden, O, oracle_model, oracle_prior, rel_err
+
+    g = Golden("aggregate_m71")
+    L = g.meta[f"L{level}"]
+    axis, D, N = L["axis"], L["D"], g.meta["N"]
+    child_dim = (L["dimH"] if axis == 0 else L["dimW"]) // 2
+    c, l, f = O.agg_join(g[f"L{level}_in_counts"], g[f"L{level}_in_locs"], g[f"L{level}_in_fluxes"], axis, child_dim)
+    assert np.array_equal(c, g[f"L{level}_counts"])
+    assert np.array_equal(l[..., :D, :], g[f"L{level}_locs"]) and np.array_equal(f[..., :D], g[f"L{level}_fluxes"])
+    T = L["numH"] * L["numW"]
+    locs, fluxes = g[f"L{level}_locs"].reshape(T, N, D, 2), g[f"L{level}_fluxes"].reshape(T, N, D)
+    cc, cl, cf = O.agg_unjoin(locs, fluxes, axis, child_dim)
+    want = g[f"L{level}_child_locs"]
+    want = np.stack([want[:L["numH"]], want[L["numH"]:]], 2) if axis == 0 else np.stack([want[:, :L["numW"]], want[:, L["numW"]:]], 2)
+    assert np.array_equal(cl.reshape(want.shape), want)
+    tiles = g[f"L{level}_data"].reshape(T, L["dimH"], L["dimW"])
+    par, kid = O.agg_logliks(oracle_model(g.meta), tiles, locs, fluxes, axis)
+    assert rel_err(par, g[f"L{level}_parent_loglik"].reshape(T, N)) < 1e-5
+    assert rel_err(par - kid, g[f"L{level}_loglik_diff"].reshape(T, N)) < 1e-4
+    meta = dict(g.meta, D=D)
+    pr = oracle_prior(meta)
+    pad = g.meta["pad"]
+    pr.loc_high[0], pr.loc_high[1] = L["dimH"] + pad, L["dimW"] + pad
+    pr.count_rate = g.meta["prior_params"]["counts_rate"] * (L["dimH"] + 2 * pad) * (L["dimW"] + 2 * pad)
+    lt = O.agg_log_target(oracle_model(g.meta), pr, tiles, g[f"L{level}_counts"].reshape(T, N), locs, fluxes,
+                          g[f"L{level}_tau"].reshape(T), axis)
+    assert rel_err(lt, g[f"L{level}_log_target"].reshape(T, N)) < 1e-5

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--stars", type=int, default=6)
     ap.add_argument("--mh-iters", type=int, default=25)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--merge", action="store_true", help="finish with the Aggregate tree merge of the field (rank 0); "
+                    "needs --tiles 4 or 16 (a 2x2 / 4x4 grid of 8x8 tiles)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -57,6 +59,12 @@ def main():
         s = out["summaries"]
         print(f"{a.tiles} tiles on {world} GPU(s): mean posterior count {s[:, 4].mean():.3f}, "
               f"mean logZ {s[:, 0].mean():.2f}, all at temperature 1: {bool((s[:, 2] == 1).all())}")
+    if a.merge:
+        side = int(round(a.tiles ** 0.5))
+        agg = job.aggregate((side, side), SingleComponentMH(10, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"]))
+        if rank == 0:
+            print(f"tree merge to one {agg.dimH}x{agg.dimW} tile: mean detected count "
+                  f"{agg.pruned_counts.float().mean():.2f}, detected flux {agg.pruned_fluxes.sum(-1).mean():.1f}")
     if a.check:
         from smcdet_b200.sampler import SMCsampler
 

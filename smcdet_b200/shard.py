@@ -65,6 +65,7 @@ class ShardedSMC(object):
             self.world, self.rank = 1, 0
         self.local_ids = shard_tile_ids(self.num_tiles, self.world, self.rank)
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._tiles, self._device = tiles, dev
         local = tiles[self.local_ids].to(dev).unsqueeze(1)  # [T_r, 1, h, w]
         self.sampler = SMCsampler(local, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs,
                                   ess_threshold_prop, resample_method, flux_detection_threshold, max_smc_iters,
@@ -93,3 +94,28 @@ class ShardedSMC(object):
         """All-gather the named per-tile results into global tile order ([T, ...] on every rank)."""
         local = self.local_results()
         return {k: gather_tiles(local[k].contiguous(), self.num_tiles, self.group) for k in keys}
+
+    def aggregate(self, grid, MutationKernel, *, resample_method=None, ess_threshold_prop=0.5, print_every=10**6,
+                  root_only=True):
+        """Gather every tile's weighted catalogs and run the divide-and-conquer tree merge (``Aggregate.run``) on
+        the field laid out as ``grid`` = (numH, numW) tiles in global tile order (row-major).  The gather is the
+        only collective; the merge itself runs on rank 0 (``root_only``) or redundantly on every rank.  Returns the
+        ``Aggregate`` (None on the other ranks)."""
+        from .aggregate import Aggregate
+
+        numH, numW = grid
+        if numH * numW != self.num_tiles:
+            raise ValueError("grid does not match the number of tiles")
+        out = self.gather(keys=("counts", "locs", "fluxes", "weights", "summaries"))
+        if root_only and self.rank != 0:
+            return None
+        s = self.sampler
+        n, d = out["counts"].shape[1], out["fluxes"].shape[-1]
+        data = self._tiles.to(self._device).reshape(numH, numW, *self._tiles.shape[1:])
+        agg = Aggregate(s.Prior, s.ImageModel, MutationKernel, data, out["counts"].view(numH, numW, n),
+                        out["locs"].view(numH, numW, n, d, 2), out["fluxes"].view(numH, numW, n, d),
+                        out["weights"].view(numH, numW, n), out["summaries"][:, 0].reshape(numH, numW),
+                        s.flux_detection_threshold, resample_method or s.resample_method, ess_threshold_prop,
+                        print_every=print_every)
+        agg.run()
+        return agg

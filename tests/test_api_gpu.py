@@ -794,3 +794,69 @@ def test_aggregate_tree_merge_end_to_end():
     direct_flux = float(direct.pruned_fluxes.sum(-1).mean())
     assert abs(merged_count - direct_count) < 1.5, (merged_count, direct_count)
     assert abs(merged_flux / direct_flux - 1) < 0.2, (merged_flux, direct_flux)
+
+
+@pytest.mark.parametrize("name", ["smc_stages_m71", "smc_stages_gauss"])
+def test_aggregate_tree_merge_four_levels_both_models(name):
+    """A 32 x 32 image as 4 x 4 tiles of 8 x 8 merged through all four parent shapes (16x8, 16x16, 32x16, 32x32),
+    for the M71/Normal and the Gaussian-PSF/Poisson model."""
+    from smcdet_b200.aggregate import Aggregate
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden(name)
+    meta = g.meta
+    torch.manual_seed(8)
+    model, prior, mh = build_objects(meta, iters=10)
+    small = cu(g["image"])                       # the fixture's image tiled 2 x 2 -> 32 x 32
+    reps = 32 // small.shape[0]
+    image = small.repeat(reps, reps)
+    s = SMCsampler(image, 8, prior, model, mh, 400, 0.5, "systematic", meta["flux_threshold"], 200, verbose=False)
+    s.run()
+    assert (s.numH, s.numW) == (4, 4)
+    aggmh = SingleComponentMH(5, meta["locs_stdev"], meta["fluxes_stdev"], meta["fluxes_min"], meta["fluxes_max"])
+    agg = Aggregate(s.Prior, s.ImageModel, aggmh, s.tiled_image, s.counts, s.locs, s.fluxes, s.weights,
+                    s.log_normalizing_constant, meta["flux_threshold"], "systematic", 0.5, print_every=10**6)
+    assert agg.num_aggregation_levels == 4
+    agg.run()
+    assert (agg.numH, agg.numW, agg.dimH, agg.dimW) == (1, 1, 32, 32) and torch.equal(agg.data[0, 0], image)
+    assert float(agg.temperature.min()) == 1.0
+    assert torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts)
+    assert torch.isfinite(agg.locs).all() and torch.isfinite(agg.fluxes).all()
+    assert int(agg.pruned_counts.max()) <= agg.locs.shape[-2] and agg.pruned_counts.shape == (1, 1, 400)
+    # SMCsampler and the caller's objects are untouched (Aggregate deep-copies them, aggregate.py:25-27)
+    assert s.Prior.image_height == 8 and s.ImageModel.image_height == 8 and s.Prior.max_objects == meta["D"]
+
+
+def test_sharded_job_feeds_the_tree_merge():
+    """ShardedSMC.aggregate: gather of the weighted catalogs + Aggregate tree merge (one process here; the gather is
+    covered by the gloo tests).  Same result as building the Aggregate from an unsharded SMCsampler by hand."""
+    from smcdet_b200.aggregate import Aggregate
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.sampler import SMCsampler
+    from smcdet_b200.shard import ShardedSMC
+
+    g = Golden("aggregate_m71")
+    meta = g.meta
+    tiles = cu(g["leaf_data"]).reshape(4, 8, 8)
+
+    def kernel():
+        return SingleComponentMH(5, 0.1, 2.5, meta["fluxes_min"], meta["fluxes_max"])
+
+    torch.manual_seed(21)
+    model, prior, mh = build_objects(meta, iters=10)
+    job = ShardedSMC(tiles.cpu(), 8, prior, model, mh, 600, 0.5, "multinomial", meta["flux_threshold"], 200, device=dev()).run()
+    agg = job.aggregate((2, 2), kernel())
+    torch.manual_seed(21)
+    model, prior, mh = build_objects(meta, iters=10)
+    s = SMCsampler(tiles.view(4, 1, 8, 8), 8, prior, model, mh, 600, 0.5, "multinomial", meta["flux_threshold"], 200,
+                   tile_ids=torch.arange(4, device=dev()).view(4, 1), freeze_finished=True, verbose=False)
+    s.run()
+    by_hand = Aggregate(prior, model, kernel(), tiles.view(2, 2, 8, 8), s.counts.view(2, 2, 600), s.locs.view(2, 2, 600, -1, 2),
+                        s.fluxes.view(2, 2, 600, -1), s.weights.view(2, 2, 600), s.log_normalizing_constant.view(2, 2),
+                        meta["flux_threshold"], "multinomial", 0.5, print_every=10**6)
+    by_hand.run()
+    assert (agg.dimH, agg.dimW) == (16, 16) and torch.equal(agg.locs, by_hand.locs)
+    assert torch.equal(agg.pruned_counts, by_hand.pruned_counts)
+    with pytest.raises(ValueError):
+        job.aggregate((3, 2), kernel())

@@ -1373,9 +1373,9 @@ int launch_agg_t(MHArgs a, const AggOut& o, cudaStream_t st) {
 template <int MODEL>
 int dispatch_agg(int h, int w, int axis, const MHArgs& a, const AggOut& o, cudaStream_t st) {
     // a parent tile is two child tiles side by side: 2s x s after a merge along rows, 2s x 2s after the next one
-    if (h == 16 && w == 8 && axis == 0) return launch_agg_t<MODEL, 16, 8, 4, 0>(a, o, st);
-    if (h == 16 && w == 16 && axis == 1) return launch_agg_t<MODEL, 16, 16, 8, 1>(a, o, st);
-    if (h == 32 && w == 16 && axis == 0) return launch_agg_t<MODEL, 32, 16, 16, 0>(a, o, st);
+    if (h == 16 && w == 8 && axis == 0) return launch_agg_t<MODEL, 16, 8, 8, 0>(a, o, st);
+    if (h == 16 && w == 16 && axis == 1) return launch_agg_t<MODEL, 16, 16, 16, 1>(a, o, st);
+    if (h == 32 && w == 16 && axis == 0) return launch_agg_t<MODEL, 32, 16, 32, 0>(a, o, st);
     if (h == 32 && w == 32 && axis == 1) return launch_agg_t<MODEL, 32, 32, 32, 1>(a, o, st);
     return fail(SMCDET_E_UNSUPPORTED, "smcdet_agg_mutate: parent tile must be 16x8, 16x16, 32x16 or 32x32 with the matching axis");
 }

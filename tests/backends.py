@@ -29,6 +29,8 @@ def hostsim_backend():
 class GpuBackend:
     """numpy in / numpy out through libsmcdet_b200.so on cuda:0."""
 
+    is_emulator = False
+
     def __init__(self):
         import torch
 

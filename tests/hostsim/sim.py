@@ -40,6 +40,9 @@ def lib():
     return _lib
 
 
+is_emulator = True  # tests trim their heaviest loops on the (slow) CPU emulation; the GPU tier runs them in full
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

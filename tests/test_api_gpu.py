@@ -860,3 +860,34 @@ def test_sharded_job_feeds_the_tree_merge():
     assert torch.equal(agg.pruned_counts, by_hand.pruned_counts)
     with pytest.raises(ValueError):
         job.aggregate((3, 2), kernel())
+
+
+def test_count_stratified_tiles_into_the_tree_merge():
+    """The stratified pipeline of the reference's drivers on a grid: CS-SMC per tile over counts 0..3 (every
+    (tile, count) stratum tempered on its own), then the Aggregate tree merge of the stratified populations with
+    their inter-count weights and per-tile evidences."""
+    from smcdet_b200.aggregate import Aggregate
+    from smcdet_b200.cssmc import CountStratifiedSMC
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.prior import M71Prior
+
+    g = Golden("aggregate_m71")
+    meta = g.meta
+    pp = meta["prior_params"]
+    torch.manual_seed(13)
+    model, _, mh = build_objects(meta, iters=10)
+    prior = M71Prior(0, 3, pp["counts_rate"], 8, 8, flux_alpha=pp["flux_alpha"], flux_lower=pp["flux_lower"],
+                     flux_upper=pp["flux_upper"], pad=meta["pad"])
+    cs = CountStratifiedSMC(cu(g["image"]), 8, prior, model, mh, 500, 0.5, "multinomial", meta["flux_threshold"], 200,
+                            verbose=False)
+    cs.run()
+    assert cs.posterior_count_probs.shape == (2, 2, 4) and cs.counts.shape == (2, 2, 2000)
+    assert torch.allclose(cs.posterior_count_probs.sum(-1), torch.ones(2, 2, device=dev()), atol=1e-5)
+    assert cs.iters[1:].min() >= 1                      # every non-empty stratum tempered
+    agg = Aggregate(prior, model, SingleComponentMH(5, 0.1, 2.5, meta["fluxes_min"], meta["fluxes_max"]), cs.tiled_image,
+                    cs.counts, cs.locs, cs.fluxes, cs.weights_intercount, cs.log_evidence, meta["flux_threshold"],
+                    "multinomial", 0.5, print_every=10**6)
+    agg.run()
+    assert (agg.dimH, agg.dimW) == (16, 16) and agg.counts.shape == (1, 1, 2000)
+    assert torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts) and float(agg.temperature.min()) == 1.0
+    assert len(agg.counts.unique()) > 1                 # catalogs of several sizes survive the merge

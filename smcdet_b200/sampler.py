@@ -75,6 +75,8 @@ class SMCsampler(object):
         self.iter = 0
         self.history = []
         self.record_history = False
+        self.stage_timing = False
+        self._stage_events = []
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -298,6 +300,7 @@ class SMCsampler(object):
             self._base_seed = None
             self._seed_uses = {}
             self.history = []
+            self._stage_events = []
             self._print("starting...")
             self.initialize()
             self._temper_and_update()
@@ -317,9 +320,9 @@ class SMCsampler(object):
                 )
             if self.freeze_finished:
                 self._active = self.temperature < 1
-            self.resample()
-            self.mutate()
-            self._temper_and_update()
+            self._timed("resample", self.resample)
+            self._timed("mutate", self.mutate)
+            self._timed("temper+update_weights", self._temper_and_update)
             self._record()
 
         self._active = None
@@ -332,6 +335,27 @@ class SMCsampler(object):
             self.MutationKernel.check_status()
         self.has_run = True
         self._print("done!\n")
+
+    def _timed(self, stage, fn):
+        """Run one stage; with ``stage_timing`` set, bracket it with CUDA events on the current stream (tracing hook:
+        the reference only has wall-clock timers around whole runs, experiments/basic/run_smc.py:143-166)."""
+        if not getattr(self, "stage_timing", False):
+            return fn()
+        stream = torch.cuda.current_stream(self._device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = fn()
+        e1.record(stream)
+        self._stage_events.append((stage, e0, e1))
+        return out
+
+    def stage_report(self):
+        """Device milliseconds per stage of the last run() (needs ``stage_timing = True`` before run())."""
+        torch.cuda.synchronize(self._device)
+        ms = {}
+        for stage, e0, e1 in self._stage_events:
+            ms[stage] = ms.get(stage, 0.0) + e0.elapsed_time(e1)
+        return ms
 
     def _record(self):
         """Per-iteration record (temperature, ESS, log Z, acceptance, root-finder evaluations) kept as device

@@ -616,7 +616,10 @@ def test_checkpoint_resume_is_bit_identical(freeze, tmp_path):
     torch.manual_seed(5)
     whole = make()
     whole.record_history = True
+    whole.stage_timing = True
     whole.run()
+    ms = whole.stage_report()
+    assert set(ms) == {"resample", "mutate", "temper+update_weights"} and all(v > 0 for v in ms.values())
     assert len(whole.history) == whole.iter + 1 and float(whole.history[-1]["temperature"].min()) == 1.0
     taus = torch.stack([h["temperature"] for h in whole.history])
     assert (taus[1:] >= taus[:-1]).all()

@@ -48,15 +48,24 @@ def parse():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--tiles-per-gpu", type=int, default=800)
     ap.add_argument("--particles", type=int, default=10000)
-    ap.add_argument("--stars", type=int, default=10)
+    ap.add_argument("--stars", type=int, default=None, help="stars per catalog (default 10; 16 for m71semisynthetic)")
+    ap.add_argument("--workload", default="m71synthetic", choices=["m71synthetic", "m71semisynthetic"],
+                    help="m71semisynthetic = BASELINE.json configs[2]: three times the source density, D = 16 (SURVEY.md 8d)")
     ap.add_argument("--mh-iters", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.stars is None:
+        a.stars = 16 if a.workload == "m71semisynthetic" else 10
+    return a
 
 
 def workload_config(a):
-    return {"workload": "m71synthetic: M71 PSF + Normal likelihood, 8x8 tiles, psf_radius 8, pad 4 "
-                        "(BASELINE.json configs[1]; notebooks/smc.ipynb of the reference)",
+    dense = getattr(a, "workload", "m71synthetic") == "m71semisynthetic"
+    name = ("m71semisynthetic-shaped: as m71synthetic with three times the source density and larger catalogs "
+            "(BASELINE.json configs[2]; SURVEY.md 8d config 3)") if dense else (
+        "m71synthetic: M71 PSF + Normal likelihood, 8x8 tiles, psf_radius 8, pad 4 "
+        "(BASELINE.json configs[1]; notebooks/smc.ipynb of the reference)")
+    return {"workload": name,
             "tiles_per_gpu": a.tiles_per_gpu, "particles_per_tile": a.particles, "stars_per_catalog": a.stars,
             "mh_iters": a.mh_iters, "ess_threshold_prop": 0.5, "resample": "multinomial",
             "loglik_for_tempering": "from the incrementally updated rate image (default; 7e-7 relative drift measured)",
@@ -243,7 +252,8 @@ def make_field(a, rank, dev):
                           flux_lower=DETECTION, flux_upper=PRIOR["flux_upper"], pad=PAD)
     T = a.tiles_per_gpu
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    counts = torch.poisson(torch.full((T,), float(true_prior._count_rate()), device=dev), generator=g).clamp(max=24)
+    density = 3.0 if getattr(a, "workload", "m71synthetic") == "m71semisynthetic" else 1.0
+    counts = torch.poisson(torch.full((T,), density * float(true_prior._count_rate()), device=dev), generator=g).clamp(max=24)
     D = 24
     low, high = -PAD, TILE + PAD
     locs = low + torch.rand(T, 1, 1, D, 2, device=dev, generator=g) * (high - low)

@@ -155,3 +155,31 @@ def test_distribution_classes_follow_their_definitions():
     assert torch.isneginf(lp[0]) and torch.isneginf(lp[3]) and abs(float(lp[1]) + np.log(4)) < 1e-6
     s = u.sample([100])
     assert int(s.min()) >= 2 and int(s.max()) <= 5
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference on the host cores) on a tiny setting: exactly one
+    JSON line on stdout with the contract's keys; and the own arm refuses to run without a GPU instead of
+    falling back."""
+    import json
+    import subprocess
+    import sys
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--particles", "300", "--mh-iters", "3"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and "workload" in d["config"]
+    if not torch.cuda.is_available():
+        own = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
+                             capture_output=True, text=True, timeout=300)
+        assert own.returncode != 0 and "no CPU fallback" in (own.stderr + own.stdout)

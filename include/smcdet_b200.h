@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMCDET_ABI_VERSION 4
+#define SMCDET_ABI_VERSION 5
 
 enum {
     SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
@@ -91,6 +91,10 @@ typedef struct smcdet_mh_params {
     int32_t refresh_loglik; /* 1: loglik_out from a fresh full render of the final state (bit-for-bit what
                                smcdet_loglik returns); 0: from the resident rate image that the sweeps
                                updated incrementally (rounding drift ~1e-6 relative, one render cheaper) */
+    int32_t live_only;      /* 0: the updated component is uniform over all D slots (kernel.py:35-44);
+                               1: uniform over the catalog's live stars j < count, and a catalog without stars
+                               is left as it is -- for populations whose counts are below D (count strata),
+                               where moving an empty slot would create a star the prior never sees */
 } smcdet_mh_params;
 
 /* Injected draws for smcdet_mh_mutate (parity testing).  Entries are the draws the

@@ -2,7 +2,7 @@
 
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 MODEL_GAUSS_POISSON, MODEL_M71_NORMAL = 0, 1
 COUNT_DISCRETE_UNIFORM, COUNT_POISSON, COUNT_NONE = 0, 1, 2
@@ -45,6 +45,7 @@ class MHParams(C.Structure):
         ("fluxes_min", C.c_float), ("fluxes_max", C.c_float),
         ("locs_min", C.c_float * 2), ("locs_max", C.c_float * 2),
         ("refresh_loglik", C.c_int32),
+        ("live_only", C.c_int32),
     ]
 
 

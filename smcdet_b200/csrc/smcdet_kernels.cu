@@ -725,6 +725,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     for (int it = -1; it < it_end; ++it) {
         const bool full = (it < 0) || (it == a.mh.num_iters);
         int k = 0;
+        bool frozen_slot = false;
         float u0 = 0.5f, u1 = 0.5f, uf = 0.5f, ua = 0.5f;
         float l0 = 0.f, l1 = 0.f, f = 0.f, pl0 = 0.f, pl1 = 0.f, pf = 0.f, lq = 0.f;
         const size_t e = ((size_t)max(it, 0) * a.T + t) * N + (n0 + pi);
@@ -746,12 +747,17 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                 u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]); ua = u01_f(r.v[3]);
                 const int sel = it & 3;
                 const uint32_t cw = sel == 0 ? rc.v[0] : (sel == 1 ? rc.v[1] : (sel == 2 ? rc.v[2] : rc.v[3]));
-                k = (int)(((uint64_t)cw * (uint64_t)D) >> 32);
+                k = (int)(((uint64_t)cw * (uint64_t)(a.mh.live_only ? max((int)count, 1) : D)) >> 32);
             }
+            // live_only: only stars j < count move; otherwise the proposal is the current state
+            frozen_slot = a.mh.live_only && !((float)k < count);
+            if (frozen_slot) k = 0;
 
             // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
             l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
-            if constexpr (!MALA) {
+            if (frozen_slot) {
+                pl0 = l0; pl1 = l1; pf = f; lq = 0.0f;  // nothing is rendered or re-priced below
+            } else if constexpr (!MALA) {
                 if (wide_l && wide_f) {
                     const float4 pr = truncnormal_step3_wide(l0, l1, f, sl, isl, sf, isf, a.mh.locs_min[0], a.mh.locs_min[1],
                                                              a.mh.fluxes_min, a.mh.locs_max[0], a.mh.locs_max[1],
@@ -771,7 +777,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
 #pragma unroll
         for (int p = 0; p < PPT; ++p) acc[p] = 0.0f;
         if constexpr (MALA) {
-            if (!full) {
+            if (!full) {  // (a frozen slot runs through the same shuffles as its warp's other particles)
                 // gradient of the log target wrt star k at the current state (kernel.py:159-167), removing the star
                 // from the rate image in the same pass, then the Langevin proposal (kernel.py:170-195)
                 float sP, s0, s1;
@@ -794,11 +800,12 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                 pl0 = truncnormal_propose(qm0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, q0);
                 pl1 = truncnormal_propose(qm1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, q1);
                 pf = truncnormal_propose(qmf, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, qf);
+                if (frozen_slot) { pl0 = l0; pl1 = l1; pf = f; }  // the star removed above is put back unchanged
                 lq = -((q0 + q1) + qf);  // - log q(proposal | current); the reverse term is added below
                 if (pf != 0.0f) star_accumulate<MODEL, RPT, W>(m, pl0, pl1, m.c0 * pf, row0, acc);
             }
         }
-        const int ns = full ? D : (MALA ? 0 : 2);
+        const int ns = full ? D : ((MALA || frozen_slot) ? 0 : 2);
 #pragma unroll 1
         for (int s = 0; s < ns; ++s) {
             float s0, s1, sw;
@@ -835,7 +842,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         // ---- prior of the proposal and the MH ratio (sampler.py:87-91, kernel.py:114-116)
         float fin_p = prior_fin;
         int bad_p = prior_bad;
-        if ((float)k < count) {
+        if ((float)k < count && !frozen_slot) {
             int bad_old, bad_new;
             const float t_old = star_prior_term(a.pk, l0, l1, f, bad_old);
             const float t_new = star_prior_term(a.pk, pl0, pl1, pf, bad_new);
@@ -867,6 +874,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
             lq += (truncnormal_logq(rm0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], wide_l, l0) +
                    truncnormal_logq(rm1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], wide_l, l1)) +
                   truncnormal_logq(rmf, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, wide_f, f);
+            if (frozen_slot) lq = 0.0f;
         }
         const float log_alpha = (target_p - cached) + lq;
         float alpha = ex2_fast(log_alpha * kLog2e);

@@ -6,9 +6,13 @@ SURVEY.md section 0.5); its drivers still speak the stratified interface -- ``nu
 ``sampler.weights_intercount``, a per-(tile, count) ``log_normalizing_constant`` handed to ``Aggregate``
 (experiments/m71synthetic/run_smc.py:129-158).  This class provides that interface on top of the CUDA path:
 
-  for s in min_objects..max_objects:   SMCsampler with exactly s stars per catalog, all tiles in one launch
-                                       (the kernels are launched with D = s, so a stratum costs what its
-                                       catalogs cost; s = 0 is the closed-form likelihood of the empty catalog)
+  strata (tile, s), s = min_objects..max_objects: tempered SMC with exactly s stars per catalog, every stratum
+                                       with its own temperature schedule.  ``batched=True`` (default): all strata
+                                       of all tiles are the pseudo-tiles of ONE sampler -- one stratified prior
+                                       draw, catalogs padded to max_objects slots, MH sweeps restricted to the
+                                       live stars (smcdet_mh_params.live_only) -- so every launch covers the
+                                       whole (tile, count) grid.  ``batched=False``: one sampler per count with
+                                       D = s (s = 0 is the closed-form likelihood of the empty catalog)
   p(s | x)  proportional to  p(s) * Z_s          per tile, from the count prior and the samplers' evidences
   (s^n, z^n): s^n ~ p(s | x), z^n uniform among stratum s^n's equally weighted catalogs
               (indices drawn from ``weights_intercount`` by smcdet_resample)
@@ -29,8 +33,9 @@ from .sampler import SMCsampler
 class CountStratifiedSMC(object):
     def __init__(self, image, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs_per_count, ess_threshold_prop,
                  resample_method, flux_detection_threshold=0.0, max_smc_iters=100, print_every=5, *, num_catalogs=None,
-                 tile_ids=None, verbose=True, keep_samplers=False):
+                 tile_ids=None, verbose=True, keep_samplers=False, batched=True):
         self.keep_samplers = keep_samplers
+        self.batched = batched and int(Prior.max_objects) >= 1
         self.Prior, self.ImageModel, self.MutationKernel = Prior, ImageModel, MutationKernel
         self.tile_dim = tile_dim
         self.num_catalogs_per_count = int(num_catalogs_per_count)
@@ -65,7 +70,48 @@ class CountStratifiedSMC(object):
         z = torch.zeros(self.numH, self.numW, 1, 1, device=self._device)
         return self.ImageModel.loglikelihood(self.tiled_image, z.unsqueeze(-1).expand(-1, -1, -1, -1, 2).contiguous(), z)[..., 0]
 
+    def _run_batched(self):
+        """All (tile, count) strata as pseudo-tiles of one SMCsampler (tile-major, count-minor)."""
+        dev, n = self._device, self.num_catalogs_per_count
+        nh, nw, ns, d = self.numH, self.numW, len(self.count_values), int(self.Prior.max_objects)
+        T = nh * nw
+        real_ids = (torch.arange(T, device=dev, dtype=torch.int64) if self.tile_ids is None
+                    else self.tile_ids.to(device=dev, dtype=torch.int64).reshape(T))
+        counts, locs, fluxes = self.Prior._sample_grid(nh, nw, None, True, n, seed=L.fresh_seed(), tile_ids=real_ids)
+        tiles = self.tiled_image.reshape(T, 1, self.tile_dim, self.tile_dim).repeat_interleave(ns, dim=0).contiguous()
+        pseudo_ids = (real_ids.view(T, 1) * ns + torch.arange(ns, device=dev)).reshape(T * ns, 1)
+        mh = deepcopy(self.MutationKernel)
+        mh.live_only = True
+        smp = SMCsampler(tiles, self.tile_dim, deepcopy(self.Prior), self.ImageModel, mh, n, self.ess_threshold_prop,
+                         self.resample_method, self.flux_detection_threshold, self.max_smc_iters, self.print_every,
+                         tile_ids=pseudo_ids, freeze_finished=True, verbose=self.verbose,
+                         initial_catalogs=(counts.reshape(T * ns, 1, n), locs.reshape(T * ns, 1, n, d, 2),
+                                           fluxes.reshape(T * ns, 1, n, d)))
+        smp.run()
+        if self.keep_samplers:
+            self.samplers["all"] = smp
+        self.iters = torch.full((ns,), int(smp.iter), dtype=torch.int64)
+        self.log_normalizing_constant = smp.log_normalizing_constant.reshape(nh, nw, ns)
+        self.counts = smp.counts.reshape(nh, nw, ns * n)
+        self.locs = smp.locs.reshape(nh, nw, ns * n, d, 2)
+        self.fluxes = smp.fluxes.reshape(nh, nw, ns * n, d)
+
     def run(self):
+        if self.batched:
+            self._run_batched()
+        else:
+            self._run_per_count()
+        dev, n = self._device, self.num_catalogs_per_count
+        # posterior over counts and the inter-count weights of all ns * n catalogs
+        cv = torch.tensor(self.count_values, device=dev, dtype=torch.float32)
+        self.log_count_prior = self.Prior.count_prior.log_prob(cv).to(dev)
+        self.posterior_count_probs = torch.softmax(self.log_normalizing_constant + self.log_count_prior, dim=-1)
+        self.weights_intercount = (self.posterior_count_probs / n).repeat_interleave(n, dim=-1)
+        self.log_evidence = torch.logsumexp(self.log_normalizing_constant + self.log_count_prior, dim=-1)
+        self._draw_joint()
+        self.has_run = True
+
+    def _run_per_count(self):
         dev, n, dmax = self._device, self.num_catalogs_per_count, max(1, self.count_values[-1])
         nh, nw, ns = self.numH, self.numW, len(self.count_values)
         self.log_normalizing_constant = torch.zeros(nh, nw, ns, device=dev)
@@ -92,14 +138,6 @@ class CountStratifiedSMC(object):
             self.counts[:, :, sl] = float(s)
             self.locs[:, :, sl, :s] = smp.locs
             self.fluxes[:, :, sl, :s] = smp.fluxes
-        # posterior over counts and the inter-count weights of all ns * n catalogs
-        cv = torch.tensor(self.count_values, device=dev, dtype=torch.float32)
-        self.log_count_prior = self.Prior.count_prior.log_prob(cv).to(dev)
-        self.posterior_count_probs = torch.softmax(self.log_normalizing_constant + self.log_count_prior, dim=-1)
-        self.weights_intercount = (self.posterior_count_probs / n).repeat_interleave(n, dim=-1)
-        self.log_evidence = torch.logsumexp(self.log_normalizing_constant + self.log_count_prior, dim=-1)
-        self._draw_joint()
-        self.has_run = True
 
     def _draw_joint(self):
         """N (count, catalog) pairs per tile from the stratified population (Algorithm 1, last step)."""

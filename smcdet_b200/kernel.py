@@ -30,6 +30,8 @@ class SingleComponentMH(object):
         # updated incrementally (measured drift after 100 sweeps: 7e-7 relative, tests/test_api_gpu.py), True = from a
         # fresh full render, bit-for-bit what ImageModel.loglikelihood returns (one render per launch dearer)
         self.refresh_loglik = False
+        # True: sweeps update only live stars (j < count); for populations with counts below max_objects
+        self.live_only = False
         self.event_log = None  # set to a list to record (start, end, active, n, iters) CUDA events per launch
 
     def _params(self):
@@ -44,6 +46,7 @@ class SingleComponentMH(object):
         k.locs_min[0], k.locs_min[1] = lo
         k.locs_max[0], k.locs_max[1] = hi
         k.refresh_loglik = 1 if self.refresh_loglik else 0
+        k.live_only = 1 if getattr(self, "live_only", False) else 0
         return k
 
     @staticmethod

@@ -21,13 +21,15 @@ from . import _lib as L
 class SMCsampler(object):
     def __init__(self, image, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
                  resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, tile_ids=None,
-                 freeze_finished=False, verbose=True):
+                 freeze_finished=False, verbose=True, initial_catalogs=None):
         """``image``: square 2-D tensor (reference sampler.py:25-31), or -- an extension used by the
         tile-sharding layer -- an already tiled [numH, numW, tile_dim, tile_dim] tensor.
         Keyword-only extras: ``tile_ids`` [numH, numW] global tile ids keying the Philox streams
         (results then do not depend on how tiles are sharded), ``freeze_finished`` stops mutating
         tiles that reached temperature 1 (the reference keeps mutating them, sampler.py:230),
-        ``verbose`` silences the progress prints."""
+        ``verbose`` silences the progress prints, ``initial_catalogs`` = (counts, locs, fluxes) replaces the
+        prior draw of ``initialize`` (used by the count-stratified sampler, whose pseudo-tiles are the strata of
+        one stratified draw)."""
         dev = image.device if (isinstance(image, torch.Tensor) and image.is_cuda) else L.device()
         self.image = image
         self.tile_dim = tile_dim
@@ -65,6 +67,7 @@ class SMCsampler(object):
         self.has_run = False
 
         self.tile_ids = None if tile_ids is None else tile_ids.to(device=dev, dtype=torch.int64).contiguous()
+        self.initial_catalogs = initial_catalogs
         self.freeze_finished = freeze_finished
         self.verbose = verbose
         self._loglik_key = None
@@ -106,9 +109,15 @@ class SMCsampler(object):
     def initialize(self, *, tape=None):
         """Prior draws, first likelihood, uniform weights (reference sampler.py:57-85).
         ``tape`` = (u_locs, u_fluxes) injects the uniforms of the prior draw."""
-        self.counts, self.locs, self.fluxes = self.Prior._sample_grid(
-            self.numH, self.numW, None, True, self.num_catalogs, tape=tape, seed=self._seed(0), tile_ids=self.tile_ids)
         dev = self._device
+        if self.initial_catalogs is not None:
+            c, l, f = self.initial_catalogs
+            self.counts = L.f32(c, dev).reshape(self.numH, self.numW, self.num_catalogs).clone()
+            self.fluxes = L.f32(f, dev).reshape(self.numH, self.numW, self.num_catalogs, -1).clone()
+            self.locs = L.f32(l, dev).reshape(*self.fluxes.shape, 2).clone()
+        else:
+            self.counts, self.locs, self.fluxes = self.Prior._sample_grid(
+                self.numH, self.numW, None, True, self.num_catalogs, tape=tape, seed=self._seed(0), tile_ids=self.tile_ids)
         self.temperature_prev = torch.zeros(self.numH, self.numW, device=dev)
         self.temperature = torch.zeros(self.numH, self.numW, device=dev)
         self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)

@@ -43,7 +43,7 @@ def test_struct_layouts_match_the_header():
 
     assert ctypes.sizeof(_abi.ModelParams) == 15 * 4
     assert ctypes.sizeof(_abi.PriorParams) == 4 * 4 + 4 + 4 * 4 + 6 * 4
-    assert ctypes.sizeof(_abi.MHParams) == 4 + 4 * 4 + 4 * 4 + 4
+    assert ctypes.sizeof(_abi.MHParams) == 4 + 4 * 4 + 4 * 4 + 4 + 4
     assert ctypes.sizeof(_abi.DrawTape) == 4 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_abi.MHTrace) == 5 * ctypes.sizeof(ctypes.c_void_p)
 

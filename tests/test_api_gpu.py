@@ -662,15 +662,22 @@ def test_count_stratified_smc_against_exact_evidences():
     assert abs(float(g["exact_logz1_coarse"]) - logz1) < 1e-3          # the quadrature has converged
     assert abs(g["reference_runs"][:, 0].mean() - logz1) < 0.5         # and the reference agrees with it
 
-    def run(max_objects, method, seed, n=20000):
+    def run(max_objects, method, seed, n=20000, batched=True):
         torch.manual_seed(seed)
         prior = M71Prior(0, max_objects, pp["counts_rate"], 8, 8, flux_alpha=pp["flux_alpha"], flux_lower=pp["flux_lower"],
                          flux_upper=pp["flux_upper"], pad=g.meta["pad"])
         mh = SingleComponentMH(25, 0.1, 2.5, pp["flux_lower"], pp["flux_upper"])
-        cs = CountStratifiedSMC(image, 8, prior, model, mh, n, 0.5, method, g.meta["flux_threshold"], 200, verbose=False)
+        cs = CountStratifiedSMC(image, 8, prior, model, mh, n, 0.5, method, g.meta["flux_threshold"], 200, verbose=False,
+                                batched=batched)
         cs.run()
         return cs, prior, mh
 
+    # one sampler per count (D = s each) ...
+    seq, _, _ = run(1, "multinomial", 0, batched=False)
+    lzs = seq.log_normalizing_constant[0, 0].cpu().numpy()
+    assert abs(lzs[0] / logz0 - 1) < 1e-5 and abs(lzs[1] - logz1) < 0.15, (lzs, logz0, logz1)
+    assert np.allclose(seq.posterior_count_probs[0, 0].cpu().numpy(), exact, atol=0.015)
+    # ... and all (tile, count) strata as pseudo-tiles of one sampler, MH restricted to live stars (the default)
     cs, prior, mh = run(1, "multinomial", 0)
     lz = cs.log_normalizing_constant[0, 0].cpu().numpy()
     assert abs(lz[0] / logz0 - 1) < 1e-5 and abs(lz[1] - logz1) < 0.15, (lz, logz0, logz1)

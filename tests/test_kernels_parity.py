@@ -667,3 +667,51 @@ def test_aggregate_join_on_larger_grids_against_oracle(backend, axis):
     cu_, lu, fu = backend.agg_unjoin(got[1].reshape(T, N, D, 2), got[2].reshape(T, N, D), axis, dim)
     wc, wl, wf = O.agg_unjoin(got[1].reshape(T, N, D, 2), got[2].reshape(T, N, D), axis, dim)
     assert np.array_equal(cu_, wc) and np.array_equal(lu, wl) and np.array_equal(fu, wf)
+
+
+def test_mh_live_only_equals_a_run_on_the_truncated_catalogs(backend):
+    """smcdet_mh_params.live_only: catalogs with count < D (count strata padded to a common D).  On the same draws a
+    live-only run over [D] slots is bit-identical to an ordinary run over the first `count` slots; empty slots never
+    move, empty catalogs are left alone, and a taped component >= count is a no-op sweep."""
+    g = Golden("mh_m71")
+    meta = g.meta
+    D, c, iters = meta["D"], 4, 5
+    m, p = abi_model(meta), abi_prior(meta)
+    tiles, tau = g.flat("tiles"), g["tau"].reshape(-1)
+    T, N = g.flat("counts").shape
+    locs, fluxes = g.flat("locs").copy(), g.flat("fluxes").copy()
+    locs[:, 7, 2, 0] = meta["tile"] / 2             # undo the golden's star parked on the prior bound
+    locs[:, :, c:], fluxes[:, :, c:] = 0, 0
+    counts = np.full((T, N), float(c), np.float32)
+    comp = (g["comp"][:iters].reshape(iters, T, N) % c).astype(np.int32)
+    tape = dict(comp=comp, u_loc=g["u_loc"][:iters], u_flux=g["u_flux"][:iters], u_acc=g["u_acc"][:iters])
+    k = abi_mh(meta, iters)
+    k.live_only = 1
+    a = backend.mh_mutate(m, p, k, tiles, counts, locs, fluxes, tau, tape=tape)
+    k0 = abi_mh(meta, iters)
+    p0 = abi_prior(meta)
+    p0.max_objects = p0.min_objects = c
+    b = backend.mh_mutate(m, p0, k0, tiles, counts, locs[:, :, :c].copy(), fluxes[:, :, :c].copy(), tau, tape=tape)
+    assert np.array_equal(a["locs"][:, :, :c], b["locs"]) and np.array_equal(a["fluxes"][:, :, :c], b["fluxes"])
+    assert np.array_equal(a["accept"], b["accept"]) and np.array_equal(a["loglik"], b["loglik"])
+    assert np.all(a["locs"][:, :, c:] == 0) and np.all(a["fluxes"][:, :, c:] == 0)
+    assert (a["locs"][:, :, :c] != locs[:, :, :c]).any()
+    # a taped component beyond the count: nothing moves in that sweep
+    tape2 = dict(tape, comp=np.full_like(comp, c + 1))
+    z = backend.mh_mutate(m, p, k, tiles, counts, locs, fluxes, tau, tape=tape2)
+    assert np.array_equal(z["locs"], locs) and np.array_equal(z["fluxes"], fluxes) and np.all(z["accept"] == 1)
+    # Philox draws: empty catalogs stay empty, mixed counts only move live stars
+    mixed = counts.copy()
+    mixed[:, ::3] = 0
+    mixed[:, 1::3] = 2
+    l2, f2 = locs.copy(), fluxes.copy()
+    live = np.arange(D)[None, None, :] < mixed[..., None]
+    l2, f2 = l2 * live[..., None], f2 * live
+    r = backend.mh_mutate(m, p, k, tiles, mixed, l2, f2, tau, seed=9, offset=1)
+    assert np.all(r["fluxes"][~live] == 0) and np.all(r["locs"][~live] == 0)
+    assert np.array_equal(r["locs"][:, ::3], l2[:, ::3])
+    moved = (r["locs"] != l2).any(-1)
+    assert moved[:, 1::3, :2].mean() > 0.3 and moved[:, 2::3, :c].mean() > 0.3
+    # MALA honours it too
+    q = backend.mh_mutate(m, p, k, tiles, mixed, l2, f2, tau, seed=9, offset=1, mala=True)
+    assert np.all(q["fluxes"][~live] == 0) and np.array_equal(q["locs"][:, ::3], l2[:, ::3])

@@ -695,8 +695,9 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                 prior_fin += star_prior_term(a.pk, l0, l1, f, bad);
                 prior_bad += bad;
             }
-            oob |= !(l0 >= a.mh.locs_min[0] && l0 <= a.mh.locs_max[0] && l1 >= a.mh.locs_min[1] &&
-                     l1 <= a.mh.locs_max[1] && f >= a.mh.fluxes_min && f <= a.mh.fluxes_max);
+            if (!a.mh.live_only || (float)d < count)  // with live_only the empty slots are never proposed from
+                oob |= !(l0 >= a.mh.locs_min[0] && l0 <= a.mh.locs_max[0] && l1 >= a.mh.locs_min[1] &&
+                         l1 <= a.mh.locs_max[1] && f >= a.mh.fluxes_min && f <= a.mh.fluxes_max);
         }
         if (a.status != nullptr && valid && sub == 0 && oob) atomicOr(a.status, SMCDET_STATUS_OUT_OF_BOX);
     }

@@ -696,6 +696,9 @@ def test_mh_live_only_equals_a_run_on_the_truncated_catalogs(backend):
     assert np.array_equal(a["accept"], b["accept"]) and np.array_equal(a["loglik"], b["loglik"])
     assert np.all(a["locs"][:, :, c:] == 0) and np.all(a["fluxes"][:, :, c:] == 0)
     assert (a["locs"][:, :, :c] != locs[:, :, :c]).any()
+    assert a["status"] == 0          # empty slots (flux 0 < fluxes_min) are not "outside the proposal box"
+    k0.live_only = 0
+    assert backend.mh_mutate(m, p, k0, tiles, counts, locs, fluxes, tau, tape=tape)["status"] == 1
     # a taped component beyond the count: nothing moves in that sweep
     tape2 = dict(tape, comp=np.full_like(comp, c + 1))
     z = backend.mh_mutate(m, p, k, tiles, counts, locs, fluxes, tau, tape=tape2)

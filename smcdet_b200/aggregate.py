@@ -69,35 +69,55 @@ class Aggregate(object):
 
     # ---- resampling (reference aggregate.py:69-103) -------------------------------------------
     def get_resampled_index(self, weights, multiplier, *, u=None):
-        if int(multiplier) != 1:
-            raise NotImplementedError("resampling to a different number of catalogs belongs to the tree merge")
+        """``int(multiplier * n)`` indices per tile drawn from ``weights`` [numH, numW, n] (reference
+        aggregate.py:69-83; float64 CDF as in SMCsampler.resample)."""
         numH, numW, n = weights.shape
-        T = numH * numW
+        T, num = numH * numW, int(multiplier * n)
+        if num < 1:
+            raise ValueError("multiplier too small: no catalogs would be drawn")
         w = L.f32(weights).view(T, n)
         dev = w.device
         method = A.RESAMPLE_MULTINOMIAL if self.resample_method == "multinomial" else A.RESAMPLE_SYSTEMATIC
-        idx = torch.empty(T, n, device=dev, dtype=torch.int64)
-        cdf = torch.empty(T, n, device=dev, dtype=torch.float64)
+        # smcdet_resample draws as many indices as there are weights: pad the weights with zeros up to a multiple
+        # of `num`; every (width / num)-th point of a systematic grid of `width` points is a grid of `num` points
+        width = num * ((n + num - 1) // num)
+        if width != n:
+            if u is not None:
+                raise ValueError("injected uniforms need multiplier == 1")
+            wp = torch.zeros(T, width, device=dev)
+            wp[:, :n] = w
+            w = wp
+        idx = torch.empty(T, width, device=dev, dtype=torch.int64)
+        cdf = torch.empty(T, width, device=dev, dtype=torch.float64)
         uu = None if u is None else u.to(device=dev, dtype=torch.float64).contiguous()
         L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(), None, None,
-                                        L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64), T, n, L.stream_for(w)))
-        return idx.view(numH, numW, n)
+                                        L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64), T, width, L.stream_for(w)))
+        if width != n:
+            if method == A.RESAMPLE_SYSTEMATIC:
+                idx = idx[:, :: width // num]
+            idx = idx[:, :num].clamp(max=n - 1).contiguous()
+        return idx.view(numH, numW, num)
 
     def apply_resampled_index(self, resampled_index, counts, locs, fluxes):
-        numH, numW, n = resampled_index.shape
+        """reference aggregate.py:85-103"""
+        numH, numW, num = resampled_index.shape
         d = fluxes.shape[-1]
         T = numH * numW
-        idx = resampled_index.to(torch.int64).contiguous().view(T, n)
+        idx = resampled_index.to(torch.int64).contiguous().view(T, num)
         dev = idx.device
         cin = L.f32(counts, dev).view(T, -1)
-        lin = L.f32(locs, dev).view(T, cin.shape[1], d, 2)
-        fin = L.f32(fluxes, dev).view(T, cin.shape[1], d)
-        if cin.shape[1] != n:
-            raise NotImplementedError("resampling to a different number of catalogs belongs to the tree merge")
+        n = cin.shape[1]
+        lin = L.f32(locs, dev).view(T, n, d, 2)
+        fin = L.f32(fluxes, dev).view(T, n, d)
+        ws = torch.full((numH, numW, num), 1.0 / num, device=dev)
+        if num != n:  # a different number of catalogs than came in: plain indexed copies
+            cs = torch.gather(cin, 1, idx)
+            ls = torch.gather(lin, 1, idx.view(T, num, 1, 1).expand(-1, -1, d, 2))
+            fs = torch.gather(fin, 1, idx.view(T, num, 1).expand(-1, -1, d))
+            return cs.view(numH, numW, num), ls.view(numH, numW, num, d, 2), fs.view(numH, numW, num, d), ws
         cs, ls, fs = torch.empty_like(cin), torch.empty_like(lin), torch.empty_like(fin)
         L.check(L.lib().smcdet_gather(L.ptr(idx, torch.int64), L.ptr(cin), L.ptr(lin), L.ptr(fin), L.ptr(cs), L.ptr(ls),
                                       L.ptr(fs), None, T, n, d, L.stream_for(cin)))
-        ws = torch.full((numH, numW, n), 1.0 / n, device=dev)
         return cs.view(numH, numW, n), ls.view(numH, numW, n, d, 2), fs.view(numH, numW, n, d), ws
 
     # ---- prune (reference aggregate.py:326-345) -----------------------------------------------

@@ -244,6 +244,23 @@ def test_aggregate_single_tile_sink():
                      cu(g[f"k{k}_weights"]), torch.zeros(2, 2), 0.25, "systematic", 0.5, merge=False)
     sink.run(u=cu(g[f"k{k}_u"].astype(np.float64)))
     assert np.array_equal(sink.locs.cpu().numpy(), g[f"k{k}_f64_locs"])
+    # a different number of catalogs out than in (the `multiplier` of aggregate.py:69-70), both methods
+    for method in ("systematic", "multinomial"):
+        sink.resample_method = method
+        wts = cu(g[f"k{k}_weights"])
+        for mult in (0.5, 2, 1.5):
+            idx = sink.get_resampled_index(wts, mult)
+            n_in = wts.shape[-1]
+            assert idx.shape == (2, 2, int(mult * n_in)) and int(idx.min()) >= 0 and int(idx.max()) < n_in
+            if method == "systematic":
+                assert bool((idx[..., 1:] >= idx[..., :-1]).all())
+            # systematic resampling: every catalog is drawn floor or ceil (num * weight) times
+            copies = torch.zeros_like(wts).scatter_add_(2, idx, torch.ones_like(idx, dtype=torch.float32))
+            if method == "systematic":
+                assert float((copies - idx.shape[-1] * wts).abs().max()) < 1 + 1e-3
+            cs, ls, fs, ws = sink.apply_resampled_index(idx, cu(g["counts"]), cu(g["locs"]), cu(g["fluxes"]))
+            assert ls.shape[2] == idx.shape[-1] and abs(float(ws.sum(-1).mean()) - 1) < 1e-5
+            assert torch.equal(ls[0, 0, 0], cu(g["locs"])[0, 0, idx[0, 0, 0]])
 
 
 def test_full_size_properties_m71():

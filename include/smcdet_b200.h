@@ -130,6 +130,12 @@ int smcdet_loglik(const smcdet_model_params *model, const float *tiles, const fl
 int smcdet_psf(const smcdet_model_params *model, const float *locs, float *psf, int T, int N,
                int D, int h, int w, void *stream);
 
+/* ImageModel._compute_normalized_psf (smcdet/images.py:25-26), M71ImageModel._compute_unnormalized_psf /
+ * _compute_normalized_psf (images.py:137-145): the PSF as a function of the radius r [n] -> out [n].
+ * normalized = 0 drops the 1/Z of the M71 PSF (no effect for the Gaussian-PSF model). */
+int smcdet_psf_radial(const smcdet_model_params *model, int normalized, const float *r, float *out,
+                      long long n, void *stream);
+
 /* rate image of ImageModel.sample / loglikelihood (smcdet/images.py:78-89, :147-167):
  * rate [T,h,w,N] = sum_d psf_d * flux_d (* adu_per_nmgy) + background. */
 int smcdet_render(const smcdet_model_params *model, const float *locs, const float *fluxes,

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "smcdet_last_error_string": (C.c_char_p, []),
     "smcdet_loglik": (C.c_int, [C.POINTER(ModelParams), _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "smcdet_psf": (C.c_int, [C.POINTER(ModelParams), _P, _P, _I, _I, _I, _I, _I, _P]),
+    "smcdet_psf_radial": (C.c_int, [C.POINTER(ModelParams), _I, _P, _P, C.c_longlong, _P]),
     "smcdet_render": (C.c_int, [C.POINTER(ModelParams), _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "smcdet_prior_logprob": (C.c_int, [C.POINTER(PriorParams), _P, _P, _P, _P, _I, _I, _I, _P]),
     "smcdet_prior_sample": (C.c_int, [C.POINTER(PriorParams), _P, _P, C.c_uint64, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -66,6 +66,8 @@ class Aggregate(object):
         self.ess_threshold_prop = ess_threshold_prop
         self.print_every = print_every
         self.has_run = False
+        self.iter = 0
+        self._logz = None
 
     # ---- resampling (reference aggregate.py:69-103) -------------------------------------------
     def get_resampled_index(self, weights, multiplier, *, u=None):
@@ -190,39 +192,12 @@ class Aggregate(object):
         if (self.numH if axis == 0 else self.numW) % 2 != 0:
             raise ValueError("the tree merge needs an even number of tiles along the merge axis")
         self._resample()
-        T, n, m, counts, locs, fluxes = self._flat_state()
-        dev = counts.device
         nH, nW = self.numH, self.numW
-        pH, pW = (nH // 2, nW) if axis == 0 else (nH, nW // 2)
-        cs = torch.empty(pH * pW, n, device=dev)
-        ls = torch.empty(pH * pW, n, 2 * m, 2, device=dev)
-        fs = torch.empty(pH * pW, n, 2 * m, device=dev)
-        child_dim = self.dimH if axis == 0 else self.dimW
-        L.check(L.lib().smcdet_agg_join(L.ptr(locs), L.ptr(fluxes), axis, float(child_dim), L.ptr(cs), L.ptr(ls), L.ptr(fs),
-                                        nH, nW, n, m, L.stream_for(locs)))
-        d = max(1, int(cs.max().item()))  # max objects detected (aggregate.py:236)
-        data = L.f32(self.data, dev)
-        if axis == 0:
-            self.data = data.reshape(pH, 2, nW, self.dimH, self.dimW).permute(0, 2, 1, 3, 4).reshape(pH, pW, 2 * self.dimH, self.dimW)
-            self._logz = self._logz.reshape(pH, 2, nW).sum(1)
-            self.dimH *= 2
-        else:
-            self.data = data.reshape(nH, pW, 2, self.dimH, self.dimW).permute(0, 1, 3, 2, 4).reshape(pH, pW, self.dimH, 2 * self.dimW)
-            self._logz = self._logz.reshape(nH, pW, 2).sum(2)
-            self.dimW *= 2
-        self.data = self.data.contiguous()
-        self.numH, self.numW = pH, pW
-        self.ImageModel.image_height, self.ImageModel.image_width = self.dimH, self.dimW
-        self.Prior.image_height, self.Prior.image_width = self.dimH, self.dimW
-        self.Prior.max_objects = d
-        self.Prior.update_attrs()
-        self.MutationKernel.locs_min = self.Prior.loc_prior.low
-        self.MutationKernel.locs_max = self.Prior.loc_prior.high
-        self.counts = cs.view(pH, pW, n)
-        self.locs = ls[:, :, :d].contiguous().view(pH, pW, n, d, 2)
-        self.fluxes = fs[:, :, :d].contiguous().view(pH, pW, n, d)
-        self.weights = torch.full((pH, pW, n), 1.0 / n, device=dev)
-        self.num_catalogs_per_count = [[[n] for _ in range(pW)] for _ in range(pH)]
+        self.data, self.counts, self.locs, self.fluxes = self.join(axis, self.data, self.counts, self.locs, self.fluxes)
+        self._logz = self._logz.reshape(nH // 2, 2, nW).sum(1) if axis == 0 else self._logz.reshape(nH, nW // 2, 2).sum(2)
+        n = self.counts.shape[-1]
+        self.weights = torch.full((self.numH, self.numW, n), 1.0 / n, device=self.counts.device)
+        self.num_catalogs_per_count = [[[n] for _ in range(self.numW)] for _ in range(self.numH)]
 
     def run(self, *, u=None, max_iters=500):
         """reference aggregate.py:523-593"""
@@ -262,6 +237,163 @@ class Aggregate(object):
         self.pruned_counts, self.pruned_locs, self.pruned_fluxes = self.prune(self.locs, self.fluxes)
         self.has_run = True
         print("done!\n")
+
+    # ---- the reference's method surface on top of the launches above -----------------------------
+    def log_target(self, axis, ChildImageModel, child_data, child_locs, child_fluxes, parent_data, parent_counts,
+                   parent_locs, parent_fluxes, temperature):
+        """Bridge target of the merge (reference aggregate.py:105-128).  The children's catalogs are a function of
+        the parent's (``unjoin``), so the fused kernel evaluates everything from the parent arguments."""
+        numH, numW, n, d, _ = parent_locs.shape
+        T = numH * numW
+        dev = L.f32(parent_locs).device
+        k = self.MutationKernel._params()
+        k.num_iters = 0
+        model, prior = self.ImageModel._params(), self.Prior._params()
+        tiles = L.f32(parent_data, dev).reshape(T, *parent_data.shape[-2:])
+        out, lld, acc = torch.empty(T, n, device=dev), torch.empty(T, n, device=dev), torch.empty(T, device=dev)
+        locs, fluxes = L.f32(parent_locs, dev).reshape(T, n, d, 2).clone(), L.f32(parent_fluxes, dev).reshape(T, n, d).clone()
+        L.check(L.lib().smcdet_agg_mutate(C.byref(model), C.byref(prior), C.byref(k), int(axis), L.ptr(tiles),
+                                          L.ptr(L.f32(parent_counts, dev).reshape(T, n)), L.ptr(locs), L.ptr(fluxes),
+                                          L.ptr(L.f32(temperature, dev).reshape(T)), L.ptr(lld), None, None, L.ptr(out),
+                                          L.ptr(acc), None, None, 0, 0, None, None, T, n, d, int(tiles.shape[-2]),
+                                          int(tiles.shape[-1]), L.stream_for(tiles)))
+        return out.view(numH, numW, n)
+
+    def tempering_objective(self, loglikelihood, delta):
+        """ESS(delta) - threshold of one stratum (reference aggregate.py:130-138)."""
+        log_numerator = 2 * ((delta * loglikelihood).logsumexp(0))
+        log_denominator = (2 * delta * loglikelihood).logsumexp(0)
+        return (log_numerator - log_denominator).exp() - self.ess_threshold_prop * loglikelihood.shape[0]
+
+    def _temper_update(self, do_temper):
+        T, n = self.numH * self.numW, self.loglik_diff.shape[-1]
+        dev = self.loglik_diff.device
+        lld = self.loglik_diff.reshape(T, n).contiguous()
+        tau, tau_prev = self.temperature.reshape(T).clone(), self.temperature_prev.reshape(T).clone()
+        logz = torch.zeros(T, device=dev) if self._logz is None else self._logz.reshape(T).clone()
+        wlog, weights, ess = torch.empty(T, n, device=dev), torch.empty(T, n, device=dev), torch.empty(T, device=dev)
+        L.check(L.lib().smcdet_temper_update(L.ptr(lld), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold_prop * n),
+                                             int(do_temper), L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz), None, None,
+                                             T, n, L.stream_for(lld)))
+        return tau, tau_prev, weights, logz
+
+    def temper(self):
+        """Adaptive temperature step on ``self.loglik_diff`` (reference aggregate.py:140-174, one stratum per tile)."""
+        tau, tau_prev, _, _ = self._temper_update(1)
+        self.temperature, self.temperature_prev = tau.view(self.numH, self.numW), tau_prev.view(self.numH, self.numW)
+
+    def update_weights(self):
+        """Weights and log normalising constant from the last temperature step (reference aggregate.py:439-483)."""
+        _, _, weights, logz = self._temper_update(0)
+        n = weights.shape[-1]
+        self.weights = self.weights_intracount = weights.view(self.numH, self.numW, n)
+        self._logz = logz.view(self.numH, self.numW)
+        self.log_normalizing_constant = [[[float(self._logz[h, w])] for w in range(self.numW)] for h in range(self.numH)]
+
+    def mutate(self, axis, ChildImageModel=None):
+        """reference aggregate.py:176-187: MutationKernel.num_iters sweeps under ``log_target``."""
+        self._bridge(axis, self.MutationKernel.num_iters)
+
+    def drop_sources_from_overlap(self, axis, counts, locs, fluxes):
+        """Zero the stars a tile holds inside its neighbour's territory (reference aggregate.py:189-218): tiles at even
+        positions along ``axis`` keep 0 != loc < dim, tiles at odd positions keep loc > 0."""
+        dim = self.dimH if axis == 0 else self.dimW
+        coord = locs[..., axis]
+        odd = (torch.arange(locs.shape[axis], device=locs.device) % 2 == 1).view(-1, *([1] * (coord.dim() - 1 - axis)))
+        keep = torch.where(odd, coord > 0, (coord < dim) & (coord != 0))
+        return keep.sum(-1).to(counts.dtype), locs * keep.unsqueeze(-1), fluxes * keep
+
+    def join(self, axis, data, counts, locs, fluxes):
+        """Join neighbouring tiles along ``axis`` (reference aggregate.py:220-265); updates the tile geometry, the
+        prior and the proposal box like the reference and returns [data, counts, locs, fluxes] of the parents."""
+        nH, nW, n, m, _ = locs.shape
+        dev = L.f32(locs).device
+        pH, pW = (nH // 2, nW) if axis == 0 else (nH, nW // 2)
+        cs, ls = torch.empty(pH * pW, n, device=dev), torch.empty(pH * pW, n, 2 * m, 2, device=dev)
+        fs = torch.empty(pH * pW, n, 2 * m, device=dev)
+        child_dim = self.dimH if axis == 0 else self.dimW
+        L.check(L.lib().smcdet_agg_join(L.ptr(L.f32(locs, dev).contiguous()), L.ptr(L.f32(fluxes, dev).contiguous()), axis,
+                                        float(child_dim), L.ptr(cs), L.ptr(ls), L.ptr(fs), nH, nW, n, m, L.stream_for(cs)))
+        d = max(1, int(cs.max().item()))  # max objects detected (aggregate.py:236)
+        data = L.f32(data, dev)
+        if axis == 0:
+            dat = data.reshape(pH, 2, nW, self.dimH, self.dimW).permute(0, 2, 1, 3, 4).reshape(pH, pW, 2 * self.dimH, self.dimW)
+            self.dimH *= 2
+        else:
+            dat = data.reshape(nH, pW, 2, self.dimH, self.dimW).permute(0, 1, 3, 2, 4).reshape(pH, pW, self.dimH, 2 * self.dimW)
+            self.dimW *= 2
+        self.numH, self.numW = pH, pW
+        self.ImageModel.image_height, self.ImageModel.image_width = self.dimH, self.dimW
+        self.Prior.image_height, self.Prior.image_width = self.dimH, self.dimW
+        self.Prior.max_objects = d
+        self.Prior.update_attrs()
+        self.MutationKernel.locs_min = self.Prior.loc_prior.low
+        self.MutationKernel.locs_max = self.Prior.loc_prior.high
+        return [dat.contiguous(), cs.view(pH, pW, n), ls[:, :, :d].contiguous().view(pH, pW, n, d, 2),
+                fs[:, :, :d].contiguous().view(pH, pW, n, d)]
+
+    def unjoin(self, axis, data, locs, fluxes):
+        """Split parent tiles and catalogs back into their two children (reference aggregate.py:267-324), children
+        laid out child-major along ``axis`` as the reference does."""
+        numH, numW, n, d, _ = locs.shape
+        T = numH * numW
+        dev = L.f32(locs).device
+        half = (self.dimH if axis == 0 else self.dimW) / 2
+        cc, cl, cf = torch.empty(T, 2, n, device=dev), torch.empty(T, 2, n, d, 2, device=dev), torch.empty(T, 2, n, d, device=dev)
+        L.check(L.lib().smcdet_agg_unjoin(L.ptr(L.f32(locs, dev).reshape(T, n, d, 2).contiguous()),
+                                          L.ptr(L.f32(fluxes, dev).reshape(T, n, d).contiguous()), axis, float(half),
+                                          L.ptr(cc), L.ptr(cl), L.ptr(cf), T, n, d, L.stream_for(cc)))
+
+        def lay(t):  # [T, 2, ...] -> child-major along the merge axis
+            t = t.view(numH, numW, 2, *t.shape[2:])
+            return torch.cat((t[:, :, 0], t[:, :, 1]), dim=axis)
+
+        data = L.f32(data, dev)
+        h2, w2 = (self.dimH // 2, self.dimW) if axis == 0 else (self.dimH, self.dimW // 2)
+        dat = torch.cat((data[..., :h2, :w2], data[..., self.dimH - h2:, self.dimW - w2:]), dim=axis)
+        return dat, lay(cc), lay(cl), lay(cf)
+
+    def sort_by_count(self):
+        """Order every tile's catalogs by their star count and record the stratum sizes (reference
+        aggregate.py:424-437).  Tempering, weights and resampling of ``run()`` treat a tile as one stratum, so this is
+        bookkeeping for callers that inspect ``num_catalogs_per_count``."""
+        self.counts, order = torch.sort(self.counts, dim=-1, stable=True)
+        d = self.fluxes.shape[-1]
+        self.locs = torch.gather(self.locs, 2, order.view(*order.shape, 1, 1).expand(-1, -1, -1, d, 2))
+        self.fluxes = torch.gather(self.fluxes, 2, order.unsqueeze(-1).expand(-1, -1, -1, d))
+        self.weights = torch.gather(self.weights, 2, order)
+        self.num_catalogs_per_count = [[self.counts[h, w].unique(return_counts=True)[-1].tolist() for w in range(self.numW)]
+                                       for h in range(self.numH)]
+
+    def resample_intracount(self):
+        """Multinomial resampling inside every count stratum given by ``num_catalogs_per_count`` (reference
+        aggregate.py:485-521), all strata of all tiles at once: with the intra-stratum weights normalised to one per
+        stratum, the tile's running sum rises by one per stratum, so a catalog of stratum c draws its replacement at
+        the position where that sum reaches c + u."""
+        numH, numW, n = self.weights.shape
+        dev = self.weights.device
+        stratum = torch.zeros(numH, numW, n, device=dev, dtype=torch.int64)
+        for h in range(numH):
+            for w in range(numW):
+                cuts = torch.tensor(self.num_catalogs_per_count[h][w], device=dev).cumsum(0)[:-1]
+                stratum[h, w] = torch.bucketize(torch.arange(n, device=dev), cuts, right=True)
+        wts = self.weights_intracount if self.weights_intracount is not None else self.weights
+        mass = torch.zeros(numH, numW, n, device=dev, dtype=torch.float64).scatter_add_(2, stratum, wts.double())
+        cdf = (wts.double() / mass.gather(2, stratum)).cumsum(-1)
+        target = stratum.double() + torch.rand(numH, numW, n, device=dev, dtype=torch.float64)
+        index = torch.searchsorted(cdf, target).clamp(max=n - 1)
+        # rounding at a stratum's upper edge must not leak into the next stratum
+        first = torch.zeros(numH, numW, n, device=dev, dtype=torch.int64).scatter_reduce_(
+            2, stratum, torch.arange(n, device=dev).expand(numH, numW, n), "amin", include_self=False)
+        last = torch.zeros(numH, numW, n, device=dev, dtype=torch.int64).scatter_reduce_(
+            2, stratum, torch.arange(n, device=dev).expand(numH, numW, n), "amax", include_self=False)
+        index = torch.minimum(torch.maximum(index, first.gather(2, stratum)), last.gather(2, stratum))
+        d = self.fluxes.shape[-1]
+        self.locs = torch.gather(self.locs, 2, index.view(numH, numW, n, 1, 1).expand(-1, -1, -1, d, 2))
+        self.fluxes = torch.gather(self.fluxes, 2, index.unsqueeze(-1).expand(-1, -1, -1, d))
+        size = torch.zeros(numH, numW, n, device=dev).scatter_add_(2, stratum, torch.ones(numH, numW, n, device=dev))
+        self.weights_intracount = 1.0 / size.gather(2, stratum)
+        self.resampled_index = index
 
     # ---- summaries (reference aggregate.py:595-639) -------------------------------------------
     @property

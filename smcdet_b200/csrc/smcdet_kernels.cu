@@ -232,6 +232,18 @@ __global__ void psf_kernel(const ModelK m, float norm, const float* __restrict__
     }
 }
 
+// PSF as a function of the radius (images.py:25-26, :137-145): the elementwise helper behind ImageModel.psf
+__global__ void psf_radial_kernel(const ModelK m, float norm, const float* __restrict__ r, float* __restrict__ out,
+                                  size_t n) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const float r2 = r[e] * r[e];
+        float v = ex2_fast(-m.k1 * r2);
+        if (m.kind == SMCDET_MODEL_M71_NORMAL)
+            v += m.b * ex2_fast(-m.k2 * r2) + m.p0 * ex2_fast(m.hb * lg2_fast(fmaf(m.cpl, r2, 1.0f)));
+        out[e] = norm * v;
+    }
+}
+
 __global__ void render_kernel(const ModelK m, const float* __restrict__ locs, const float* __restrict__ fluxes,
                               float* __restrict__ out, int T, int N, int D, int h, int w) {
     const size_t total = (size_t)T * h * w * N;
@@ -1539,6 +1551,17 @@ int smcdet_psf(const smcdet_model_params* model, const float* locs, float* psf, 
     const size_t total = (size_t)T * h * w * N * D;
     SMC_LAUNCH(psf_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, m, norm, locs, psf, T, N, D, h, w);
     return launch_status("psf_kernel");
+}
+
+int smcdet_psf_radial(const smcdet_model_params* model, int normalized, const float* r, float* out, long long n,
+                      void* stream) {
+    SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_psf_radial: bad model parameters");
+    SMC_REQUIRE(r && out && n > 0, SMCDET_E_INVALID, "smcdet_psf_radial: null pointer or non-positive size");
+    const ModelK m = make_model_k(*model);
+    // m.cn carries 1 / ((1 + b + p0) Z) for the M71 PSF: the un-normalised form drops the Z
+    const float norm = (normalized || model->model_kind != SMCDET_MODEL_M71_NORMAL) ? m.cn : m.cn * model->psf_norm;
+    SMC_LAUNCH(psf_radial_kernel, grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream, m, norm, r, out, (size_t)n);
+    return launch_status("psf_radial_kernel");
 }
 
 int smcdet_render(const smcdet_model_params* model, const float* locs, const float* fluxes, float* rate, int T,

@@ -56,6 +56,17 @@ class ImageModel(object):
                                    self.image_width, L.stream_for(lf)))
         return out.view(numH, numW, self.image_height, self.image_width, n, d)
 
+    def _psf_radial(self, r, normalized):
+        rf = L.f32(r)
+        out = torch.empty_like(rf)
+        p = self._params()
+        L.check(L.lib().smcdet_psf_radial(C.byref(p), int(normalized), L.ptr(rf), L.ptr(out), rf.numel(), L.stream_for(rf)))
+        return out
+
+    def _compute_normalized_psf(self, r):
+        """PSF value at radius r (reference images.py:25-26; M71: images.py:143-145)."""
+        return self._psf_radial(r, True)
+
     def _rate(self, locs, fluxes):
         numH, numW, n, d, lf, ff = self._flat(locs, fluxes)
         out = torch.empty(numH * numW, self.image_height, self.image_width, n, device=lf.device, dtype=torch.float32)
@@ -95,6 +106,10 @@ class M71ImageModel(ImageModel):
         core = torch.exp(-r2 / (2 * self.sigma1)) + self.b * torch.exp(-r2 / (2 * self.sigma2))
         wing = self.p0 * (1 + r2 / (self.beta * self.sigmap)) ** (-self.beta / 2)
         return (core + wing) / (1 + self.b + self.p0)
+
+    def _compute_unnormalized_psf(self, r):
+        """reference images.py:137-141, evaluated on the GPU"""
+        return self._psf_radial(r, False)
 
     def _normalizing_constant(self):
         """Z: sum of the un-normalised PSF over a (32 R)^2 pixel grid centred on one star

@@ -918,3 +918,83 @@ def test_count_stratified_tiles_into_the_tree_merge():
     assert (agg.dimH, agg.dimW) == (16, 16) and agg.counts.shape == (1, 1, 2000)
     assert torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts) and float(agg.temperature.min()) == 1.0
     assert len(agg.counts.unique()) > 1                 # catalogs of several sizes survive the merge
+
+
+def test_radial_psf_helpers_match_the_reference_formulas():
+    """ImageModel._compute_normalized_psf and M71ImageModel._compute_unnormalized_psf / _compute_normalized_psf
+    (images.py:25-26, :137-145) against the formulas in float64."""
+    import math
+
+    g = Golden("loglik_m71_t8_d10")
+    model, _, _ = build_objects(g.meta)
+    r = torch.linspace(0, 12, 1001, device=dev())
+    s1, s2, sp, beta, b, p0 = g.meta["model_params"]["psf_params"]
+    rr = r.double().cpu()
+    un = (torch.exp(-rr**2 / (2 * s1)) + b * torch.exp(-rr**2 / (2 * s2)) + p0 * (1 + rr**2 / (beta * sp)) ** (-beta / 2)) / (1 + b + p0)
+    got = model._compute_unnormalized_psf(r)
+    assert got.is_cuda and torch.allclose(got.cpu().double(), un, rtol=2e-6, atol=1e-9)
+    assert torch.allclose(model._compute_normalized_psf(r).cpu().double(), un / float(model.psf_normalizing_constant), rtol=2e-6, atol=1e-9)
+    g2 = Golden("loglik_gauss_t8_d8")
+    gm, _, _ = build_objects(g2.meta)
+    sd = g2.meta["model_params"]["psf_stdev"]
+    want = torch.exp(-rr**2 / (2 * sd * sd)) / (sd * math.sqrt(2 * math.pi))
+    assert torch.allclose(gm._compute_normalized_psf(r).cpu().double(), want, rtol=2e-6, atol=1e-12)
+
+
+def test_aggregate_method_surface_against_the_reference():
+    """The reference's Aggregate methods by name -- drop_sources_from_overlap, join, unjoin, log_target,
+    temper / update_weights, mutate, sort_by_count, resample_intracount -- on the aggregate_m71 fixture (the
+    reference's own outputs) and their invariants."""
+    from smcdet_b200.aggregate import Aggregate
+    from smcdet_b200.kernel import SingleComponentMH
+
+    g = Golden("aggregate_m71")
+    meta = g.meta
+    model, prior, _ = build_objects(meta)
+    N = meta["N"]
+    mh = SingleComponentMH(meta["iters"], 0.1, 2.5, meta["fluxes_min"], meta["fluxes_max"])
+    agg = Aggregate(prior, model, mh, cu(g["leaf_data"]), cu(g["L0_in_counts"]), cu(g["L0_in_locs"]), cu(g["L0_in_fluxes"]),
+                    torch.full((2, 2, N), 1.0 / N, device=dev()), torch.zeros(2, 2), meta["flux_threshold"], "multinomial", 0.5)
+    for level in range(2):
+        L_ = meta[f"L{level}"]
+        axis = L_["axis"]
+        counts, locs, fluxes = cu(g[f"L{level}_in_counts"]), cu(g[f"L{level}_in_locs"]), cu(g[f"L{level}_in_fluxes"])
+        dc, dl, df = agg.drop_sources_from_overlap(axis, counts.clone(), locs.clone(), fluxes.clone())
+        assert np.array_equal(dc.cpu().numpy(), g[f"L{level}_drop_counts"])
+        assert np.array_equal(dl.cpu().numpy(), g[f"L{level}_drop_locs"]) and np.array_equal(df.cpu().numpy(), g[f"L{level}_drop_fluxes"])
+        data = agg.data if level == 0 else data
+        data, cs, ls, fs = agg.join(axis, data, dc, dl, df)
+        assert (agg.dimH, agg.dimW, agg.numH, agg.numW) == (L_["dimH"], L_["dimW"], L_["numH"], L_["numW"])
+        assert agg.Prior.max_objects == L_["D"] and np.array_equal(agg.Prior.loc_prior.high.cpu().numpy(), g[f"L{level}_loc_high"])
+        assert np.array_equal(data.cpu().numpy(), g[f"L{level}_data"]) and np.array_equal(cs.cpu().numpy(), g[f"L{level}_counts"])
+        assert np.array_equal(ls.cpu().numpy(), g[f"L{level}_locs"]) and np.array_equal(fs.cpu().numpy(), g[f"L{level}_fluxes"])
+        cd, cc, cl, cf = agg.unjoin(axis, data, ls, fs)
+        assert np.array_equal(cd.cpu().numpy(), g[f"L{level}_child_data"]) and np.array_equal(cc.cpu().numpy(), g[f"L{level}_child_counts"])
+        assert np.array_equal(cl.cpu().numpy(), g[f"L{level}_child_locs"]) and np.array_equal(cf.cpu().numpy(), g[f"L{level}_child_fluxes"])
+        tau = cu(g[f"L{level}_tau"])
+        lt = agg.log_target(axis, None, cd, cl, cf, data, cs, ls, fs, tau)
+        assert rel_err(lt.cpu().numpy(), g[f"L{level}_log_target"]) < RTOL
+    # one merge iteration by hand with the reference's method names
+    agg.data, agg.counts, agg.locs, agg.fluxes = data, cs, ls, fs
+    agg._logz = torch.zeros(1, 1, device=dev())
+    agg.temperature = agg.temperature_prev = torch.zeros(1, 1, device=dev())
+    agg._bridge(1, 0)
+    assert np.max(np.abs(agg.loglik_diff.cpu().numpy() - g["L1_loglik_diff"])) < 1e-4 * np.max(np.abs(g["L1_parent_loglik"]))
+    agg.temper()
+    agg.update_weights()
+    assert 0 < float(agg.temperature) <= 1 and abs(float(agg.weights.sum()) - 1) < 1e-4
+    ess = float(1 / (agg.weights**2).sum())
+    assert float(agg.temperature) == 1.0 or abs(ess / (0.5 * N) - 1) < 1e-3
+    obj = agg.tempering_objective(agg.loglik_diff[0, 0], float(agg.temperature))
+    assert float(agg.temperature) == 1.0 or abs(float(obj)) < 0.05
+    agg.sort_by_count()
+    assert bool((agg.counts[..., 1:] >= agg.counts[..., :-1]).all())
+    assert sum(agg.num_catalogs_per_count[0][0]) == N and torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts)
+    before = agg.fluxes.clone()
+    torch.manual_seed(0)
+    agg.resample_intracount()
+    assert torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts)          # nobody left its stratum
+    assert abs(float(agg.weights_intracount.sum()) - len(agg.num_catalogs_per_count[0][0])) < 1e-4
+    assert not torch.equal(before, agg.fluxes)
+    agg.mutate(1)
+    assert agg.mutation_acc_rates.shape == (1, 1) and torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts)

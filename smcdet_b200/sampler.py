@@ -18,6 +18,9 @@ from . import _abi as A
 from . import _lib as L
 
 
+_FLAG_RING = None
+
+
 class SMCsampler(object):
     def __init__(self, image, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
                  resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, tile_ids=None,
@@ -315,24 +318,22 @@ class SMCsampler(object):
             self._temper_and_update()
             self._record()
 
-        while torch.any(self.temperature < 1) and self.iter <= self.max_smc_iters:
-            if stop_after is not None and self.iter >= stop_after:
-                return
-            self.iter += 1
-            if self.iter % self.print_every == 0:
-                self._print(
-                    f"iteration {self.iter}: "
-                    f"temperature in [{round(self.temperature.min().item(), 2)}, "
-                    f"{round(self.temperature.max().item(), 2)}], "
-                    f"acceptance rate in [{round(self.mutation_acc_rates.min().item(), 2)}, "
-                    f"{round(self.mutation_acc_rates.max().item(), 2)}]"
-                )
-            if self.freeze_finished:
-                self._active = self.temperature < 1
-            self._timed("resample", self.resample)
-            self._timed("mutate", self.mutate)
-            self._timed("temper+update_weights", self._temper_and_update)
-            self._record()
+        if self.freeze_finished and stop_after is None and not self.verbose:
+            self._iterate_ahead()
+        else:
+            while torch.any(self.temperature < 1) and self.iter <= self.max_smc_iters:
+                if stop_after is not None and self.iter >= stop_after:
+                    return
+                self.iter += 1
+                if self.verbose and self.iter % self.print_every == 0:
+                    self._print(
+                        f"iteration {self.iter}: "
+                        f"temperature in [{round(self.temperature.min().item(), 2)}, "
+                        f"{round(self.temperature.max().item(), 2)}], "
+                        f"acceptance rate in [{round(self.mutation_acc_rates.min().item(), 2)}, "
+                        f"{round(self.mutation_acc_rates.max().item(), 2)}]"
+                    )
+                self._one_iteration()
 
         self._active = None
         self._spare = self._active_prev = None
@@ -344,6 +345,54 @@ class SMCsampler(object):
             self.MutationKernel.check_status()
         self.has_run = True
         self._print("done!\n")
+
+    def _one_iteration(self):
+        if self.freeze_finished:
+            self._active = self.temperature < 1
+        self._timed("resample", self.resample)
+        self._timed("mutate", self.mutate)
+        self._timed("temper+update_weights", self._temper_and_update)
+        self._record()
+
+    def _iterate_ahead(self):
+        """The SMC loop with the host one iteration ahead of the device.  The reference's loop test
+        ``torch.any(self.temperature < 1)`` (sampler.py:230) waits for the iteration just launched, which leaves the
+        GPU idle while the host prepares the next one.  With frozen tiles an iteration launched after every tile
+        has finished changes nothing (all kernels skip inactive tiles), so iteration k + 1 is launched on the
+        strength of the flag of iteration k - 1, and is rolled back from the counters if it turns out to have
+        been superfluous.  Results are identical to the plain loop."""
+        dev = self._device
+        global _FLAG_RING
+        if _FLAG_RING is None:  # pinned one-word landing pads for the loop flag, allocated once per process
+            _FLAG_RING = [torch.empty(1, dtype=torch.int32, pin_memory=True) for _ in range(3)]
+        ring = _FLAG_RING
+        slot = [0]
+
+        def post_flag():
+            host = ring[slot[0] % len(ring)]
+            slot[0] += 1
+            host.copy_(torch.any(self.temperature < 1).to(torch.int32), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            return host, ev
+
+        def read(flag):
+            flag[1].synchronize()
+            return bool(flag[0].item())
+
+        prev, cur = None, post_flag()
+        while True:
+            if not read(cur if prev is None else prev):
+                if prev is not None:  # the iteration in flight was launched after every tile had finished
+                    self.iter -= 1
+                    if self.history:
+                        self.history.pop()
+                break
+            if self.iter > self.max_smc_iters:
+                break
+            self.iter += 1
+            self._one_iteration()
+            prev, cur = cur, post_flag()
 
     def _timed(self, stage, fn):
         """Run one stage; with ``stage_timing`` set, bracket it with CUDA events on the current stream (tracing hook:

@@ -532,23 +532,52 @@ __global__ void __launch_bounds__(kTB) resample_kernel(int method, const float* 
     }
 }
 
+// Latency-bound by nature (index -> load -> store per element), so the kernel keeps as many bytes in flight per
+// thread as it can: 8-byte elements (VEC = 2: a location pair, two fluxes; needs an even D) and two independent
+// elements per loop trip.  IdxT = uint32_t whenever the element count fits (32-bit divisions).
+template <typename IdxT, int VEC>
+__device__ __forceinline__ void gather_one(IdxT e, IdxT row, const int64_t* __restrict__ index,
+                                           const float* __restrict__ counts_in, const float* __restrict__ locs_in,
+                                           const float* __restrict__ fluxes_in, float* __restrict__ counts_out,
+                                           float* __restrict__ locs_out, float* __restrict__ fluxes_out,
+                                           const int32_t* __restrict__ tile_mask, int N, int D) {
+    const IdxT pn = e / row;
+    const int c = (int)(e - pn * row);
+    const IdxT t = pn / (IdxT)N;
+    if (tile_mask != nullptr && tile_mask[t] == 0) return;
+    const size_t src = (size_t)t * N + (size_t)index[pn];
+    if constexpr (VEC == 2) {
+        // row = D location pairs, D/2 flux pairs, the count
+        if (c < D)
+            reinterpret_cast<float2*>(locs_out)[(size_t)pn * D + c] = reinterpret_cast<const float2*>(locs_in)[src * D + c];
+        else if (c < D + D / 2)
+            reinterpret_cast<float2*>(fluxes_out)[(size_t)pn * (D / 2) + (c - D)] =
+                reinterpret_cast<const float2*>(fluxes_in)[src * (D / 2) + (c - D)];
+        else counts_out[pn] = counts_in[src];
+    } else {
+        if (c < 2 * D) locs_out[(size_t)pn * 2 * D + c] = locs_in[src * 2 * D + c];
+        else if (c < 3 * D) fluxes_out[(size_t)pn * D + (c - 2 * D)] = fluxes_in[src * D + (c - 2 * D)];
+        else counts_out[pn] = counts_in[src];
+    }
+}
+
+template <typename IdxT, int VEC>
 __global__ void gather_kernel(const int64_t* __restrict__ index, const float* __restrict__ counts_in,
                               const float* __restrict__ locs_in, const float* __restrict__ fluxes_in,
                               float* __restrict__ counts_out, float* __restrict__ locs_out,
                               float* __restrict__ fluxes_out, const int32_t* __restrict__ tile_mask, int T, int N,
                               int D) {
-    const int row = 3 * D + 1;
-    const size_t total = (size_t)T * N * row;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const size_t pn = e / row;
-        const int c = (int)(e - pn * row);
-        const size_t t = pn / N;
-        if (tile_mask != nullptr && tile_mask[t] == 0) continue;
-        const size_t src = t * N + (size_t)index[pn];
-        if (c < 2 * D) locs_out[pn * 2 * D + c] = locs_in[src * 2 * D + c];
-        else if (c < 3 * D) fluxes_out[pn * D + (c - 2 * D)] = fluxes_in[src * D + (c - 2 * D)];
-        else counts_out[pn] = counts_in[src];
+    const IdxT row = (IdxT)(VEC == 2 ? D + D / 2 + 1 : 3 * D + 1);
+    const IdxT total = (IdxT)T * (IdxT)N * row;
+    const IdxT stride = (IdxT)gridDim.x * (IdxT)blockDim.x;
+    IdxT e = (IdxT)blockIdx.x * (IdxT)blockDim.x + threadIdx.x;
+    for (; e < total && total - e > stride; e += 2 * stride) {
+        gather_one<IdxT, VEC>(e, row, index, counts_in, locs_in, fluxes_in, counts_out, locs_out, fluxes_out, tile_mask, N, D);
+        gather_one<IdxT, VEC>(e + stride, row, index, counts_in, locs_in, fluxes_in, counts_out, locs_out, fluxes_out,
+                              tile_mask, N, D);
     }
+    if (e < total)
+        gather_one<IdxT, VEC>(e, row, index, counts_in, locs_in, fluxes_in, counts_out, locs_out, fluxes_out, tile_mask, N, D);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1629,9 +1658,17 @@ int smcdet_gather(const int64_t* index, const float* counts_in, const float* loc
     SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_gather: non-positive size");
     SMC_REQUIRE(counts_in != counts_out && locs_in != locs_out && fluxes_in != fluxes_out, SMCDET_E_INVALID,
                 "smcdet_gather: in-place gather is not supported");
-    const size_t total = (size_t)T * N * (3 * D + 1);
-    SMC_LAUNCH(gather_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, index, counts_in, locs_in, fluxes_in,
-                                                                          counts_out, locs_out, fluxes_out, tile_mask, T, N, D);
+    // 8-byte elements need an even D and 8-byte aligned arrays (every record then is)
+    const bool vec = (D % 2 == 0) && (((uintptr_t)locs_in | (uintptr_t)locs_out | (uintptr_t)fluxes_in | (uintptr_t)fluxes_out) % 8 == 0);
+    const size_t total = (size_t)T * N * (vec ? D + D / 2 + 1 : 3 * D + 1);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SMC_GATHER(IDX, VEC) \
+    SMC_LAUNCH((gather_kernel<IDX, VEC>), grid_for(total, 256), 256, 0, st, index, counts_in, locs_in, fluxes_in, counts_out, \
+               locs_out, fluxes_out, tile_mask, T, N, D)
+    // 32-bit element arithmetic with headroom for two grid-stride increments
+    if (total < (size_t)3000000000u) { if (vec) SMC_GATHER(uint32_t, 2); else SMC_GATHER(uint32_t, 1); }
+    else { if (vec) SMC_GATHER(size_t, 2); else SMC_GATHER(size_t, 1); }
+#undef SMC_GATHER
     return launch_status("gather_kernel");
 }
 

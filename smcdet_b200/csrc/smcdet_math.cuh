@@ -22,6 +22,7 @@
 #endif
 
 #if !defined(__CUDACC__)
+struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 #endif

@@ -998,3 +998,31 @@ def test_aggregate_method_surface_against_the_reference():
     assert not torch.equal(before, agg.fluxes)
     agg.mutate(1)
     assert agg.mutation_acc_rates.shape == (1, 1) and torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts)
+
+
+@pytest.mark.parametrize("max_iters", [200, 2])
+def test_host_ahead_loop_equals_the_plain_loop(max_iters, capsys):
+    """With frozen tiles run() keeps the host one iteration ahead of the device (SMCsampler._iterate_ahead); the plain
+    loop (taken when progress is printed) must give the same iteration count and bit-identical state, also when
+    max_smc_iters cuts the run short."""
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("smc_stages_m71")
+    meta = g.meta
+
+    def run(verbose):
+        torch.manual_seed(17)
+        model, prior, mh = build_objects(meta, iters=6)
+        s = SMCsampler(cu(g["image"]), meta["tile"], prior, model, mh, 768, 0.5, "multinomial", meta["flux_threshold"],
+                       max_iters, print_every=10**6, freeze_finished=True, verbose=verbose)
+        s.record_history = True
+        s.run()
+        return s
+
+    ahead, plain = run(False), run(True)
+    capsys.readouterr()
+    assert ahead.iter == plain.iter and len(ahead.history) == len(plain.history) == plain.iter + 1
+    assert (max_iters == 2) == bool(float(plain.temperature.min()) < 1.0)
+    for k in ("locs", "fluxes", "counts", "weights", "temperature", "log_normalizing_constant", "loglik", "ess",
+              "mutation_acc_rates", "pruned_counts", "pruned_fluxes"):
+        assert torch.equal(getattr(ahead, k), getattr(plain, k)), k

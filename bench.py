@@ -286,10 +286,19 @@ def run_own(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its version banner on stdout, which must carry the JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG=VERSION/WARN/INFO);
+        # stdout must carry the JSON line only, so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
 
     T, N, D, iters = a.tiles_per_gpu, a.particles, a.stars, a.mh_iters

@@ -18,9 +18,6 @@ from . import _abi as A
 from . import _lib as L
 
 
-_FLAG_RING = None
-
-
 class SMCsampler(object):
     def __init__(self, image, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
                  resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, tile_ids=None,
@@ -362,10 +359,8 @@ class SMCsampler(object):
         strength of the flag of iteration k - 1, and is rolled back from the counters if it turns out to have
         been superfluous.  Results are identical to the plain loop."""
         dev = self._device
-        global _FLAG_RING
-        if _FLAG_RING is None:  # pinned one-word landing pads for the loop flag, allocated once per process
-            _FLAG_RING = [torch.empty(1, dtype=torch.int32, pin_memory=True) for _ in range(3)]
-        ring = _FLAG_RING
+        # pinned one-word landing pads for the loop flag (torch's caching host allocator makes these cheap)
+        ring = [torch.empty(1, dtype=torch.int32, pin_memory=True) for _ in range(3)]
         slot = [0]
 
         def post_flag():

@@ -391,8 +391,8 @@ def run_own(a):
     mufu_per_particle = 4 * star_pixels + 2 * pixel_terms
     fp32_per_particle = 12 * star_pixels + 7 * pixel_terms
     # what the kernel issues: separable Gaussians (2*(8+8) ex2 per star) + 2 MUFU per star-pixel for the wing +
-    # 1 for the star weight; pixel pairs share one rcp and one lg2 (1 per pixel); ~45 in the proposal step
-    exec_mufu_per_particle = (1 * D + 2 * iters) * (2 * 16 + 2 * P + 1) + pixel_terms + 45 * iters
+    # 1 for the star weight; four pixels share one rcp and one lg2 (0.5 per pixel); ~45 in the proposal step
+    exec_mufu_per_particle = (1 * D + 2 * iters) * (2 * 16 + 2 * P + 1) + pixel_terms // 2 + 45 * iters
     live_particles = live_total * N
     peaks = {}
     try:
@@ -446,7 +446,7 @@ def run_own(a):
                        "evals_per_s": ll_rate, "launch_ms": ll_ms,
                        "achieved": ll_rate * (4 * D * P + 2 * P) / 1e12, "peak": sfu_peak, "unit": "TOP/s (MUFU)",
                        "frac": ll_rate * (4 * D * P + 2 * P) / 1e12 / sfu_peak,
-                       "executed_frac": ll_rate * (D * (2 * 16 + 2 * P + 1) + P) / 1e12 / sfu_peak,
+                       "executed_frac": ll_rate * (D * (2 * 16 + 2 * P + 1) + P // 2) / 1e12 / sfu_peak,
                        "hbm_gbs": ll_rate * (12 * D + 8) / 1e9}
     del counts0, locs0, fluxes0
 

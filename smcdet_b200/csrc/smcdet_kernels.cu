@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kBT) loglik_generic_kernel(const ModelK m, con
         rate += m.bg;
         const float x = tile[p];
         if (m.kind == SMCDET_MODEL_M71_NORMAL) {
-            const float var = fmaf(m.nm, rate, m.na), dd = x - rate;
+            const float var = fmaf(m.nms * 4096.0f, rate, m.nas * 4096.0f), dd = x - rate;
             acc += fmaf(-0.5f * dd * dd, rcp_fast(var), fmaf(-0.5f * kLn2, lg2_fast(var), -kLogSqrt2Pi));
         } else {
             const float lg = lg2_fast(rate) * kLn2;

@@ -32,6 +32,7 @@ namespace smc {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kLogSqrt2Pi = 0.9189385332046727f;
+constexpr float kQuadScale = 1.0f / 4096.0f;  // 2^-12: scale of the noise variance carried in ModelK::nas / nms
 constexpr float kSqrt2 = 1.4142135623730951f;
 constexpr float kInvSqrt2 = 0.7071067811865476f;
 
@@ -129,7 +130,7 @@ struct ModelK {
     float b, p0;
     float cn;       // PSF normalisation: M71 1/((1+b+p0) Z); Gaussian 1/(stdev sqrt(2pi))
     float c0;       // flux -> weight: cn * adu_per_nmgy (M71), cn (Gaussian)
-    float bg, na, nm, nswitch;
+    float bg, nas, nms, nswitch;  // nas / nms: noise_additive / noise_multiplicative times kQuadScale (M71 model)
     float is1, is2, isp;  // 1/sigma1, 1/sigma2, 1/sigmap (M71); is1 = 1/stdev^2 (Gaussian): PSF gradients (MALA)
     float lp0;            // lg2(p0)
 };
@@ -149,8 +150,8 @@ inline ModelK make_model_k(const smcdet_model_params& p) {
         m.p0 = p.p0;
         m.cn = (float)(1.0 / ((1.0 + (double)p.b + (double)p.p0) * (double)p.psf_norm));
         m.c0 = (float)((double)p.adu_per_nmgy / ((1.0 + (double)p.b + (double)p.p0) * (double)p.psf_norm));
-        m.na = p.noise_additive;
-        m.nm = p.noise_multiplicative;
+        m.nas = p.noise_additive * kQuadScale;   // exact: a power of two
+        m.nms = p.noise_multiplicative * kQuadScale;
         m.is1 = (float)(1.0 / (double)p.sigma1); m.is2 = (float)(1.0 / (double)p.sigma2);
         m.isp = (float)(1.0 / (double)p.sigmap);
         m.lp0 = (float)log2((double)p.p0);
@@ -160,7 +161,7 @@ inline ModelK make_model_k(const smcdet_model_params& p) {
         m.k2 = 0.f; m.cpl = 0.f; m.hb = 0.f; m.b = 0.f; m.p0 = 0.f;
         m.cn = (float)(1.0 / (s * 2.5066282746310002));
         m.c0 = m.cn;
-        m.na = 0.f; m.nm = 1.f;
+        m.nas = 0.f; m.nms = kQuadScale;
         m.is1 = (float)(1.0 / (s * s)); m.is2 = 0.f; m.isp = 0.f; m.lp0 = 0.f;
     }
     return m;
@@ -259,7 +260,7 @@ SMC_HD float tree_sum(float (&v)[N]) {
 
 // Per-pixel log density summed over the lane's RPT rows of W pixels; returns the two partial sums (Q, S) that
 // finish_loglik combines after the reduction over the lanes of the particle:
-//   M71 (images.py:169-175): Q = sum (x-r)^2 / v, S = sum lg2 v, v = na + nm r (pixel pairs share a rcp and a lg2)
+//   M71 (images.py:169-175): Q = sum (x-r)^2 / v, S = sum lg2 v, v = (na + nm r) * 2^-12 (four pixels share a rcp and a lg2)
 //   Gaussian-PSF model (images.py:91-102): Q = sum of Poisson / Normal terms, S = 0
 // x / lgam: the lane's observed pixels and lgamma(x+1) (16-byte aligned); rate4(g) = expected counts of pixels 4g..4g+3.
 template <int MODEL, int RPT, int W, class Rate4>
@@ -274,20 +275,18 @@ SMC_HD void pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam,
             for (int g = r * (W / 4); g < (r + 1) * (W / 4); ++g) {
                 const float4 rt = rate4(g);
                 const float4 xv = x4[g];
-                {
-                    const float va = fmaf(m.nm, rt.x, m.na), vb = fmaf(m.nm, rt.y, m.na);
-                    const float da = xv.x - rt.x, db = xv.y - rt.y;
-                    const float den = va * vb;
-                    q = fmaf(fmaf(da * da, vb, (db * db) * va), rcp_fast(den), q);
-                    s += lg2_fast(den);
-                }
-                {
-                    const float va = fmaf(m.nm, rt.z, m.na), vb = fmaf(m.nm, rt.w, m.na);
-                    const float da = xv.z - rt.z, db = xv.w - rt.w;
-                    const float den = va * vb;
-                    q = fmaf(fmaf(da * da, vb, (db * db) * va), rcp_fast(den), q);
-                    s += lg2_fast(den);
-                }
+                // four pixels share one rcp and one lg2:
+                //   sum d_i^2 / v_i = (n_ab v_cd + n_cd v_ab) / (v_ab v_cd),  sum lg2 v_i = lg2(v_ab v_cd)
+                // on variances scaled by kQuadScale = 2^-12 (exact), which keeps the products of four far from the
+                // float range for any pixel value below ~3e9; finish_loglik undoes the scale
+                const float va = fmaf(m.nms, rt.x, m.nas), vb = fmaf(m.nms, rt.y, m.nas);
+                const float vc = fmaf(m.nms, rt.z, m.nas), vd = fmaf(m.nms, rt.w, m.nas);
+                const float da = xv.x - rt.x, db = xv.y - rt.y, dc = xv.z - rt.z, dd = xv.w - rt.w;
+                const float vab = va * vb, vcd = vc * vd;
+                const float nab = fmaf(da * da, vb, (db * db) * va), ncd = fmaf(dc * dc, vd, (dd * dd) * vc);
+                const float den = vab * vcd;
+                q = fmaf(fmaf(nab, vcd, ncd * vab), rcp_fast(den), q);
+                s += lg2_fast(den);
             }
             qrow[r] = q; srow[r] = s;
         }
@@ -327,8 +326,8 @@ SMC_HD void pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam,
 // log-likelihood of the tile from the totals of pixel_loglik_sum over all NPIX_TOTAL pixels
 template <int MODEL>
 SMC_HD float finish_loglik(float Q, float S, int npix_total) {
-    if (MODEL == SMCDET_MODEL_M71_NORMAL)
-        return fmaf(-0.5f, Q, fmaf(-0.5f * kLn2, S, -(float)npix_total * kLogSqrt2Pi));
+    if (MODEL == SMCDET_MODEL_M71_NORMAL)  // Q and S arrive on variances scaled by kQuadScale = 2^-12
+        return fmaf(-0.5f * kQuadScale, Q, fmaf(-0.5f * kLn2, S, -(float)npix_total * (kLogSqrt2Pi + 6.0f * kLn2)));
     return Q;
 }
 
@@ -346,8 +345,9 @@ SMC_HD float finish_loglik(float Q, float S, int npix_total) {
 template <int MODEL>
 SMC_HD float pixel_dlogpdf(const ModelK& m, float x, float r) {
     if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-        const float v = fmaf(m.nm, r, m.na), d = x - r, iv = rcp_fast(v);
-        return fmaf(0.5f * m.nm * iv, fmaf(d, d, -v) * iv, d * iv);
+        const float nm = m.nms * 4096.0f;
+        const float v = fmaf(nm, r, m.nas * 4096.0f), d = x - r, iv = rcp_fast(v);
+        return fmaf(0.5f * nm * iv, fmaf(d, d, -v) * iv, d * iv);
     }
     const float ir = rcp_fast(r);
     if (r > m.nswitch) {

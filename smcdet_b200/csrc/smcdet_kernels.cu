@@ -84,6 +84,12 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 
+// pixels 4g..4g+3 of a lane: resident rate + pending change (pairs acc[2g], acc[2g+1]), as two packed additions
+__device__ __forceinline__ float4 rate_plus(const float4 r, const float2 a, const float2 b) {
+    const float2 lo = add2(make_float2(r.x, r.y), a), hi = add2(make_float2(r.z, r.w), b);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // stage the tile and the block's particle catalogs (AoS in global memory, coalesced reads) into
 // shared memory as s_star[(d*3 + c) * PB + particle], c = 0 row, 1 col, 2 flux
 template <int MODEL, int HW, int PB>
@@ -130,9 +136,9 @@ __device__ __forceinline__ void unstage_block(float* __restrict__ locs, float* _
 // full render of the lane's pixels from the staged catalog (without the background)
 template <int MODEL, int RPT, int W, int PB>
 __device__ __forceinline__ void render_rows(const ModelK& m, const float* s_star, int pi, int D, int row0,
-                                            float (&acc)[RPT * W]) {
+                                            float2 (&acc)[RPT * W / 2]) {
 #pragma unroll
-    for (int p = 0; p < RPT * W; ++p) acc[p] = 0.0f;
+    for (int p = 0; p < RPT * W / 2; ++p) acc[p] = make_float2(0.0f, 0.0f);
     for (int d = 0; d < D; ++d) {
         const float f = s_star[(d * 3 + 2) * PB + pi];
         if (f != 0.0f) {  // empty slots contribute exactly zero (prior.py:61-62 zero-fills them)
@@ -166,11 +172,11 @@ __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float
     __syncthreads();
 
     const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
-    float acc[PPT];
+    float2 acc[PPT / 2];
     render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
     float Q, S;
     pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
-        return make_float4(acc[4 * g] + m.bg, acc[4 * g + 1] + m.bg, acc[4 * g + 2] + m.bg, acc[4 * g + 3] + m.bg);
+        return rate_plus(make_float4(m.bg, m.bg, m.bg, m.bg), acc[2 * g], acc[2 * g + 1]);
     }, Q, S);
     const float ll = finish_loglik<MODEL>(group_sum<TPP>(Q), group_sum<TPP>(S), HW);
     if (sub == 0 && pi < n_here) out[pbase + pi] = ll;
@@ -755,7 +761,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     Philox4 rc = {{0u, 0u, 0u, 0u}};
     int last_acc = 0;
     float ll = 0.0f, cached = 0.0f;
-    float acc[PPT];
+    float2 acc[PPT / 2];
 
     // One loop, one copy of the render / pixel code (the unrolled body is large, so it must not be
     // replicated: instruction-cache misses were 12% of the stalls when it was):
@@ -817,7 +823,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
 
         // ---- expected counts: all D stars (full render) or -old star +new star (MH sweep)
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) acc[p] = 0.0f;
+        for (int p = 0; p < PPT / 2; ++p) acc[p] = make_float2(0.0f, 0.0f);
         if constexpr (MALA) {
             if (!full) {  // (a frozen slot runs through the same shuffles as its warp's other particles)
                 // gradient of the log target wrt star k at the current state (kernel.py:159-167), removing the star
@@ -863,15 +869,13 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         if (full) {
 #pragma unroll
             for (int g = 0; g < PPT / 4; ++g) {
-                my_rate[g * kBT] = make_float4(acc[4 * g] + m.bg, acc[4 * g + 1] + m.bg, acc[4 * g + 2] + m.bg,
-                                               acc[4 * g + 3] + m.bg);
-                acc[4 * g] = acc[4 * g + 1] = acc[4 * g + 2] = acc[4 * g + 3] = 0.0f;
+                my_rate[g * kBT] = rate_plus(make_float4(m.bg, m.bg, m.bg, m.bg), acc[2 * g], acc[2 * g + 1]);
+                acc[2 * g] = acc[2 * g + 1] = make_float2(0.0f, 0.0f);
             }
         }
         float pq, ps;
         pixel_loglik_sum<MODEL, RPT, W>(m, xs, lg, [&](int g) {
-            const float4 r = my_rate[g * kBT];
-            return make_float4(r.x + acc[4 * g], r.y + acc[4 * g + 1], r.z + acc[4 * g + 2], r.w + acc[4 * g + 3]);
+            return rate_plus(my_rate[g * kBT], acc[2 * g], acc[2 * g + 1]);
         }, pq, ps);
         const float llp = finish_loglik<MODEL>(group_sum<TPP>(pq), group_sum<TPP>(ps), HW);
 
@@ -902,10 +906,10 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                     const float4 rt = my_rate[(r * (W / 4) + g) * kBT];
                     const float4 xv = reinterpret_cast<const float4*>(xs)[r * (W / 4) + g];
                     const int p = r * W + 4 * g;
-                    wr[4 * g] = pixel_dlogpdf<MODEL>(m, xv.x, rt.x + acc[p]);
-                    wr[4 * g + 1] = pixel_dlogpdf<MODEL>(m, xv.y, rt.y + acc[p + 1]);
-                    wr[4 * g + 2] = pixel_dlogpdf<MODEL>(m, xv.z, rt.z + acc[p + 2]);
-                    wr[4 * g + 3] = pixel_dlogpdf<MODEL>(m, xv.w, rt.w + acc[p + 3]);
+                    wr[4 * g] = pixel_dlogpdf<MODEL>(m, xv.x, rt.x + acc[p / 2].x);
+                    wr[4 * g + 1] = pixel_dlogpdf<MODEL>(m, xv.y, rt.y + acc[p / 2].y);
+                    wr[4 * g + 2] = pixel_dlogpdf<MODEL>(m, xv.z, rt.z + acc[p / 2 + 1].x);
+                    wr[4 * g + 3] = pixel_dlogpdf<MODEL>(m, xv.w, rt.w + acc[p / 2 + 1].y);
                 }
             }, acc, sP, s0, s1);
             sP = group_sum<TPP>(sP); s0 = group_sum<TPP>(s0); s1 = group_sum<TPP>(s1);
@@ -926,11 +930,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         __syncwarp();  // every lane of the particle has read the old star
         if (accept) {
 #pragma unroll
-            for (int g = 0; g < PPT / 4; ++g) {
-                float4 r = my_rate[g * kBT];
-                r.x += acc[4 * g]; r.y += acc[4 * g + 1]; r.z += acc[4 * g + 2]; r.w += acc[4 * g + 3];
-                my_rate[g * kBT] = r;
-            }
+            for (int g = 0; g < PPT / 4; ++g) my_rate[g * kBT] = rate_plus(my_rate[g * kBT], acc[2 * g], acc[2 * g + 1]);
             ll = llp;
             prior_fin = fin_p;
             prior_bad = bad_p;
@@ -1201,15 +1201,16 @@ struct AggOut {
 // the same in the child's frame.  A sweep renders the old and the new star once each (star_accumulate) and
 // updates both images' lane pixels incrementally, like mh_kernel; it = -1 is the full render of the entry state.
 template <int RPT, int W, int H, int AXIS>
-__device__ __forceinline__ void agg_split_add(const float (&tmp)[RPT * W], bool second, int row0, float (&accP)[RPT * W],
-                                              float (&accC)[RPT * W]) {
+__device__ __forceinline__ void agg_split_add(const float2 (&tmp)[RPT * W / 2], bool second, int row0,
+                                              float2 (&accP)[RPT * W / 2], float2 (&accC)[RPT * W / 2]) {
 #pragma unroll
     for (int r = 0; r < RPT; ++r)
 #pragma unroll
-        for (int c = 0; c < W; ++c) {
-            const bool pix_second = AXIS == 0 ? (row0 + r >= H / 2) : (c >= W / 2);
-            accP[r * W + c] += tmp[r * W + c];
-            accC[r * W + c] += (pix_second == second) ? tmp[r * W + c] : 0.0f;
+        for (int c = 0; c < W / 2; ++c) {  // a pair of columns never straddles the split (W / 2 is even)
+            const bool pix_second = AXIS == 0 ? (row0 + r >= H / 2) : (2 * c >= W / 2);
+            const float2 v = tmp[r * (W / 2) + c];
+            accP[r * (W / 2) + c] = add2(accP[r * (W / 2) + c], v);
+            accC[r * (W / 2) + c] = add2(accC[r * (W / 2) + c], (pix_second == second) ? v : make_float2(0.0f, 0.0f));
         }
 }
 
@@ -1301,9 +1302,9 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
             }
         }
         // ---- changes of both images on the lane's pixels: all D stars (entry) or -old star +new star (sweep)
-        float accP[PPT], accC[PPT];
+        float2 accP[PPT / 2], accC[PPT / 2];
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) { accP[p] = 0.0f; accC[p] = 0.0f; }
+        for (int p = 0; p < PPT / 2; ++p) { accP[p] = make_float2(0.0f, 0.0f); accC[p] = make_float2(0.0f, 0.0f); }
         const int ns = full ? D : (live ? 2 : 0);
 #pragma unroll 1
         for (int s = 0; s < ns; ++s) {
@@ -1316,9 +1317,9 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
                 s0 = pl0; s1 = pl1; sw = m.c0 * pf;
             }
             if (sw == 0.0f) continue;
-            float tmp[PPT];
+            float2 tmp[PPT / 2];
 #pragma unroll
-            for (int p = 0; p < PPT; ++p) tmp[p] = 0.0f;
+            for (int p = 0; p < PPT / 2; ++p) tmp[p] = make_float2(0.0f, 0.0f);
             star_accumulate<MODEL, RPT, W>(m, s0, s1, sw, row0, tmp);
             // aggregate.py:279-281: a star belongs to the first child iff loc_axis <= half
             agg_split_add<RPT, W, H, AXIS>(tmp, (AXIS == 0 ? s0 : s1) > o.half, row0, accP, accC);
@@ -1326,21 +1327,19 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
         if (full) {
 #pragma unroll
             for (int g = 0; g < PPT / 4; ++g) {
-                rateP[g * kBT] = make_float4(accP[4 * g] + m.bg, accP[4 * g + 1] + m.bg, accP[4 * g + 2] + m.bg, accP[4 * g + 3] + m.bg);
-                rateC[g * kBT] = make_float4(accC[4 * g] + m.bg, accC[4 * g + 1] + m.bg, accC[4 * g + 2] + m.bg, accC[4 * g + 3] + m.bg);
-                accP[4 * g] = accP[4 * g + 1] = accP[4 * g + 2] = accP[4 * g + 3] = 0.0f;
-                accC[4 * g] = accC[4 * g + 1] = accC[4 * g + 2] = accC[4 * g + 3] = 0.0f;
+                const float4 bg4 = make_float4(m.bg, m.bg, m.bg, m.bg);
+                rateP[g * kBT] = rate_plus(bg4, accP[2 * g], accP[2 * g + 1]);
+                rateC[g * kBT] = rate_plus(bg4, accC[2 * g], accC[2 * g + 1]);
+                accP[2 * g] = accP[2 * g + 1] = accC[2 * g] = accC[2 * g + 1] = make_float2(0.0f, 0.0f);
             }
         }
         float q, sg;
         pixel_loglik_sum<MODEL, RPT, W>(m, xs, lg, [&](int g) {
-            const float4 r = rateP[g * kBT];
-            return make_float4(r.x + accP[4 * g], r.y + accP[4 * g + 1], r.z + accP[4 * g + 2], r.w + accP[4 * g + 3]);
+            return rate_plus(rateP[g * kBT], accP[2 * g], accP[2 * g + 1]);
         }, q, sg);
         const float llp = finish_loglik<MODEL>(group_sum<TPP>(q), group_sum<TPP>(sg), HW);
         pixel_loglik_sum<MODEL, RPT, W>(m, xs, lg, [&](int g) {
-            const float4 r = rateC[g * kBT];
-            return make_float4(r.x + accC[4 * g], r.y + accC[4 * g + 1], r.z + accC[4 * g + 2], r.w + accC[4 * g + 3]);
+            return rate_plus(rateC[g * kBT], accC[2 * g], accC[2 * g + 1]);
         }, q, sg);
         const float llc = finish_loglik<MODEL>(group_sum<TPP>(q), group_sum<TPP>(sg), HW);
         float fin_p = prior_fin;
@@ -1365,12 +1364,8 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
         if (accept) {
 #pragma unroll
             for (int g = 0; g < PPT / 4; ++g) {
-                float4 r = rateP[g * kBT];
-                r.x += accP[4 * g]; r.y += accP[4 * g + 1]; r.z += accP[4 * g + 2]; r.w += accP[4 * g + 3];
-                rateP[g * kBT] = r;
-                float4 c = rateC[g * kBT];
-                c.x += accC[4 * g]; c.y += accC[4 * g + 1]; c.z += accC[4 * g + 2]; c.w += accC[4 * g + 3];
-                rateC[g * kBT] = c;
+                rateP[g * kBT] = rate_plus(rateP[g * kBT], accP[2 * g], accP[2 * g + 1]);
+                rateC[g * kBT] = rate_plus(rateC[g * kBT], accC[2 * g], accC[2 * g + 1]);
             }
             ll_par = llp; ll_chi = llc;
             prior_fin = fin_p; prior_bad = bad_p;

@@ -10,6 +10,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/smcdet_b200.h"
 
@@ -24,6 +25,7 @@
 #if !defined(__CUDACC__)
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 #endif
 
@@ -78,6 +80,86 @@ SMC_HD float rcp_fast(float x) {
 #else
     return 1.0f / x;
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed pairs: sm_100a executes two independent float32 operations per FFMA2 / FADD2 / FMUL2 instruction
+// (a scalar operand is broadcast for free), which halves the issue slots of the per-pixel arithmetic.  Each
+// half is the correctly rounded scalar operation, so results are bit-identical to the scalar host build.
+// ---------------------------------------------------------------------------------------------
+SMC_HD float2 bcast2(float s) { return make_float2(s, s); }
+
+SMC_HD float2 fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
+SMC_HD float2 add2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    volatile float x = a.x + b.x, y = a.y + b.y;
+    return make_float2(x, y);
+#endif
+}
+
+SMC_HD float2 sub2(float2 a, float2 b) { return add2(a, make_float2(-b.x, -b.y)); }
+
+SMC_HD float2 mul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    volatile float x = a.x * b.x, y = a.y * b.y;
+    return make_float2(x, y);
+#endif
+}
+
+SMC_HD float2 ex2_fast2(float2 x) { return make_float2(ex2_fast(x.x), ex2_fast(x.y)); }
+SMC_HD float2 lg2_fast2(float2 x) { return make_float2(lg2_fast(x.x), lg2_fast(x.y)); }
+SMC_HD float2 rcp_fast2(float2 x) { return make_float2(rcp_fast(x.x), rcp_fast(x.y)); }
+
+SMC_HD uint32_t f32_bits(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    return u;
+#endif
+}
+
+SMC_HD float bits_f32(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+#endif
+}
+
+// 2^x on the FMA / ALU pipes instead of the MUFU pipe (Cody-Waite: x = n + f, |f| <= 1/2, 2^f by a degree-5
+// minimax polynomial, 2^n added to the exponent field), for a pair of arguments.  The mutation kernel is bound by
+// the 16-lane MUFU pipe while the FMA pipe is two-thirds idle, so a fixed share of the power-law wing's ex2 goes
+// through here (kSoftPairs).  Relative error <= 2.2e-7 in float32 (ex2.approx: 2 ulp = 2.4e-7); arguments <= -127 (masked pixels
+// arrive as -inf) give exactly 0, arguments must stay below 128.
+SMC_HD float2 ex2_soft2(float2 x) {
+    const float magic = 12582912.0f;  // 1.5 * 2^23: adding it rounds to the nearest integer
+    x.x = fmaxf(x.x, -127.0f);
+    x.y = fmaxf(x.y, -127.0f);
+    const float2 j = add2(x, bcast2(magic));
+    const float2 n = add2(j, bcast2(-magic));
+    const float2 f = sub2(x, n);
+    float2 p = fma2(bcast2(1.327647245e-3f), f, bcast2(9.675540961e-3f));  // minimax on [-1/2, 1/2], 7.5e-8
+    p = fma2(p, f, bcast2(5.550713092e-2f));
+    p = fma2(p, f, bcast2(2.402212024e-1f));
+    p = fma2(p, f, bcast2(6.931469440e-1f));
+    p = fma2(p, f, bcast2(1.000000119f));
+    // the low bits of j hold n in two's complement: shifted into the exponent field
+    return make_float2(bits_f32(f32_bits(p.x) + (f32_bits(j.x) << 23)), bits_f32(f32_bits(p.y) + (f32_bits(j.y) << 23)));
 }
 
 SMC_HD float erfinv_f(float y) {
@@ -177,12 +259,24 @@ inline ModelK make_model_k(const smcdet_model_params& p) {
 // The (2R+1)^2 patch anchored at floor(loc) (smcdet/images.py:33-43) is separable as well:
 // rows/columns outside it get zero Gaussian factors and an infinite wing argument.
 // ---------------------------------------------------------------------------------------------
+// Column pairs (2 jp, 2 jp + 1) whose power-law wing takes the FMA-pipe exponential (ex2_soft2) instead of two
+// MUFU ex2: a 4-bit mask over the four pairs of every group of 8 columns.  It depends on the column only, so a
+// pixel's value does not depend on how rows are split over the lanes of a particle.  Tuned on B200.
+#ifndef SMC_SOFT_EX2_MASK
+#define SMC_SOFT_EX2_MASK 0x1
+#endif
+constexpr int kSoftEx2Mask = SMC_SOFT_EX2_MASK;
+
 template <int MODEL, int W>
 struct ColFactors {
-    float e1[W];
-    float e2[MODEL == SMCDET_MODEL_M71_NORMAL ? W : 1];
-    float bx[MODEL == SMCDET_MODEL_M71_NORMAL ? W : 1];
+    float2 e1[W / 2];
+    float2 e2[MODEL == SMCDET_MODEL_M71_NORMAL ? W / 2 : 1];
+    float2 bx[MODEL == SMCDET_MODEL_M71_NORMAL ? W / 2 : 1];
 };
+
+// element p of an array of pairs (p is a compile-time constant wherever this is used)
+SMC_HD float& pair_elem(float2* v, int p) { return (p & 1) ? v[p >> 1].y : v[p >> 1].x; }
+SMC_HD float pair_elem(const float2* v, int p) { return (p & 1) ? v[p >> 1].y : v[p >> 1].x; }
 
 template <int MODEL, int W>
 SMC_HD void col_factors(const ModelK& m, float l1, ColFactors<MODEL, W>& c) {
@@ -190,29 +284,26 @@ SMC_HD void col_factors(const ModelK& m, float l1, ColFactors<MODEL, W>& c) {
     // factors become ex2(-inf) = 0 and their wing argument +inf
     const float lo = floorf(l1) - m.radius, hi = floorf(l1) + m.radius;
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const float dx = ((float)j + 0.5f) - l1;
-        const float d2 = ((float)j >= lo && (float)j <= hi) ? dx * dx : INFINITY;
-        c.e1[j] = ex2_fast(-m.k1 * d2);
+    for (int jp = 0; jp < W / 2; ++jp) {
+        const float j0 = (float)(2 * jp), j1 = (float)(2 * jp + 1);
+        const float dx0 = (j0 + 0.5f) - l1, dx1 = (j1 + 0.5f) - l1;
+        const float2 d2 = make_float2((j0 >= lo && j0 <= hi) ? dx0 * dx0 : INFINITY,
+                                      (j1 >= lo && j1 <= hi) ? dx1 * dx1 : INFINITY);
+        c.e1[jp] = ex2_fast2(mul2(bcast2(-m.k1), d2));
         if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-            c.e2[j] = ex2_fast(-m.k2 * d2);
-            c.bx[j] = m.cpl * d2;
+            c.e2[jp] = ex2_fast2(mul2(bcast2(-m.k2), d2));
+            c.bx[jp] = mul2(bcast2(m.cpl), d2);
         }
     }
 }
 
-// acc[r*W + j] += wgt * psf(star, pixel (row0+r, j)) for the thread's RPT x W pixels.
+// acc[(r*W + j)/2] += wgt * psf(star, pixel (row0+r, j)) for the thread's RPT x W pixels (pairs of columns).
 template <int MODEL, int RPT, int W>
-SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int row0, float (&acc)[RPT * W]) {
+SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int row0, float2 (&acc)[RPT * W / 2]) {
     ColFactors<MODEL, W> c;
     col_factors<MODEL, W>(m, l1, c);
     const float lo = floorf(l0) - m.radius, hi = floorf(l0) + m.radius;
-    float lw = 0.f, sgn = 1.f;
-    if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-        lw = lg2_fast(fabsf(wgt) * m.p0);
-        sgn = (wgt < 0.f) ? -1.f : 1.f;
-    }
-    const float wb = wgt * m.b;
+    const float wb = wgt * m.b, wp = wgt * m.p0;
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const float fi = (float)(row0 + r);
@@ -223,16 +314,18 @@ SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int 
             const float g2 = wb * ex2_fast(-m.k2 * d2);
             const float ay = fmaf(m.cpl, d2, 1.0f);
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const float t = ay + c.bx[j];
-                const float pw = ex2_fast(fmaf(m.hb, lg2_fast(t), lw));
-                float v = fmaf(g1, c.e1[j], acc[r * W + j]);
-                v = fmaf(g2, c.e2[j], v);
-                acc[r * W + j] = fmaf(sgn, pw, v);
+            for (int jp = 0; jp < W / 2; ++jp) {
+                // wing p0 t^(-beta/2) = ex2(hb lg2 t); masked rows / columns have t = +inf -> exactly 0
+                const float2 t = add2(bcast2(ay), c.bx[jp]);
+                const float2 arg = mul2(bcast2(m.hb), lg2_fast2(t));
+                const float2 pw = ((kSoftEx2Mask >> (jp & 3)) & 1) ? ex2_soft2(arg) : ex2_fast2(arg);
+                float2 v = fma2(bcast2(g1), c.e1[jp], acc[r * (W / 2) + jp]);
+                v = fma2(bcast2(g2), c.e2[jp], v);
+                acc[r * (W / 2) + jp] = fma2(bcast2(wp), pw, v);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < W; ++j) acc[r * W + j] = fmaf(g1, c.e1[j], acc[r * W + j]);
+            for (int jp = 0; jp < W / 2; ++jp) acc[r * (W / 2) + jp] = fma2(bcast2(g1), c.e1[jp], acc[r * (W / 2) + jp]);
         }
     }
 }
@@ -260,63 +353,82 @@ SMC_HD float tree_sum(float (&v)[N]) {
 
 // Per-pixel log density summed over the lane's RPT rows of W pixels; returns the two partial sums (Q, S) that
 // finish_loglik combines after the reduction over the lanes of the particle:
-//   M71 (images.py:169-175): Q = sum (x-r)^2 / v, S = sum lg2 v, v = (na + nm r) * 2^-12 (four pixels share a rcp and a lg2)
-//   Gaussian-PSF model (images.py:91-102): Q = sum of Poisson / Normal terms, S = 0
+//   M71 (images.py:169-175): Q = sum (x-r)^2 / v, S = sum lg2 v, v = (na + nm r) * 2^-12.  Four pixels share one rcp
+//     and one lg2; an octet of pixels is handled as two such quads in the two halves of packed (FFMA2) operations:
+//     the even pixels of the octet in one half, the odd ones in the other.
+//   Gaussian-PSF model (images.py:91-102): Q = sum of Poisson / Normal terms, S = 0; the Normal branch (rate >
+//     normal_switch_rate) is only evaluated for rows that hold such a pixel.
 // x / lgam: the lane's observed pixels and lgamma(x+1) (16-byte aligned); rate4(g) = expected counts of pixels 4g..4g+3.
 template <int MODEL, int RPT, int W, class Rate4>
 SMC_HD void pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam, Rate4 rate4, float& Q, float& S) {
     const float4* x4 = reinterpret_cast<const float4*>(x);
     float qrow[RPT], srow[RPT];
     if (MODEL == SMCDET_MODEL_M71_NORMAL) {
+        const float2 nm = bcast2(m.nms), na = bcast2(m.nas), neg1 = bcast2(-1.0f);
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            float q = 0.f, s = 0.f;
+            float2 q = make_float2(0.f, 0.f), s = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int g = r * (W / 4); g < (r + 1) * (W / 4); ++g) {
-                const float4 rt = rate4(g);
-                const float4 xv = x4[g];
-                // four pixels share one rcp and one lg2:
-                //   sum d_i^2 / v_i = (n_ab v_cd + n_cd v_ab) / (v_ab v_cd),  sum lg2 v_i = lg2(v_ab v_cd)
+            for (int g = r * (W / 4); g < (r + 1) * (W / 4); g += 2) {
+                const float4 ra = rate4(g), rb = rate4(g + 1);
+                const float4 xa = x4[g], xb = x4[g + 1];
+                const float2 r0 = make_float2(ra.x, ra.y), r1 = make_float2(ra.z, ra.w);
+                const float2 r2 = make_float2(rb.x, rb.y), r3 = make_float2(rb.z, rb.w);
+                // per quad {a, b, c, d}:  sum d_i^2 / v_i = (n_ab v_cd + n_cd v_ab) / (v_ab v_cd),  sum lg2 v_i = lg2(v_ab v_cd)
                 // on variances scaled by kQuadScale = 2^-12 (exact), which keeps the products of four far from the
                 // float range for any pixel value below ~3e9; finish_loglik undoes the scale
-                const float va = fmaf(m.nms, rt.x, m.nas), vb = fmaf(m.nms, rt.y, m.nas);
-                const float vc = fmaf(m.nms, rt.z, m.nas), vd = fmaf(m.nms, rt.w, m.nas);
-                const float da = xv.x - rt.x, db = xv.y - rt.y, dc = xv.z - rt.z, dd = xv.w - rt.w;
-                const float vab = va * vb, vcd = vc * vd;
-                const float nab = fmaf(da * da, vb, (db * db) * va), ncd = fmaf(dc * dc, vd, (dd * dd) * vc);
-                const float den = vab * vcd;
-                q = fmaf(fmaf(nab, vcd, ncd * vab), rcp_fast(den), q);
-                s += lg2_fast(den);
+                const float2 va = fma2(nm, r0, na), vb = fma2(nm, r1, na), vc = fma2(nm, r2, na), vd = fma2(nm, r3, na);
+                const float2 da = fma2(neg1, r0, make_float2(xa.x, xa.y)), db = fma2(neg1, r1, make_float2(xa.z, xa.w));
+                const float2 dc = fma2(neg1, r2, make_float2(xb.x, xb.y)), dd = fma2(neg1, r3, make_float2(xb.z, xb.w));
+                const float2 vab = mul2(va, vb), vcd = mul2(vc, vd);
+                const float2 nab = fma2(mul2(da, da), vb, mul2(mul2(db, db), va));
+                const float2 ncd = fma2(mul2(dc, dc), vd, mul2(mul2(dd, dd), vc));
+                const float2 den = mul2(vab, vcd);
+                q = fma2(fma2(nab, vcd, mul2(ncd, vab)), rcp_fast2(den), q);
+                s = add2(s, lg2_fast2(den));
             }
-            qrow[r] = q; srow[r] = s;
+            qrow[r] = q.x + q.y; srow[r] = s.x + s.y;
         }
         Q = tree_sum<RPT>(qrow);
         S = tree_sum<RPT>(srow);
     } else {
         const float4* l4 = reinterpret_cast<const float4*>(lgam);
+        const float2 neg1 = bcast2(-1.0f);
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            float acc = 0.f;
+            float4 rr[W / 4];
+            float rmax = 0.0f;
 #pragma unroll
-            for (int g = r * (W / 4); g < (r + 1) * (W / 4); ++g) {
-                const float4 r4 = rate4(g);
-                const float4 xv4 = x4[g];
-                const float4 lg4 = l4[g];
-                const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-                const float xx[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
-                const float gg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+            for (int g = 0; g < W / 4; ++g) {
+                rr[g] = rate4(r * (W / 4) + g);
+                rmax = fmaxf(fmaxf(rmax, fmaxf(rr[g].x, rr[g].y)), fmaxf(rr[g].z, rr[g].w));
+            }
+            const bool bright = rmax > m.nswitch;  // rare: only then is the Normal branch evaluated (images.py:96-101)
+            float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float rv = rr[e], xv = xx[e];
-                    const float lg = lg2_fast(rv) * kLn2;
-                    // both branches are evaluated and selected: a per-pixel branch cost more than the extra rcp
-                    const float d = xv - rv;
-                    const float normal = fmaf(-0.5f * (d * d), rcp_fast(rv), fmaf(-0.5f, lg, -kLogSqrt2Pi));
-                    const float xl = (xv == 0.0f) ? 0.0f : xv * lg;
-                    acc += (rv > m.nswitch) ? normal : ((xl - rv) - gg[e]);
+            for (int g = 0; g < W / 4; ++g) {
+                const float4 xv4 = x4[r * (W / 4) + g];
+                const float4 lg4 = l4[r * (W / 4) + g];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 rv = h ? make_float2(rr[g].z, rr[g].w) : make_float2(rr[g].x, rr[g].y);
+                    const float2 xv = h ? make_float2(xv4.z, xv4.w) : make_float2(xv4.x, xv4.y);
+                    const float2 gg = h ? make_float2(lg4.z, lg4.w) : make_float2(lg4.x, lg4.y);
+                    const float2 lg = mul2(lg2_fast2(rv), bcast2(kLn2));
+                    float2 xl = mul2(xv, lg);  // xlogy: 0 where x == 0
+                    xl.x = (xv.x == 0.0f) ? 0.0f : xl.x;
+                    xl.y = (xv.y == 0.0f) ? 0.0f : xl.y;
+                    float2 term = fma2(neg1, gg, fma2(neg1, rv, xl));  // (xl - rate) - lgamma(x + 1)
+                    if (bright) {
+                        const float2 d = fma2(neg1, rv, xv);
+                        const float2 nrm = fma2(mul2(bcast2(-0.5f), mul2(d, d)), rcp_fast2(rv), fma2(bcast2(-0.5f), lg, bcast2(-kLogSqrt2Pi)));
+                        term.x = (rv.x > m.nswitch) ? nrm.x : term.x;
+                        term.y = (rv.y > m.nswitch) ? nrm.y : term.y;
+                    }
+                    acc = add2(acc, term);
                 }
             }
-            qrow[r] = acc;
+            qrow[r] = acc.x + acc.y;
         }
         Q = tree_sum<RPT>(qrow);
         S = 0.f;
@@ -359,7 +471,7 @@ SMC_HD float pixel_dlogpdf(const ModelK& m, float x, float r) {
 
 template <int MODEL, int RPT, int W, bool ACC, class WRow>
 SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_wgt, int row0, WRow w_row,
-                                 float (&acc)[RPT * W], float& sP, float& s0, float& s1) {
+                                 float2 (&acc)[RPT * W / 2], float& sP, float& s0, float& s1) {
     ColFactors<MODEL, W> c;
     col_factors<MODEL, W>(m, l1, c);
     float dxs[W];
@@ -381,13 +493,13 @@ SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_
             const float ay = fmaf(m.cpl, d2, 1.0f);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                const float t = ay + c.bx[j];
+                const float t = ay + pair_elem(c.bx, j);
                 const float pw = ex2_fast(fmaf(m.hb, lg2_fast(t), m.lp0));
-                const float e1 = g1 * c.e1[j], e2 = g2 * c.e2[j];
+                const float e1 = g1 * pair_elem(c.e1, j), e2 = g2 * pair_elem(c.e2, j);
                 const float P = (e1 + e2) + pw;
                 const float Q = fmaf(pw * rcp_fast(t), m.isp, fmaf(e2, m.is2, e1 * m.is1));
                 const float wp = wr[j];
-                if (ACC) acc[r * W + j] = fmaf(acc_wgt, P, acc[r * W + j]);
+                if (ACC) pair_elem(acc, r * W + j) = fmaf(acc_wgt, P, pair_elem(acc, r * W + j));
                 rowP = fmaf(wp, P, rowP);
                 const float wq = wp * Q;
                 rowQ0 += wq;
@@ -396,9 +508,9 @@ SMC_HD void star_grad_accumulate(const ModelK& m, float l0, float l1, float acc_
         } else {
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                const float P = g1 * c.e1[j];
+                const float P = g1 * pair_elem(c.e1, j);
                 const float wp = wr[j];
-                if (ACC) acc[r * W + j] = fmaf(acc_wgt, P, acc[r * W + j]);
+                if (ACC) pair_elem(acc, r * W + j) = fmaf(acc_wgt, P, pair_elem(acc, r * W + j));
                 rowP = fmaf(wp, P, rowP);
                 const float wq = wp * (P * m.is1);
                 rowQ0 += wq;

@@ -2,21 +2,35 @@
 """Benchmark of the smcdet per-tile SMC hot path on B200 (contract: see the task statement).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          own arm (CUDA library)
-  python bench.py --impl reference [...]                        reference arm (CPU port of the reference)
+  python bench.py --impl reference [...]                        reference arm (the reference's path on the host CPU)
   torchrun --nproc-per-node N bench.py --gpus N ...             one rank per GPU
 
-Workload (BASELINE.json configs[1], "m71synthetic"): a synthetic SDSS-r-band-like field drawn from the
-M71 model itself, cut into 8x8 tiles; per tile a likelihood-tempered SMC sampler with N = 10 000
-catalogs of D = 10 stars, 100 single-site MH sweeps per SMC iteration, ESS threshold 0.5 N,
-multinomial resampling, run to temperature 1 (notebooks/smc.ipynb cells 3-7 of the reference).
-Every rank owns `--tiles-per-gpu` tiles (weak scaling; tiles are independent, no data-path collective).
+Workloads (--workload):
+  m71synthetic      BASELINE.json configs[1] (default): synthetic SDSS-r-band-like field drawn from the M71 model, cut
+                    into 8x8 tiles; per tile a likelihood-tempered SMC sampler with N = 10 000 catalogs of D = 10 stars,
+                    100 single-site MH sweeps per SMC iteration, ESS threshold 0.5 N, multinomial resampling, run to
+                    temperature 1 (notebooks/smc.ipynb cells 3-7 of the reference)
+  m71semisynthetic  configs[2]: three times the source density, D = 16
+  basic             configs[0]: Gaussian PSF + Poisson likelihood, D = 8, pad 2 (experiments/basic/run_smc.py:44-105)
+  allstrata         north_star's target sentence: every tile x every count stratum 0..D as count-stratified SMC
+                    (manuscript.tex:312-356), the (tile, count) strata spread over the GPUs by expected cost
 
-A "step" is one complete SMCsampler.run() over the rank's tiles.  `value` = particle-likelihood
-evaluations per second over the whole job, counted as the reference evaluates them: per SMC iteration
-and live tile N*(num_iters + 2) (kernel.py:64-70, :89-96; sampler.py:100-102), plus N for initialize.
+Scaling (--scaling):
+  weak    every rank owns --tiles-per-gpu tiles of its own field (tiles are independent: no data-path collective)
+  strong  ONE field of --field-tiles tiles (BASELINE.json configs[3]) sharded round-robin over the ranks
+  both    (default) the line's `value` is the weak-scaling number; the object `strong` carries the fixed-field number
+          and a checksum of the field's per-tile summaries, which must not depend on the number of GPUs
+In every mode the end-to-end region gathers the posterior catalogs with NCCL onto rank 0 and runs the reference's
+`Aggregate` finish there (aggregate.py:583-589), then reads the pruned catalogs back to the host.
+
+A "step" is one complete run to temperature 1 over the rank's tiles.  `value` = particle-likelihood evaluations per
+second over the whole job, counted as the reference evaluates them: per SMC iteration and live tile N*(num_iters + 2)
+(kernel.py:64-70, :89-96; sampler.py:100-102), plus N for initialize.
 """
 
 import argparse
+import contextlib
+import hashlib
 import json
 import os
 import sys
@@ -36,7 +50,12 @@ M71 = dict(background=104.1486587524414, adu_per_nmgy=241.02658081054688,
 PRIOR = dict(counts_rate=0.030264640226960182, flux_alpha=0.21411753249015655, flux_lower=0.06291294097900389,
              flux_upper=1804.6791992187502)
 DETECTION = 0.25165176391601557
-TILE, PAD = 8, 4
+TILE = 8
+# experiments/basic/run_smc.py:44-105 (Gaussian PSF, Poisson likelihood)
+BASIC_STDEV, BASIC_BG = 0.93, 200.0
+_PSF_MAX = 1.0 / (2 * np.pi * BASIC_STDEV**2)
+BASIC_SCALE = float(5 * np.sqrt(BASIC_BG) / _PSF_MAX)          # 384.265: the detection threshold
+BASIC_ALPHA = float(-np.log(1 - 0.99) / (np.log(50 * np.sqrt(BASIC_BG) / _PSF_MAX) - np.log(BASIC_SCALE)))
 METRIC, UNIT = "particle-likelihood evals/sec", "evals/s"
 
 
@@ -46,38 +65,68 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--tiles-per-gpu", type=int, default=800)
+    ap.add_argument("--workload", default="m71synthetic", choices=["m71synthetic", "m71semisynthetic", "basic", "allstrata"])
+    ap.add_argument("--scaling", default="both", choices=["weak", "strong", "both"])
+    ap.add_argument("--tiles-per-gpu", type=int, default=None, help="weak scaling: tiles per rank (default 800; 96 for allstrata)")
+    ap.add_argument("--field-tiles", type=int, default=None, help="strong scaling: tiles of the one field (default 800; 96 for allstrata)")
     ap.add_argument("--particles", type=int, default=10000)
-    ap.add_argument("--stars", type=int, default=None, help="stars per catalog (default 10; 16 for m71semisynthetic)")
-    ap.add_argument("--workload", default="m71synthetic", choices=["m71synthetic", "m71semisynthetic"],
-                    help="m71semisynthetic = BASELINE.json configs[2]: three times the source density, D = 16 (SURVEY.md 8d)")
+    ap.add_argument("--stars", type=int, default=None, help="stars per catalog (10; 16 m71semisynthetic; 8 basic)")
     ap.add_argument("--mh-iters", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.stars is None:
-        a.stars = 16 if a.workload == "m71semisynthetic" else 10
+        a.stars = {"m71semisynthetic": 16, "basic": 8}.get(a.workload, 10)
+    small = a.workload == "allstrata"
+    if a.tiles_per_gpu is None:
+        a.tiles_per_gpu = 96 if small else 800
+    if a.field_tiles is None:
+        a.field_tiles = 96 if small else 800
     return a
 
 
+def is_m71(a):
+    return a.workload != "basic"
+
+
+def pad_of(a):
+    return 2 if a.workload == "basic" else 4
+
+
 def workload_config(a):
-    dense = getattr(a, "workload", "m71synthetic") == "m71semisynthetic"
-    name = ("m71semisynthetic-shaped: as m71synthetic with three times the source density and larger catalogs "
-            "(BASELINE.json configs[2]; SURVEY.md 8d config 3)") if dense else (
-        "m71synthetic: M71 PSF + Normal likelihood, 8x8 tiles, psf_radius 8, pad 4 "
-        "(BASELINE.json configs[1]; notebooks/smc.ipynb of the reference)")
-    return {"workload": name,
-            "tiles_per_gpu": a.tiles_per_gpu, "particles_per_tile": a.particles, "stars_per_catalog": a.stars,
-            "mh_iters": a.mh_iters, "ess_threshold_prop": 0.5, "resample": "multinomial",
+    names = {
+        "m71synthetic": "m71synthetic: M71 PSF + Normal likelihood, 8x8 tiles, psf_radius 8, pad 4 "
+                        "(BASELINE.json configs[1]; notebooks/smc.ipynb of the reference)",
+        "m71semisynthetic": "m71semisynthetic-shaped: as m71synthetic with three times the source density and larger catalogs "
+                            "(BASELINE.json configs[2]; SURVEY.md 8d config 3)",
+        "basic": "basic: Gaussian PSF (stdev 0.93) + Poisson likelihood, 8x8 tiles, psf_radius 8, pad 2, background 200 "
+                 "(BASELINE.json configs[0]; experiments/basic/run_smc.py:44-105 of the reference)",
+        "allstrata": "allstrata: count-stratified SMC, every tile x every count 0..D as its own tempered sampler "
+                     "(north_star target; manuscript.tex:312-356), M71 model as m71synthetic",
+    }
+    sharding = ("(tile, count) strata assigned to ranks by expected cost (longest-processing-time), per-stratum evidences "
+                "all-gathered (NCCL)") if a.workload == "allstrata" else (
+        "tiles sharded round-robin, no data-path collective; end to end: NCCL gather of every tile's weighted catalogs "
+        "(counts, locs, fluxes, weights, log Z) onto rank 0 and the Aggregate finish there (aggregate.py:583-589)")
+    return {"workload": names[a.workload],
+            "tiles_per_gpu": a.tiles_per_gpu, "field_tiles_strong": a.field_tiles, "particles_per_tile": a.particles,
+            "stars_per_catalog": a.stars, "mh_iters": a.mh_iters, "ess_threshold_prop": 0.5, "resample": "multinomial",
             "loglik_for_tempering": "from the incrementally updated rate image (default; 7e-7 relative drift measured)",
-            "step": "one full SMCsampler.run() to temperature 1 over all tiles of the rank",
+            "step": "one full run to temperature 1 over all tiles of the rank",
             "finished_tiles": "frozen (each tile runs as in the reference's per-tile loop, experiments/m71/run_smc.py:113-124)",
-            "parallelism": f"tiles sharded over {a.gpus} GPU(s), no data-path collective; final all_gather of catalogs",
+            "parallelism": f"{a.gpus} GPU(s): {sharding}",
             "l2": "particle state per rank (>= 1 GB at the default size) exceeds the 126 MB L2; no explicit flush"}
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle (C port of the reference's arithmetic), all host threads
+# CPU arm: the oracle (C port of the reference's arithmetic), all host threads; and the unmodified reference
 # ----------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_smc_iteration(O, om, op, mh, tiles, state, rng, N, iters):
     """One SMC iteration of the reference (sampler.py:244-247) on the oracle: resample, MH, temper,
     update_weights.  Returns the number of particle-likelihood evaluations."""
@@ -101,18 +150,29 @@ def cpu_smc_iteration(O, om, op, mh, tiles, state, rng, N, iters):
 def cpu_sample_setup(a, n_tiles, seed=0):
     from oracle import api as O
 
-    om = O.m71_model(M71["psf_radius"], M71["psf_params"], M71["background"], M71["adu_per_nmgy"],
-                     M71["noise_additive"], M71["noise_multiplicative"])
-    op = O.m71_prior(a.stars, a.stars, PRIOR["counts_rate"], TILE, TILE, PRIOR["flux_alpha"], PRIOR["flux_lower"],
-                     PRIOR["flux_upper"], pad=PAD)
-    mh = O.make_mh(a.mh_iters, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"], (-PAD, -PAD), (TILE + PAD, TILE + PAD))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm always takes every core it may run on
+    O.set_num_threads(host_cores())
+    pad = pad_of(a)
     rng = np.random.default_rng(seed)
     N, D = a.particles, a.stars
-    # observed tiles: drawn from the model with a handful of stars (true prior of the notebook)
-    tp = O.m71_prior(4, 4, PRIOR["counts_rate"], TILE, TILE, PRIOR["flux_alpha"], DETECTION, PRIOR["flux_upper"], pad=PAD)
+    if is_m71(a):
+        om = O.m71_model(M71["psf_radius"], M71["psf_params"], M71["background"], M71["adu_per_nmgy"],
+                         M71["noise_additive"], M71["noise_multiplicative"])
+        op = O.m71_prior(D, D, PRIOR["counts_rate"], TILE, TILE, PRIOR["flux_alpha"], PRIOR["flux_lower"], PRIOR["flux_upper"], pad=pad)
+        mh = O.make_mh(a.mh_iters, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"], (-pad, -pad), (TILE + pad, TILE + pad))
+        tp = O.m71_prior(4, 4, PRIOR["counts_rate"], TILE, TILE, PRIOR["flux_alpha"], DETECTION, PRIOR["flux_upper"], pad=pad)
+    else:
+        om = O.gauss_model(8, BASIC_STDEV, BASIC_BG)
+        op = O.pareto_prior(D, D, TILE, TILE, 0.9 * BASIC_SCALE, BASIC_ALPHA, pad=pad)
+        mh = O.make_mh(a.mh_iters, 0.1, 100.0, 0.9 * BASIC_SCALE, 1e6, (-pad, -pad), (TILE + pad, TILE + pad))
+        tp = O.pareto_prior(4, 4, TILE, TILE, BASIC_SCALE, BASIC_ALPHA, pad=pad)
+    # observed tiles: drawn from the model with a handful of stars
     _, tl, tf = O.prior_sample(tp, rng.random((n_tiles, 1, 4, 2), dtype=np.float32), rng.random((n_tiles, 1, 4), dtype=np.float32), 1)
     rate = O.render(om, tl, tf, TILE, TILE)[..., 0]
-    tiles = (rate + rng.standard_normal(rate.shape) * np.sqrt(M71["noise_additive"] + M71["noise_multiplicative"] * rate)).astype(np.float32)
+    if is_m71(a):
+        tiles = (rate + rng.standard_normal(rate.shape) * np.sqrt(M71["noise_additive"] + M71["noise_multiplicative"] * rate)).astype(np.float32)
+    else:
+        tiles = rng.poisson(rate).astype(np.float32)
     counts, locs, fluxes = O.prior_sample(op, rng.random((n_tiles, N, D, 2), dtype=np.float32),
                                           rng.random((n_tiles, N, D), dtype=np.float32), N)
     state = dict(counts=counts, locs=locs, fluxes=fluxes, weights=np.full((n_tiles, N), 1.0 / N, np.float32),
@@ -151,20 +211,86 @@ def cpu_measure(a, target_seconds, steps=1, warmup=0):
     return dict(value=evals / total, unit=UNIT, cores=threads, kind="port", sample=sample), total / max(1, steps) * 1e3, n_tiles
 
 
+def reference_measure(a, target_seconds=20.0):
+    """The UNMODIFIED reference (oracle/_ref/smcdet, copied from /root/reference by oracle/make_ref.sh at build time;
+    pure Python / PyTorch) timed on the host cores: SMC iterations of its own SMCsampler (resample, mutate, temper,
+    update_weights: sampler.py:244-247) on one tile at reduced N and MH sweeps.  None if the copy is absent."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "smcdet", "sampler.py")):
+        return None
+    import torch
+
+    sys.path.insert(0, ref_dir)
+    try:
+        from smcdet.images import ImageModel, M71ImageModel
+        from smcdet.kernel import SingleComponentMH
+        from smcdet.prior import M71Prior, ParetoStarPrior
+        from smcdet.sampler import SMCsampler
+    finally:
+        sys.path.remove(ref_dir)
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    N, iters, D, pad = 1000, 10, a.stars, pad_of(a)
+    torch.manual_seed(0)
+    if is_m71(a):
+        im = M71ImageModel(image_height=TILE, image_width=TILE, **M71)
+        pr = M71Prior(min_objects=D, max_objects=D, image_height=TILE, image_width=TILE, pad=pad, **PRIOR)
+        tp = M71Prior(min_objects=4, max_objects=4, image_height=TILE, image_width=TILE, pad=pad,
+                      **dict(PRIOR, flux_lower=DETECTION))
+        mh = SingleComponentMH(iters, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"])
+        thr = DETECTION
+    else:
+        im = ImageModel(image_height=TILE, image_width=TILE, psf_radius=8, psf_stdev=BASIC_STDEV, background=BASIC_BG)
+        pr = ParetoStarPrior(min_objects=D, max_objects=D, image_height=TILE, image_width=TILE, flux_scale=0.9 * BASIC_SCALE,
+                             flux_alpha=BASIC_ALPHA, pad=pad)
+        tp = ParetoStarPrior(min_objects=4, max_objects=4, image_height=TILE, image_width=TILE, flux_scale=BASIC_SCALE,
+                             flux_alpha=BASIC_ALPHA, pad=pad)
+        mh = SingleComponentMH(iters, 0.1, 100.0, 0.9 * BASIC_SCALE, 1e6)
+        thr = BASIC_SCALE
+    _, tl, tf = tp.sample(num_tiles_per_side=1, stratify_by_count=True, num_catalogs_per_count=1)
+    image = im.sample(tl, tf)[0, 0, :, :, 0].contiguous()
+    with contextlib.redirect_stdout(sys.stderr):
+        s = SMCsampler(image, TILE, pr, im, mh, N, 0.5, "multinomial", thr, 100, print_every=10**6)
+        s.initialize()
+        s.temper()
+        s.update_weights()
+        done, evals, t_total = 0, 0, 0.0
+        while t_total < target_seconds and done < 12:
+            t0 = time.perf_counter()
+            s.resample(); s.mutate(); s.temper(); s.update_weights()
+            dt = time.perf_counter() - t0
+            if done > 0:  # the first iteration warms torch's thread pool and allocator
+                t_total += dt
+                evals += N * (iters + 2)
+            done += 1
+    if evals == 0:
+        return None
+    return dict(value=evals / t_total, unit=UNIT, cores=cores, kind="reference",
+                sample=f"the unmodified reference's SMCsampler (oracle/_ref/smcdet, torch {torch.__version__} on the CPU, "
+                       f"{cores} threads): {done - 1} SMC iterations (resample, mutate, temper, update_weights) on 1 tile x "
+                       f"{N} particles x {D} stars, {iters} MH sweeps")
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     base, ms, n_tiles = cpu_measure(a, target_seconds=6.0, steps=a.steps, warmup=a.warmup)
+    real = None
+    try:
+        real = reference_measure(a, target_seconds=10.0)
+    except Exception as exc:  # noqa: BLE001  (the copy of the reference is optional test infrastructure)
+        real = {"kind": "reference", "unavailable": repr(exc)[:200]}
+    base_all = dict(base, also=[real] if real else [])
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a),
-            "cpu_baseline": base,
+            "cpu_baseline": base_all,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "tiles_per_sec_full_smc_est": base["value"] / (a.particles * (a.mh_iters + 2) * 12.0),
-            "note": "CPU port (oracle/smcdet_oracle.c, OpenMP) of the reference's arithmetic: the reference itself is "
-                    "pure Python/PyTorch and /root/reference does not exist on the GPU box; the unmodified torch path "
-                    "measured 1.2-1.45e4 evals/s on 8 threads in the build container (BASELINE.md section 2)"}
+            "note": "value = CPU port (oracle/smcdet_oracle.c, OpenMP, all host cores whatever OMP_NUM_THREADS says) of the "
+                    "reference's arithmetic -- the faster of the two CPU baselines, so ratios against it are conservative; "
+                    "cpu_baseline.also = the unmodified torch reference timed on the same cores at reduced N"}
     print(json.dumps(line))
 
 
@@ -236,36 +362,61 @@ class ClockSampler(threading.Thread):
         busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] if power else sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons,
-                "source": "NVML (pynvml) every 200 ms during the timed region", **({"error": self.error} if hasattr(self, "error") else {})}
+                "source": "NVML (pynvml) every 200 ms during the timed regions", **({"error": self.error} if hasattr(self, "error") else {})}
 
 
-def make_field(a, rank, dev):
-    """Synthetic field: tiles drawn from the M71 model with the reference's true prior
-    (notebooks/smc.ipynb cell 3); tile g of the job is seeded by its global id."""
+def make_objects(a):
+    """(image model, inference prior, true prior, detection threshold, MH kernel factory) of the workload."""
+    from smcdet_b200.images import ImageModel, M71ImageModel
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.prior import M71Prior, ParetoStarPrior
+
+    D, pad = a.stars, pad_of(a)
+    if is_m71(a):
+        model = M71ImageModel(TILE, TILE, **M71)
+        lo = 0 if a.workload == "allstrata" else D
+        prior = M71Prior(lo, D, PRIOR["counts_rate"], TILE, TILE, flux_alpha=PRIOR["flux_alpha"],
+                         flux_lower=PRIOR["flux_lower"], flux_upper=PRIOR["flux_upper"], pad=pad)
+        true_prior = M71Prior(0, 24, PRIOR["counts_rate"], TILE, TILE, flux_alpha=PRIOR["flux_alpha"],
+                              flux_lower=DETECTION, flux_upper=PRIOR["flux_upper"], pad=pad)
+        return model, prior, true_prior, DETECTION, lambda: SingleComponentMH(a.mh_iters, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"])
+    model = ImageModel(TILE, TILE, psf_radius=8, psf_stdev=BASIC_STDEV, background=BASIC_BG)
+    prior = ParetoStarPrior(D, D, TILE, TILE, flux_scale=0.9 * BASIC_SCALE, flux_alpha=BASIC_ALPHA, pad=pad)
+    true_prior = ParetoStarPrior(0, 8, TILE, TILE, flux_scale=BASIC_SCALE, flux_alpha=BASIC_ALPHA, pad=pad)
+    return model, prior, true_prior, BASIC_SCALE, lambda: SingleComponentMH(a.mh_iters, 0.1, 100.0, 0.9 * BASIC_SCALE, 1e6)
+
+
+def make_field(a, num_tiles, seed, dev):
+    """Synthetic field of `num_tiles` tiles drawn from the workload's image model with its true prior
+    (notebooks/smc.ipynb cell 3; experiments/basic/generate_images.py:26-76): [T, 8, 8] on `dev`."""
     import torch
 
-    from smcdet_b200.images import M71ImageModel
-    from smcdet_b200.prior import M71Prior
-
-    model = M71ImageModel(TILE, TILE, **M71)
-    true_prior = M71Prior(0, 24, PRIOR["counts_rate"], TILE, TILE, flux_alpha=PRIOR["flux_alpha"],
-                          flux_lower=DETECTION, flux_upper=PRIOR["flux_upper"], pad=PAD)
-    T = a.tiles_per_gpu
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    density = 3.0 if getattr(a, "workload", "m71synthetic") == "m71semisynthetic" else 1.0
-    counts = torch.poisson(torch.full((T,), density * float(true_prior._count_rate()), device=dev), generator=g).clamp(max=24)
-    D = 24
-    low, high = -PAD, TILE + PAD
+    model, _, _, _, _ = make_objects(a)
+    pad = pad_of(a)
+    T, D = num_tiles, 24
+    g = torch.Generator(device=dev).manual_seed(seed)
+    low, high = -pad, TILE + pad
+    if is_m71(a):
+        density = 3.0 if a.workload == "m71semisynthetic" else 1.0
+        mean = density * PRIOR["counts_rate"] * (TILE + 2 * pad) ** 2
+        counts = torch.poisson(torch.full((T,), mean, device=dev), generator=g).clamp(max=D)
+        al = PRIOR["flux_alpha"]
+        ua, la = PRIOR["flux_upper"] ** al, DETECTION ** al
+        u = torch.rand(T, 1, 1, D, device=dev, generator=g)
+        fluxes = ((ua - u * ua + u * la) / (la * ua)) ** (-1.0 / al)
+    else:
+        counts = torch.randint(0, 9, (T,), device=dev, generator=g).float()   # DiscreteUniform{0..8} (prior.py:157-162)
+        u = torch.rand(T, 1, 1, D, device=dev, generator=g)
+        fluxes = BASIC_SCALE * (1.0 - u) ** (-1.0 / BASIC_ALPHA)               # Pareto(scale, alpha)
     locs = low + torch.rand(T, 1, 1, D, 2, device=dev, generator=g) * (high - low)
-    al = PRIOR["flux_alpha"]
-    ua, la = PRIOR["flux_upper"] ** al, DETECTION ** al
-    u = torch.rand(T, 1, 1, D, device=dev, generator=g)
-    fluxes = ((ua - u * ua + u * la) / (la * ua)) ** (-1.0 / al)
     mask = torch.arange(D, device=dev).view(1, 1, 1, D) < counts.view(T, 1, 1, 1)
     rate = model._rate(locs * mask.unsqueeze(-1), fluxes * mask)  # [T,1,8,8,1]
-    noise = torch.randn(rate.shape, device=dev, generator=g)
-    img = rate + noise * (model.noise_additive + model.noise_multiplicative * rate).sqrt()
-    return img[..., 0].contiguous()  # [T,1,8,8]
+    if is_m71(a):
+        noise = torch.randn(rate.shape, device=dev, generator=g)
+        img = rate + noise * (model.noise_additive + model.noise_multiplicative * rate).sqrt()
+    else:
+        img = torch.poisson(rate, generator=g)
+    return img[:, 0, :, :, 0].contiguous()  # [T,8,8]
 
 
 def run_own(a):
@@ -273,11 +424,8 @@ def run_own(a):
     import torch.distributed as dist
 
     from smcdet_b200 import _lib as L
-    from smcdet_b200.images import M71ImageModel
-    from smcdet_b200.kernel import SingleComponentMH
-    from smcdet_b200.prior import M71Prior
-    from smcdet_b200.sampler import SMCsampler
-    from smcdet_b200.shard import gather_tiles
+    from smcdet_b200.cssmc import CountStratifiedSMC
+    from smcdet_b200.shard import ShardedSMC, gather_tiles, shard_tile_ids
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -301,103 +449,196 @@ def run_own(a):
             os.close(saved_stdout)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
 
-    T, N, D, iters = a.tiles_per_gpu, a.particles, a.stars, a.mh_iters
-    model = M71ImageModel(TILE, TILE, **M71)
-    prior = M71Prior(D, D, PRIOR["counts_rate"], TILE, TILE, flux_alpha=PRIOR["flux_alpha"],
-                     flux_lower=PRIOR["flux_lower"], flux_upper=PRIOR["flux_upper"], pad=PAD)
-    tiles_dev = make_field(a, rank, dev)
-    tiles_host = tiles_dev.cpu().pin_memory()
-    tile_ids = (torch.arange(T, device=dev, dtype=torch.int64) * world + rank).view(T, 1)
+    N, D, iters = a.particles, a.stars, a.mh_iters
+    model, prior, _, threshold, new_mh = make_objects(a)
+    strata = a.workload == "allstrata"
+    ns = D + 1 if strata else 1
     lib = L.lib()
-
-    def one_run(tiles, seed, mh):
-        torch.manual_seed(seed)
-        s = SMCsampler(tiles, TILE, prior, model, mh, N, 0.5, "multinomial", DETECTION, 200, tile_ids=tile_ids,
-                       freeze_finished=True, verbose=False)
-        s.run()
-        return s
-
-    def count_evals(s, mh):
-        # per launch: live tiles x N x (iters + 2); + T*N for initialize
-        live = sum(int(T if act is None else act.sum().item()) for (_, _, act, *_r) in mh.event_log)
-        return live * N * (iters + 2) + T * N, live
+    quiet = contextlib.redirect_stdout(sys.stderr)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    # ------------------------------------------------------------------------------------------
+    # one job = one field of `num_tiles` tiles sharded over the ranks
+    # ------------------------------------------------------------------------------------------
+    class Job(object):
+        def __init__(self, num_tiles, field_seed):
+            self.T = num_tiles
+            self.field = make_field(a, num_tiles, field_seed, dev)          # the whole field, identical on every rank
+            self.field_host = self.field.cpu().pin_memory()
+            self.local_ids = shard_tile_ids(num_tiles, world, rank)
+            self.T_local = len(self.local_ids)
+
+        def run(self, seed, tiles=None, e2e=False):
+            """One step.  Returns (evals, live segment-iterations, MH event log, outputs for the host, summaries)."""
+            torch.manual_seed(seed)
+            mh = new_mh()
+            mh.event_log = []
+            field = self.field if tiles is None else tiles
+            if strata:
+                with quiet:
+                    cs = CountStratifiedSMC(field.view(self.T, 1, TILE, TILE), TILE, prior, model, mh, N, 0.5, "multinomial",
+                                            threshold, 200, verbose=False, keep_samplers=True, rank=rank, world=world,
+                                            seed=seed)
+                    cs.run()
+                smp = cs.samplers["all"]
+                mhk = smp.MutationKernel
+                live = sum(cs.live_strata)
+                S = cs.local_strata.numel()
+                evals = live * N * (iters + 2) + S * N
+                summ = torch.stack([cs.log_evidence.view(-1), cs.posterior_mean_count().view(-1),
+                                    cs.posterior_count_probs.view(self.T, ns).max(-1).values,
+                                    cs.log_normalizing_constant.view(self.T, ns)[:, -1]], -1)   # [T, 4], identical on all ranks
+                outs = [summ, cs.posterior_count_probs.view(self.T, ns)] if rank == 0 else []
+                return evals, live, mhk.event_log, outs, summ, int(smp.iter)
+            sh = ShardedSMC(field, TILE, prior, model, mh, N, 0.5, "multinomial", threshold, 200, seed=seed, device=dev)
+            sh.run()
+            s = sh.sampler
+            live = sum(s.live_tiles)
+            evals = live * N * (iters + 2) + self.T_local * N
+            if not e2e:
+                summ = sh.local_results()["summaries"]
+                return evals, live, mh.event_log, [], summ, int(s.iter)
+            # the reference's finish: all tiles' weighted catalogs -> Aggregate on rank 0 (NCCL gather for world > 1)
+            with quiet:
+                agg = sh.sink()
+            outs = []
+            if agg is not None:
+                Tn = self.T
+                outs = [agg.summaries, agg.pruned_counts.view(Tn, N).to(torch.int16), agg.pruned_locs.view(Tn, N, D, 2),
+                        agg.pruned_fluxes.view(Tn, N, D)]
+            return evals, live, mh.event_log, outs, None, int(s.iter)
+
+        def summaries_global(self, summ):
+            """[T, k] per-tile summaries in global tile order on every rank (strata: already global)."""
+            if strata or world == 1:
+                return summ
+            return gather_tiles(summ.contiguous(), self.T)
+
+    def timed(job, steps, seed0, e2e):
+        """`steps` steps of `job` between two events; e2e: tiles start in pinned host memory and the step's results
+        land in pinned host buffers (the read-back of step k overlaps step k + 1 on a copy stream; everything is complete
+        before the closing event).  Returns a dict of measurements (times are the max over ranks)."""
+        copy_stream = torch.cuda.Stream(device=dev)
+        host_sets, pending = {}, []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.launches
+        evals = live_total = h2d = d2h = 0
+        logs, smc_iters, summ = [], [], None
+        barrier()
+        e0.record(torch.cuda.current_stream(dev))
+        for k in range(steps):
+            tiles = None
+            if e2e:
+                tiles = job.field_host.to(dev, non_blocking=True)
+                h2d += job.field_host.numel() * 4
+            ev, live, log, outs, summ_k, it = job.run(seed0 + k, tiles, e2e)
+            evals += ev
+            live_total += live
+            logs.append(log)
+            smc_iters.append(it)
+            summ = summ_k if summ_k is not None else summ
+            if e2e and outs:
+                slot = k % 2
+                if slot not in host_sets:
+                    host_sets[slot] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ready)
+                    for hbuf, o in zip(host_sets[slot], outs):
+                        hbuf.copy_(o, non_blocking=True)
+                        o.record_stream(copy_stream)
+                        d2h += o.numel() * o.element_size()
+                pending = [outs]
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+        e1.record(torch.cuda.current_stream(dev))
+        barrier()
+        ms = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+        del pending
+        return dict(ms=ms, evals=reduce_ranks(float(evals), dist.ReduceOp.SUM if world > 1 else None), live=live_total,
+                    logs=logs, smc_iters=smc_iters, launches=lib.launches - launches0, h2d=h2d // steps,
+                    d2h=int(reduce_ranks(float(d2h), dist.ReduceOp.SUM if world > 1 else None)) // steps, summ=summ)
+
+    do_weak = a.scaling in ("weak", "both")
+    do_strong = a.scaling in ("strong", "both")
+    weak_job = Job(a.tiles_per_gpu * world, 1234) if do_weak else None
+    same = do_weak and do_strong and a.tiles_per_gpu * world == a.field_tiles
+    strong_job = weak_job if same else (Job(a.field_tiles, 1234) if do_strong else None)
+    main_job = weak_job if do_weak else strong_job
 
     # ---- warm-up
     for w in range(a.warmup):
-        mh = SingleComponentMH(iters, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"])
-        mh.event_log = []
-        one_run(tiles_dev, 100 + w, mh)
+        main_job.run(100 + w)
+        if strong_job is not None and strong_job is not main_job and w == 0:
+            strong_job.run(100)
     barrier()
 
-    # ---- device-resident timing: K steps
-    sampler_clock = ClockSampler(local_rank)
-    sampler_clock.start()
+    clock = ClockSampler(local_rank)
+    clock.start()
     time.sleep(0.3)
-    launches0 = lib.launches
-    evals = live_total = 0
-    mh_logs = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(torch.cuda.current_stream(dev))
-    iters_smc = []
-    for k in range(a.steps):
-        mh = SingleComponentMH(iters, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"])
-        mh.event_log = []
-        s = one_run(tiles_dev, 1000 + k, mh)
-        mh_logs.append(mh.event_log)
-        iters_smc.append(s.iter)
-    e1.record(torch.cuda.current_stream(dev))
-    barrier()
-    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = lib.launches - launches0
-    clocks = sampler_clock.stop()
-    for log in mh_logs:
-        live = sum(int(T if act is None else act.sum().item()) for (_, _, act, *_r) in log)
-        live_total += live
-        evals += live * N * (iters + 2) + T * N
-    evals_all = sum_over_ranks(float(evals))
-    value = evals_all / (elapsed_ms * 1e-3)
-    tiles_per_sec = a.gpus * T * a.steps / (elapsed_ms * 1e-3)
+    main = timed(main_job, a.steps, 1000, e2e=False)         # device-resident
+    main_e2e = timed(main_job, a.steps, 1000, e2e=True)      # pinned host tiles -> ... -> pinned host results
+    strong = None
+    if do_strong:
+        if strong_job is main_job:
+            s_dev, s_e2e = main, main_e2e
+        else:
+            s_dev = timed(strong_job, a.steps, 1000, e2e=False)
+            s_e2e = timed(strong_job, a.steps, 1000, e2e=True)
+        full = strong_job.summaries_global(s_dev["summ"]).float().contiguous()
+        digest = hashlib.sha256(full.cpu().numpy().tobytes()).hexdigest()[:16]
+        strong = {"field_tiles": strong_job.T, "value": s_dev["evals"] / (s_dev["ms"] * 1e-3), "unit": UNIT,
+                  "ms_per_step": s_dev["ms"] / a.steps, "tiles_per_sec": strong_job.T * a.steps / (s_dev["ms"] * 1e-3),
+                  "e2e": {"value": s_e2e["evals"] / (s_e2e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": s_e2e["ms"] / a.steps,
+                          "h2d_bytes_per_step": s_e2e["h2d"], "d2h_bytes_per_step": s_e2e["d2h"]},
+                  "smc_iters_per_step": s_dev["smc_iters"],
+                  "checksum": {"sha256_16": digest, "sum_logz": float(full[:, 0].double().sum()),
+                               "of": "per-tile summaries of the last step in global tile order "
+                                     "(log Z, ESS, temperature, acceptance, mean detected count, mean detected flux; "
+                                     "allstrata: log evidence, mean count, max count probability, log Z of the top count); "
+                                     "seeded by the global tile id, so identical for every number of GPUs"},
+                  "limit": "per-rank work shrinks with the GPU count while the slowest tile's serial chain of SMC "
+                           "iterations stays: the tail of launches with few live tiles underfills a GPU"}
+    clocks = clock.stop()
+
+    value = main["evals"] / (main["ms"] * 1e-3)
+    units_per_step = main_job.T * ns
+    tiles_per_sec = main_job.T * a.steps / (main["ms"] * 1e-3)
 
     # ---- roofline of the dominant kernel (mh_kernel), timed live with CUDA events per launch.
-    # Units one launch processes, per live particle: 1 full render (entry state) of D stars and
-    # num_iters sweeps that each evaluate 2 stars (the one removed and the one proposed) on the P pixels, plus
-    # P pixel terms per evaluation.  Per-unit figures are SURVEY.md 8(d)'s: 4 MUFU / 12 FP32 instr per
-    # (star, pixel) PSF evaluation of the M71 model, 2 MUFU / 7 FP32 instr per Normal pixel term.
-    mh_ms = sum(ev0.elapsed_time(ev1) for log in mh_logs for (ev0, ev1, *_r) in log)
-    n_launch = sum(len(log) for log in mh_logs)
+    # Units one launch processes, per live particle: 1 full render (entry state) of D stars and num_iters sweeps that
+    # each evaluate 2 stars (the one removed and the one proposed) on the P pixels, plus P pixel terms per evaluation.
+    # Per-unit figures are SURVEY.md 8(d)'s: M71 4 MUFU / 12 FP32 instr per (star, pixel) and 2 / 7 per Normal pixel term;
+    # Gaussian-PSF model 1 / 6 per (star, pixel) and 1 / 3 per Poisson pixel term.
+    c_psf, i_psf, c_pix, i_pix = (4, 12, 2, 7) if is_m71(a) else (1, 6, 1, 3)
+    mh_ms = sum(ev0.elapsed_time(ev1) for log in main["logs"] for (ev0, ev1, *_r) in log)
+    n_launch = sum(len(log) for log in main["logs"])
     P = TILE * TILE
     star_pixels = (1 * D + 2 * iters) * P   # entry render + two-star sweeps (no final refresh by default)
     pixel_terms = (iters + 1) * P
-    mufu_per_particle = 4 * star_pixels + 2 * pixel_terms
-    fp32_per_particle = 12 * star_pixels + 7 * pixel_terms
-    # what the kernel issues: separable Gaussians (2*(8+8) ex2 per star) + 2 MUFU per star-pixel for the wing +
-    # 1 for the star weight; four pixels share one rcp and one lg2 (0.5 per pixel); ~45 in the proposal step
-    exec_mufu_per_particle = (1 * D + 2 * iters) * (2 * 16 + 2 * P + 1) + pixel_terms // 2 + 45 * iters
-    live_particles = live_total * N
+    mufu_per_particle = c_psf * star_pixels + c_pix * pixel_terms
+    fp32_per_particle = i_psf * star_pixels + i_pix * pixel_terms
+    # what the kernel issues per (sweep, star): separable Gaussians (2 terms x (8 + 8) ex2; 1 term for the Gaussian
+    # model), and for the M71 wing 1 lg2 + 0.75 ex2 per star-pixel (a quarter of the ex2 run on the FMA pipe); four
+    # pixels share one rcp and one lg2 (Normal) or one lg2 per pixel (Poisson); ~45 in the proposal step
+    per_star = (2 * 16 + 1.75 * P) if is_m71(a) else 16
+    exec_mufu_per_particle = (1 * D + 2 * iters) * per_star + pixel_terms * (0.5 if is_m71(a) else 1.0) + 45 * iters
+    live_particles = main["live"] * N
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
+    except Exception:  # noqa: BLE001
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     sfu_peak = 148 * 16 * sm_max * 1e6 / 1e12          # TOP/s (MUFU results per second)
@@ -407,111 +648,97 @@ def run_own(a):
     hbm_gbs = live_particles * bytes_per_launch_particle / (mh_ms * 1e-3) / 1e9
     traffic = None
     try:  # DRAM bytes per particle-launch from the committed ncu --set full capture of this kernel
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_mh_kernel.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_mh_kernel.json")))
         traffic = prof["dram_bytes_per_particle"] * live_particles / max(1, n_launch)
-    except Exception:
+    except Exception:  # noqa: BLE001
         pass
-    roofline = {"kernel": "mh_kernel<M71,8,8,TPP=1> (smcdet_mh_mutate)", "bound": "sfu",
+    kname = "mh_kernel<M71,8,8,TPP=1>" if is_m71(a) else "mh_kernel<GAUSS,8,8,TPP=1>"
+    roofline = {"kernel": f"{kname} (smcdet_mh_mutate)", "bound": "sfu",
                 "achieved": achieved, "peak": sfu_peak, "unit": "TOP/s (MUFU)", "frac": achieved / sfu_peak,
                 "peak_source": f"derived: 148 SMs x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); "
                                "the path is SFU/FP32-bound, not HBM- or tensor-bound (SURVEY.md 8d)",
-                "definition": "algorithmic MUFU of the units a launch processes (SURVEY 8d: 4 per (star,pixel) PSF "
-                              "evaluation, 2 per pixel term; 1 full render + num_iters two-star sweeps per particle) / "
-                              "CUDA-event time of the launches.  It can exceed 1 because the kernel evaluates the two "
-                              "Gaussian PSF terms separably (about 2.5 MUFU per star-pixel issued): executed_frac is "
-                              "the MUFU actually issued / peak (ncu sm__inst_executed_pipe_xu agrees, profiles/)",
+                "definition": "algorithmic MUFU of the units a launch processes (SURVEY 8d per (star,pixel) PSF evaluation "
+                              "and per pixel term; 1 full render + num_iters two-star sweeps per particle) / CUDA-event "
+                              "time of the launches.  It can exceed 1 because the kernel evaluates the Gaussian PSF terms "
+                              "separably and part of the wing's exponentials on the FMA pipe: executed_frac is the MUFU "
+                              "actually issued / peak (ncu sm__inst_executed_pipe_xu agrees, profiles/)",
                 "executed_frac": live_particles * exec_mufu_per_particle / (mh_ms * 1e-3) / 1e12 / sfu_peak,
                 "fp32_achieved_tinstr": live_particles * fp32_per_particle / (mh_ms * 1e-3) / 1e12,
                 "fp32_peak_tinstr": fp32_peak,
                 "launches": n_launch, "avg_launch_ms": mh_ms / max(1, n_launch),
-                "share_of_step": mh_ms / elapsed_ms, "traffic": traffic,
+                "share_of_step": mh_ms / main["ms"], "traffic": traffic,
+                "traffic_source": "dram__bytes_read+write per particle of the committed ncu --set full capture "
+                                  "(profiles/r02_ncu_mh_kernel.json) x the live particles of this run",
                 "algorithmic_bytes_per_launch": live_particles * bytes_per_launch_particle / max(1, n_launch),
                 "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "frac": hbm_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}}
 
     # ---- the standalone likelihood kernel on the same field (dense: D stars x P pixels per evaluation)
-    counts0, locs0, fluxes0 = prior._sample_grid(T, 1, None, True, N, seed=7)
+    Tl = min(main_job.T_local, 800)
+    prior_d = make_objects(argparse.Namespace(**dict(vars(a), workload="m71synthetic" if strata else a.workload)))[1]
+    counts0, locs0, fluxes0 = prior_d._sample_grid(Tl, 1, None, True, N, seed=7)
+    tiles_ll = main_job.field[:Tl].view(Tl, 1, TILE, TILE)
     for _ in range(3):
-        model.loglikelihood(tiles_dev, locs0, fluxes0)
+        model.loglikelihood(tiles_ll, locs0, fluxes0)
     torch.cuda.synchronize(dev)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
     for x0, x1 in evs:
         x0.record(torch.cuda.current_stream(dev))
-        model.loglikelihood(tiles_dev, locs0, fluxes0)
+        model.loglikelihood(tiles_ll, locs0, fluxes0)
         x1.record(torch.cuda.current_stream(dev))
     torch.cuda.synchronize(dev)
     ll_ms = sorted(x0.elapsed_time(x1) for x0, x1 in evs)[len(evs) // 2]
-    ll_rate = T * N / (ll_ms * 1e-3)
-    roofline_loglik = {"kernel": "loglik_kernel<M71,8,8,TPP=1> (smcdet_loglik)", "bound": "sfu",
+    ll_rate = Tl * N / (ll_ms * 1e-3)
+    ll_mufu = c_psf * D * P + c_pix * P
+    roofline_loglik = {"kernel": f"loglik_kernel<{'M71' if is_m71(a) else 'GAUSS'},8,8,TPP=1> (smcdet_loglik)", "bound": "sfu",
                        "evals_per_s": ll_rate, "launch_ms": ll_ms,
-                       "achieved": ll_rate * (4 * D * P + 2 * P) / 1e12, "peak": sfu_peak, "unit": "TOP/s (MUFU)",
-                       "frac": ll_rate * (4 * D * P + 2 * P) / 1e12 / sfu_peak,
-                       "executed_frac": ll_rate * (D * (2 * 16 + 2 * P + 1) + P // 2) / 1e12 / sfu_peak,
+                       "achieved": ll_rate * ll_mufu / 1e12, "peak": sfu_peak, "unit": "TOP/s (MUFU)",
+                       "frac": ll_rate * ll_mufu / 1e12 / sfu_peak,
+                       "executed_frac": ll_rate * (D * per_star + P * (0.5 if is_m71(a) else 1.0)) / 1e12 / sfu_peak,
                        "hbm_gbs": ll_rate * (12 * D + 8) / 1e9}
     del counts0, locs0, fluxes0
-
-    # ---- end to end through the public API: pinned host tiles -> H2D -> run -> results D2H into pinned buffers.
-    #      Per-tile summaries are all-gathered to every rank; each rank reads back its own posterior catalogs.
-    #      The read-back of step k runs on a copy stream and overlaps the sampling of step k+1 (two pinned
-    #      buffer sets); everything is complete before the closing event.
-    copy_stream = torch.cuda.Stream(device=dev)
-    shapes = [((T * world, 4), torch.float32), ((T, N), torch.int16), ((T, N, D, 2), torch.float32), ((T, N, D), torch.float32)]
-    host_out = [[torch.empty(sh, dtype=dt, pin_memory=True) for sh, dt in shapes] for _ in range(2)]  # allocated once
-    pending = []
-    barrier()
-    e0.record(torch.cuda.current_stream(dev))
-    h2d = d2h = 0
-    e2e_evals = 0
-    e2e_logs = []
-    for k in range(a.steps):
-        mh = SingleComponentMH(iters, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"])
-        mh.event_log = []
-        tiles = tiles_host.to(dev, non_blocking=True)
-        h2d += tiles_host.numel() * 4
-        s = one_run(tiles, 1000 + k, mh)
-        summ = torch.stack([s.log_normalizing_constant, s.ess, s.posterior_mean_count(s.pruned_counts.float()),
-                            s.posterior_mean_total_flux(s.pruned_fluxes)], -1).view(T, 4)
-        if world > 1:
-            summ = gather_tiles(summ.contiguous(), T * world)
-        outs = [summ, s.pruned_counts.view(T, N).to(torch.int16), s.pruned_locs.view(T, N, D, 2),
-                s.pruned_fluxes.view(T, N, D)]
-        slot = k % 2
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready)
-            for hbuf, o in zip(host_out[slot], outs):
-                hbuf.copy_(o, non_blocking=True)
-                o.record_stream(copy_stream)
-                d2h += o.numel() * o.element_size()
-        pending.append(outs)
-        if len(pending) > 1:
-            pending.pop(0)
-        e2e_logs.append(mh.event_log)
-    torch.cuda.current_stream(dev).wait_stream(copy_stream)
-    e1.record(torch.cuda.current_stream(dev))
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    for log in e2e_logs:
-        live = sum(int(T if act is None else act.sum().item()) for (_, _, act, *_r) in log)
-        e2e_evals += live * N * (iters + 2) + T * N
-    e2e_value = sum_over_ranks(float(e2e_evals)) / (e2e_ms * 1e-3)
 
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu_base, _, _ = cpu_measure(a, target_seconds=12.0, steps=1, warmup=0)
+        try:
+            real = reference_measure(a, target_seconds=12.0)
+        except Exception as exc:  # noqa: BLE001
+            real = {"kind": "reference", "unavailable": repr(exc)[:200]}
+        cpu_base["also"] = [real] if real else []
 
     if rank == 0:
+        e2e_value = main_e2e["evals"] / (main_e2e["ms"] * 1e-3)
+        per_eval = (iters + 2)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": main["ms"] / a.steps, "higher_is_better": True,
+                "scaling": "weak" if do_weak else "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(a), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
-                        "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": e2e_ms / a.steps,
-                        "tiles_per_sec": a.gpus * T * a.steps / (e2e_ms * 1e-3)},
-                "gpu_launches": launches, "kernel_calls": dict(lib.calls), "roofline": roofline,
-                "roofline_loglik": roofline_loglik,
-                "cpu_baseline": cpu_base, "tiles_per_sec": tiles_per_sec, "smc_iters_per_step": iters_smc,
-                "mean_smc_iters_per_tile": live_total / (T * a.steps)}
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main_e2e["h2d"],
+                        "d2h_bytes_per_step": main_e2e["d2h"], "ms_per_step": main_e2e["ms"] / a.steps,
+                        "tiles_per_sec": main_job.T * a.steps / (main_e2e["ms"] * 1e-3),
+                        "path": "pinned host tiles -> H2D -> sampler -> NCCL gather of the weighted catalogs onto rank 0 -> "
+                                "Aggregate finish (resample + prune) -> pruned catalogs + summaries D2H into pinned buffers"
+                                if not strata else
+                                "pinned host tiles -> H2D -> count-stratified samplers on every rank -> all-gather of the "
+                                "per-stratum evidences -> count posterior per tile -> D2H"},
+                "gpu_launches": main["launches"] + main_e2e["launches"], "kernel_calls": dict(lib.calls),
+                "launches_per_step": main["launches"] / a.steps,
+                "roofline": roofline, "roofline_loglik": roofline_loglik, "cpu_baseline": cpu_base,
+                "tiles_per_sec": tiles_per_sec, "smc_iters_per_step": main["smc_iters"],
+                "mean_smc_iters_per_segment": main["live"] * (world if not strata else 1) / (units_per_step * a.steps)
+                if not strata else None,
+                # the same rate in other units: `value` counts N*(iters+2) evaluations per live tile-iteration as the
+                # reference performs them; the kernel does iters+1 pixel sums and two-star incremental updates instead
+                "proposals_per_s": value * iters / per_eval,
+                "dense_equiv": {"definition": "evaluations/s a kernel that re-rendered all D stars per evaluation (as the "
+                                              "reference does; BASELINE.md section 3 SFU peak: 1.73e9 for M71 D = 10) would "
+                                              "need for the same step time", "value": value,
+                                "dense_sfu_peak_evals_per_s": sfu_peak * 1e12 / ll_mufu,
+                                "note": "value exceeds the dense SFU peak because a sweep re-renders 2 stars, not D"},
+                "strong": strong}
+        if strata:
+            line["strata_per_sec"] = units_per_step * a.steps / (main["ms"] * 1e-3)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMCDET_ABI_VERSION 5
+#define SMCDET_ABI_VERSION 6
 
 enum {
     SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
@@ -46,9 +46,11 @@ enum { SMCDET_RESAMPLE_MULTINOMIAL = 0, SMCDET_RESAMPLE_SYSTEMATIC = 1 };
 
 /* status bits written (OR-ed) into the optional device status word of smcdet_mh_mutate */
 enum {
-    SMCDET_STATUS_OUT_OF_BOX = 1 /* a location or flux lies outside the proposal box on entry: the
-                                    reference would fail `assert (value >= lb).all() and (value <= ub).all()`
-                                    (smcdet/distributions.py:51) */
+    SMCDET_STATUS_OUT_OF_BOX = 1, /* a location or flux lies outside the proposal box on entry: the
+                                     reference would fail `assert (value >= lb).all() and (value <= ub).all()`
+                                     (smcdet/distributions.py:51) */
+    SMCDET_STATUS_BAD_TAPE = 2    /* an injected component index lies outside [0, D): it was clamped
+                                     (torch.multinomial over D categories cannot produce one, kernel.py:35-44) */
 };
 
 /* ImageModel / M71ImageModel constructor state: smcdet/images.py:7-23, :106-135 */
@@ -95,7 +97,29 @@ typedef struct smcdet_mh_params {
                                1: uniform over the catalog's live stars j < count, and a catalog without stars
                                is left as it is -- for populations whose counts are below D (count strata),
                                where moving an empty slot would create a star the prior never sees */
+    int32_t acc_as_count;   /* 0: acc_rate [T] receives the acceptance rate of the last sweep (kernel.py:130);
+                               1: the accept COUNT of the last sweep is ADDED to acc_rate [T] (the caller keeps it
+                               zero-filled and divides by N: smcdet_temper_update does both through
+                               smcdet_loop_state), which saves two small launches per call */
+    int32_t live_tiles_hint; /* > 0: how many tiles have active != 0, when the caller knows: the threads-per-particle
+                                decomposition is then chosen for that many tiles instead of T (results are
+                                bit-identical for every decomposition) */
+    const int32_t *tile_of_segment; /* [T] device pointer, nullable.  Generic segments: "tile" t of
+                               the particle arrays is segment t of an image tiles[tile_of_segment[t]] -- e.g. the
+                               (tile, count) strata of count-stratified SMC, which share their tile's pixels
+                               (manuscript.tex:312-356).  NULL: segment t is tile t */
 } smcdet_mh_params;
+
+/* Optional device-side loop bookkeeping of smcdet_temper_update, for runs in which finished tiles are frozen
+ * (each tile stops at temperature 1, as in the reference's per-tile driver loop, experiments/m71/run_smc.py:113-124):
+ * the loop test `torch.any(temperature < 1)` of smcdet/sampler.py:230 and the masking of finished tiles then need no
+ * host round trip and no extra launches.  Any member may be NULL. */
+typedef struct smcdet_loop_state {
+    int32_t *active_next; /* [T] out: 1 where the tile's new temperature is below 1, else 0 (0 for skipped tiles)   */
+    int32_t *live_count;  /* [1] in/out: incremented once per tile whose new temperature is below 1                 */
+    float *acc_count;     /* [T] in/out: accept counts left by smcdet_mh_mutate(acc_as_count = 1); reset to 0       */
+    float *acc_rate;      /* [T] out: acc_count / N for the tiles this call updates (kernel.py:130)                 */
+} smcdet_loop_state;
 
 /* Injected draws for smcdet_mh_mutate (parity testing).  Entries are the draws the
  * reference actually consumes per iteration (kernel.py:44, :47-61, :115):
@@ -119,12 +143,24 @@ typedef struct smcdet_mh_trace {
 int smcdet_version(void);
 const char *smcdet_last_error_string(void);
 
+/* Diagnostic: force the threads-per-particle decomposition (1, 2, 4, ... lanes per particle) of the CALLING
+ * THREAD's next smcdet_loglik / smcdet_mh_mutate / smcdet_mala_mutate launches; 0 restores the automatic choice.
+ * Results do not depend on the decomposition (one summation tree for all of them); the tests use this to show it. */
+int smcdet_debug_force_tpp(int tpp);
+
 /* ImageModel.loglikelihood / M71ImageModel.loglikelihood
  * (smcdet/images.py:85-102, :159-175): fused render + per-pixel log-density + reduction.
  * loglik [T,N]. */
 int smcdet_loglik(const smcdet_model_params *model, const float *tiles, const float *locs,
                   const float *fluxes, float *loglik, int T, int N, int D, int h, int w,
                   void *stream);
+
+/* The same over generic segments: particle arrays [S, N, ...] whose segment s is evaluated on the image
+ * tiles[tile_of_segment[s]] (tile_of_segment [S] int32 on the device) -- the (tile, count) strata of
+ * count-stratified SMC share their tile's pixels (manuscript.tex:312-356; stratified layout prior.py:47-54). */
+int smcdet_loglik_segments(const smcdet_model_params *model, const float *tiles,
+                           const int32_t *tile_of_segment, const float *locs, const float *fluxes,
+                           float *loglik, int S, int N, int D, int h, int w, void *stream);
 
 /* ImageModel.psf (smcdet/images.py:28-76): dense PSF stack psf [T,h,w,N,D]. */
 int smcdet_psf(const smcdet_model_params *model, const float *locs, float *psf, int T, int N,
@@ -163,10 +199,11 @@ int smcdet_prior_sample(const smcdet_prior_params *prior, const float *u_locs,
  * With do_temper = 0 the given tau / tau_prev are used as they are.
  * tau, tau_prev, ess, logz [T]; wlog, weights [T,N]; funcalls [T] (nullable) counts objective
  * evaluations; active [T] (nullable): tiles whose entry is 0 are skipped and none of their outputs
- * is written. */
+ * is written (except loop->active_next); loop (nullable): see smcdet_loop_state. */
 int smcdet_temper_update(const float *loglik, float *tau, float *tau_prev, float ess_threshold,
                          int do_temper, float *wlog, float *weights, float *ess, float *logz,
-                         int32_t *funcalls, const int32_t *active, int T, int N, void *stream);
+                         int32_t *funcalls, const int32_t *active, const smcdet_loop_state *loop,
+                         int T, int N, void *stream);
 
 /* SMCsampler.resample, index part (smcdet/sampler.py:127-149): inclusive CDF of the weights in
  * double precision, then for every draw the first k with cdf[k] >= u, clamped to [0,N-1].

@@ -465,6 +465,34 @@ CASES = dict(loglik=case_loglik, prior_sample=case_prior_sample, truncnorm=case_
 
 
 
+def case_smc_stats_d10():
+    """Monte-Carlo-error-sized acceptance band for the end-to-end test at the benchmark's catalog size: 20 unmodified
+    reference runs (own RNG) of one 8x8 M71 tile with D = 10 stars per catalog, N = 2000, 25 MH sweeps; per run
+    (logZ, posterior mean detected count, posterior mean detected flux, posterior mean total flux, SMC iterations).
+    The GPU test compares its own mean over 20 seeds with this mean, within 3 combined standard errors."""
+    tile, nside, N, mh_iters, D = 8, 1, 2000, 25, 10
+    im, pr, meta = m71_objects(tile, D, 4)
+    torch.manual_seed(77)
+    tiles = synth_tiles(im, 4, nside, tile, 4, "m71")
+    image = tiles[0, 0].contiguous()
+    rows = []
+    for seed in range(int(os.environ.get("SMC_STATS_RUNS", "20"))):
+        torch.manual_seed(5000 + seed)
+        mh = SingleComponentMH(mh_iters, 0.1, 2.5, pr.flux_lower, pr.flux_upper)
+        s = SMCsampler(image, tile, pr, im, mh, N, 0.5, "multinomial", M71_DETECTION, 100, print_every=1000)
+        s.run()
+        rows.append([float(s.log_normalizing_constant), float(s.posterior_mean_count(s.pruned_counts.float())),
+                     float(s.posterior_mean_total_flux(s.pruned_fluxes)), float(s.posterior_mean_total_flux(s.fluxes)),
+                     float(s.iter)])
+        print("seed", seed, rows[-1], flush=True)
+    meta.update(nside=nside, N=N, mh_iters=mh_iters, flux_threshold=M71_DETECTION, ess_prop=0.5,
+                columns=["logZ", "mean_pruned_count", "mean_pruned_flux", "mean_total_flux", "smc_iters"])
+    save("smc_stats_m71_d10", meta, image=image, stats=np.array(rows))
+
+
+CASES["smc_stats_d10"] = case_smc_stats_d10
+
+
 def case_exact_d1():
     """A one-star problem whose posterior can be integrated numerically: exact log evidence and posterior
     moments from a fine 3-D grid of the oracle's float64 log-likelihood, plus what unmodified reference runs

@@ -2,13 +2,14 @@
 
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 MODEL_GAUSS_POISSON, MODEL_M71_NORMAL = 0, 1
 COUNT_DISCRETE_UNIFORM, COUNT_POISSON, COUNT_NONE = 0, 1, 2
 FLUX_PARETO, FLUX_TRUNCATED_PARETO, FLUX_NORMAL = 0, 1, 2
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 STATUS_OUT_OF_BOX = 1
+STATUS_BAD_TAPE = 2
 
 E_INVALID, E_UNSUPPORTED, E_TOO_LARGE = -1, -2, -3
 
@@ -46,7 +47,15 @@ class MHParams(C.Structure):
         ("locs_min", C.c_float * 2), ("locs_max", C.c_float * 2),
         ("refresh_loglik", C.c_int32),
         ("live_only", C.c_int32),
+        ("acc_as_count", C.c_int32),
+        ("live_tiles_hint", C.c_int32),
+        ("tile_of_segment", C.c_void_p),
     ]
+
+
+class LoopState(C.Structure):
+    _fields_ = [("active_next", C.c_void_p), ("live_count", C.c_void_p), ("acc_count", C.c_void_p),
+                ("acc_rate", C.c_void_p)]
 
 
 class DrawTape(C.Structure):
@@ -65,12 +74,13 @@ PROTOTYPES = {
     "smcdet_version": (C.c_int, []),
     "smcdet_last_error_string": (C.c_char_p, []),
     "smcdet_loglik": (C.c_int, [C.POINTER(ModelParams), _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "smcdet_loglik_segments": (C.c_int, [C.POINTER(ModelParams), _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "smcdet_psf": (C.c_int, [C.POINTER(ModelParams), _P, _P, _I, _I, _I, _I, _I, _P]),
     "smcdet_psf_radial": (C.c_int, [C.POINTER(ModelParams), _I, _P, _P, C.c_longlong, _P]),
     "smcdet_render": (C.c_int, [C.POINTER(ModelParams), _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "smcdet_prior_logprob": (C.c_int, [C.POINTER(PriorParams), _P, _P, _P, _P, _I, _I, _I, _P]),
     "smcdet_prior_sample": (C.c_int, [C.POINTER(PriorParams), _P, _P, C.c_uint64, _P, _P, _P, _P, _I, _I, _I, _P]),
-    "smcdet_temper_update": (C.c_int, [_P, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "smcdet_temper_update": (C.c_int, [_P, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P, _P, C.POINTER(LoopState), _I, _I, _P]),
     "smcdet_resample": (C.c_int, [_I, _P, _P, C.c_uint64, _P, _P, _P, _P, _I, _I, _P]),
     "smcdet_gather": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "smcdet_mh_mutate": (C.c_int, [C.POINTER(ModelParams), C.POINTER(PriorParams), C.POINTER(MHParams),
@@ -86,10 +96,6 @@ PROTOTYPES = {
                           + [_P] * 10 + [C.POINTER(DrawTape), C.POINTER(MHTrace), C.c_uint64, C.c_uint64, _P, _P]
                           + [_I] * 5 + [_P]),
     "smcdet_match_catalogs": (C.c_int, [_P] * 8 + [C.c_float, C.c_float] + [_P] * 5 + [_I] * 6 + [_P]),
-}
-
-# exported for tests only; not part of include/smcdet_b200.h
-DEBUG_PROTOTYPES = {
     "smcdet_debug_force_tpp": (C.c_int, [_I]),
 }
 
@@ -100,9 +106,4 @@ def bind(cdll):
         fn = getattr(cdll, name)
         fn.restype = res
         fn.argtypes = args
-    for name, (res, args) in DEBUG_PROTOTYPES.items():
-        if hasattr(cdll, name):
-            fn = getattr(cdll, name)
-            fn.restype = res
-            fn.argtypes = args
     return cdll

@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
 
 # kernels launched by one call of each entry point (smcdet_mh_mutate: zero + mh + divide)
 KERNELS_PER_CALL = {
-    "smcdet_loglik": 1, "smcdet_psf": 1, "smcdet_psf_radial": 1, "smcdet_render": 1, "smcdet_prior_logprob": 1, "smcdet_prior_sample": 1,
+    "smcdet_loglik": 1, "smcdet_loglik_segments": 1, "smcdet_psf": 1, "smcdet_psf_radial": 1, "smcdet_render": 1, "smcdet_prior_logprob": 1, "smcdet_prior_sample": 1,
     "smcdet_temper_update": 1, "smcdet_resample": 1, "smcdet_gather": 1, "smcdet_mh_mutate": 3, "smcdet_mala_mutate": 3, "smcdet_prune": 1,
     "smcdet_match_catalogs": 1, "smcdet_agg_join": 1, "smcdet_agg_unjoin": 1, "smcdet_agg_mutate": 3,
 }
@@ -65,6 +65,10 @@ class _CountingLib(object):
             self.calls[name] = self.calls.get(name, 0) + 1
             return fn(*args)
         return call
+
+    def adjust(self, n):
+        """Correct the launch count of the last call (e.g. smcdet_mh_mutate with acc_as_count launches 1 kernel, not 3)."""
+        self.launches += n
 
     def __getattr__(self, name):
         return getattr(self._cdll, name)

@@ -49,9 +49,10 @@ class Aggregate(object):
         self._merge_tree = merge
         self.num_aggregation_levels = (2 * torch.tensor(float(self.numH)).log2()).int().item() if merge else 0
 
-        self.log_normalizing_constant = [
-            [log_normalizing_constant[h, w].tolist() for w in range(self.numW)] for h in range(self.numH)
-        ]
+        # nested lists as in the reference (aggregate.py:43-45), from ONE device-to-host copy
+        lz = log_normalizing_constant.detach().cpu().tolist() if isinstance(log_normalizing_constant, torch.Tensor) \
+            else log_normalizing_constant
+        self.log_normalizing_constant = [[lz[h][w] for w in range(self.numW)] for h in range(self.numH)]
         self.flux_detection_threshold = flux_detection_threshold
         self.num_catalogs = self.weights.shape[-1]
         self.num_catalogs_per_count = [[None for _ in range(self.numW)] for _ in range(self.numH)]
@@ -81,7 +82,7 @@ class Aggregate(object):
         dev = w.device
         method = A.RESAMPLE_MULTINOMIAL if self.resample_method == "multinomial" else A.RESAMPLE_SYSTEMATIC
         # smcdet_resample draws as many indices as there are weights: pad the weights with zeros up to a multiple
-        # of `num`; every (width / num)-th point of a systematic grid of `width` points is a grid of `num` points
+        # of `num` and keep every (width / num)-th draw
         width = num * ((n + num - 1) // num)
         if width != n:
             if u is not None:
@@ -92,6 +93,10 @@ class Aggregate(object):
         idx = torch.empty(T, width, device=dev, dtype=torch.int64)
         cdf = torch.empty(T, width, device=dev, dtype=torch.float64)
         uu = None if u is None else u.to(device=dev, dtype=torch.float64).contiguous()
+        if width != n and method == A.RESAMPLE_SYSTEMATIC:
+            # the points i = j * s (s = width / num) of the grid (i + u) / width form the systematic grid (j + v) / num
+            # exactly when u = s * v with v uniform on [0, 1): inject that offset (u in [0, 1) would bias the draw)
+            uu = (width // num) * torch.rand(T, dtype=torch.float64).to(dev)
         L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(), None, None,
                                         L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64), T, width, L.stream_for(w)))
         if width != n:
@@ -173,7 +178,7 @@ class Aggregate(object):
         wlog, weights = torch.empty(T, n, device=dev), torch.empty(T, n, device=dev)
         ess = torch.empty(T, device=dev)
         L.check(L.lib().smcdet_temper_update(L.ptr(lld), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold_prop * n), 1,
-                                             L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz), None, None, T, n,
+                                             L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz), None, None, None, T, n,
                                              L.stream_for(lld)))
         self.temperature, self.temperature_prev = tau.view(self.numH, self.numW), tau_prev.view(self.numH, self.numW)
         self.weights = self.weights_intracount = weights.view(self.numH, self.numW, n)
@@ -274,7 +279,7 @@ class Aggregate(object):
         wlog, weights, ess = torch.empty(T, n, device=dev), torch.empty(T, n, device=dev), torch.empty(T, device=dev)
         L.check(L.lib().smcdet_temper_update(L.ptr(lld), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold_prop * n),
                                              int(do_temper), L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz), None, None,
-                                             T, n, L.stream_for(lld)))
+                                             None, T, n, L.stream_for(lld)))
         return tau, tau_prev, weights, logz
 
     def temper(self):

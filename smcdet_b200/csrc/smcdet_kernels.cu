@@ -59,18 +59,40 @@ int launch_status(const char* what) {
 constexpr int kBT = SMC_KBT;    // threads per block of the particle kernels
 constexpr int kMaxStars = 64;   // D limit (shared-memory staging)
 
-int g_num_sms = 0;
+// SM count of the calling thread's current device (cached per device ordinal; 148 on a B200)
 int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_num_sms = n;
-        else
-            g_num_sms = 148;
-    }
-    return g_num_sms;
+    constexpr int kMaxDev = 64;
+    static int cache[kMaxDev] = {0};  // benign race: every writer stores the same value
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 148;
+    if (cache[dev] == 0)
+        cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    return cache[dev];
 }
+
+// Makes the device that owns `ptr` current for the duration of a call and restores the previous one: launches go
+// to the device of the caller's buffers whatever device the calling thread had selected.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const void* ptr) {
+#ifndef SMC_HOSTSIM
+        cudaPointerAttributes at;
+        int cur = 0;
+        if (ptr != nullptr && cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+            cudaGetDevice(&cur) == cudaSuccess && cur != at.device) {
+            if (cudaSetDevice(at.device) == cudaSuccess) prev = cur;
+        }
+        (void)cudaGetLastError();  // a host pointer makes cudaPointerGetAttributes leave an error behind on old drivers
+#else
+        (void)ptr;
+#endif
+    }
+    ~DeviceGuard() {
+#ifndef SMC_HOSTSIM
+        if (prev >= 0) cudaSetDevice(prev);
+#endif
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // helpers
@@ -156,7 +178,8 @@ template <int MODEL, int H, int W, int TPP>
 __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float* __restrict__ tiles,
                                                      const float* __restrict__ locs,
                                                      const float* __restrict__ fluxes, float* __restrict__ out,
-                                                     int N, int D, int blocks_per_tile) {
+                                                     const int32_t* __restrict__ tile_map, int N, int D,
+                                                     int blocks_per_tile) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
     float* s_tile = smem;
@@ -167,7 +190,8 @@ __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float
     const int n0 = (blockIdx.x - t * blocks_per_tile) * PB;
     const int n_here = min(PB, N - n0);
     const size_t pbase = (size_t)t * N + n0;
-    stage_block<MODEL, HW, PB>(tiles + (size_t)t * HW, locs + pbase * 2 * D, fluxes + pbase * D, n_here, D, s_tile,
+    const int ti = tile_map != nullptr ? tile_map[t] : t;  // the segment's image (count strata share their tile's)
+    stage_block<MODEL, HW, PB>(tiles + (size_t)ti * HW, locs + pbase * 2 * D, fluxes + pbase * D, n_here, D, s_tile,
                                s_lgam, s_star);
     __syncthreads();
 
@@ -186,13 +210,14 @@ __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float
 __global__ void __launch_bounds__(kBT) loglik_generic_kernel(const ModelK m, const float* __restrict__ tiles,
                                                              const float* __restrict__ locs,
                                                              const float* __restrict__ fluxes,
-                                                             float* __restrict__ out, int T, int N, int D, int h,
-                                                             int w) {
+                                                             float* __restrict__ out,
+                                                             const int32_t* __restrict__ tile_map, int T, int N, int D,
+                                                             int h, int w) {
     const int lane = threadIdx.x & 31;
     const size_t warp = (size_t)blockIdx.x * (kBT / 32) + (threadIdx.x >> 5);
     if (warp >= (size_t)T * N) return;
     const int t = (int)(warp / N);
-    const float* tile = tiles + (size_t)t * h * w;
+    const float* tile = tiles + (size_t)(tile_map != nullptr ? tile_map[t] : t) * h * w;
     const float* l = locs + warp * 2 * D;
     const float* f = fluxes + warp * D;
     float acc = 0.0f;
@@ -385,11 +410,15 @@ __global__ void __launch_bounds__(kTB) temper_update_kernel(const float* __restr
                                                             int do_temper, float* __restrict__ wlog,
                                                             float* __restrict__ weights, float* __restrict__ ess,
                                                             float* __restrict__ logz, int32_t* __restrict__ funcalls,
-                                                            const int32_t* __restrict__ active, int N) {
+                                                            const int32_t* __restrict__ active,
+                                                            const smcdet_loop_state loop, int N) {
     SMC_SHARED double s_red[2 * (kTB / 32)];
     SMC_SHARED float s_redf[kTB / 32];
     const int t = blockIdx.x;
-    if (active != nullptr && active[t] == 0) return;
+    if (active != nullptr && active[t] == 0) {
+        if (threadIdx.x == 0 && loop.active_next != nullptr) loop.active_next[t] = 0;
+        return;
+    }
     const float* ll = loglik + (size_t)t * N;
 
     float tau_old, tau_new;
@@ -461,6 +490,14 @@ __global__ void __launch_bounds__(kTB) temper_update_kernel(const float* __restr
     if (threadIdx.x == 0) {
         ess[t] = (float)(1.0 / s2);
         logz[t] = logz[t] + m + logf(sf / (float)N);
+        // loop bookkeeping of a freeze_finished run (the reference's loop test, sampler.py:230, evaluated here)
+        const int live = tau_new < 1.0f ? 1 : 0;
+        if (loop.active_next != nullptr) loop.active_next[t] = live;
+        if (loop.live_count != nullptr && live) atomicAdd(loop.live_count, 1);
+        if (loop.acc_count != nullptr && loop.acc_rate != nullptr) {
+            loop.acc_rate[t] = loop.acc_count[t] / (float)N;  // accept.float().mean(-1), kernel.py:130
+            loop.acc_count[t] = 0.0f;
+        }
     }
 }
 
@@ -664,6 +701,12 @@ __device__ __noinline__ float truncnormal_logq(float mean, float sigma, float in
     return truncnormal_logpdf(q, mean, sigma, x);
 }
 
+// Philox4x32-10 block of MH sweep `it` of one particle (counter: particle, global tile id, SMC iteration and sweep)
+__device__ __forceinline__ Philox4 mh_draw_block(uint32_t pidx, uint64_t tile_key, uint64_t offset, int it, uint64_t seed) {
+    return philox4x32_10(pidx, (uint32_t)tile_key, (uint32_t)(offset << 16) ^ (uint32_t)it, kStreamMHDraws, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
 struct MHArgs {
     ModelK m;
     PriorK pk;
@@ -689,6 +732,7 @@ struct MHArgs {
     uint64_t seed, offset;
     const int64_t* tile_ids;
     const int32_t* active;
+    const int32_t* tile_map;
     int32_t* status;
     int T, N, D, blocks_per_tile;
 };
@@ -711,7 +755,8 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     const int n0 = (blockIdx.x - t * a.blocks_per_tile) * PB;
     const int n_here = min(PB, N - n0);
     const size_t pbase = (size_t)t * N + n0;
-    stage_block<MODEL, HW, PB>(a.tiles + (size_t)t * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
+    const int ti = a.tile_map != nullptr ? a.tile_map[t] : t;  // the segment's image (count strata share their tile's)
+    stage_block<MODEL, HW, PB>(a.tiles + (size_t)ti * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
                                s_tile, s_lgam, s_star);
     __syncthreads();
 
@@ -758,7 +803,10 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     // box mass underflows; it always takes the reference's two-erf arithmetic so that regime behaves alike)
     const bool wide_l = !MALA && fminf(a.mh.locs_max[0] - a.mh.locs_min[0], a.mh.locs_max[1] - a.mh.locs_min[1]) >= 12.0f * sl;
     const bool wide_f = !MALA && (a.mh.fluxes_max - a.mh.fluxes_min) >= 12.0f * sf;
-    Philox4 rc = {{0u, 0u, 0u, 0u}};
+    // Philox block of the coming sweep: generated inside the star loop of the previous pass (pure integer work that
+    // fills issue slots of that MUFU-bound stretch), again at the top of a sweep only if that loop did not run
+    Philox4 nxt = {{0u, 0u, 0u, 0u}};
+    int nxt_it = -2;
     int last_acc = 0;
     float ll = 0.0f, cached = 0.0f;
     float2 acc[PPT / 2];
@@ -776,33 +824,37 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         bool frozen_slot = false;
         float u0 = 0.5f, u1 = 0.5f, uf = 0.5f, ua = 0.5f;
         float l0 = 0.f, l1 = 0.f, f = 0.f, pl0 = 0.f, pl1 = 0.f, pf = 0.f, lq = 0.f;
-        const size_t e = ((size_t)max(it, 0) * a.T + t) * N + (n0 + pi);
         if (!full) {
             // ---- draws: component, 2 location uniforms, flux uniform, accept uniform
             if (a.tape_comp != nullptr) {
                 if (valid) {
+                    const size_t e = ((size_t)it * a.T + t) * N + (n0 + pi);
                     k = a.tape_comp[e];
+                    // a component outside the catalog would index past the staged stars: flagged, and clamped
+                    if (k < 0 || k >= D) {
+                        if (a.status != nullptr) atomicOr(a.status, SMCDET_STATUS_BAD_TAPE);
+                        k = min(max(k, 0), D - 1);
+                    }
                     u0 = a.tape_u_loc[2 * e]; u1 = a.tape_u_loc[2 * e + 1];
                     uf = a.tape_u_flux[e]; ua = a.tape_u_acc[e];
                 }
             } else {
-                const uint32_t c2 = (uint32_t)(a.offset << 16) ^ (uint32_t)it;
-                const Philox4 r = philox4x32_10(pidx, (uint32_t)tile_key, c2, kStreamMHDraws, (uint32_t)a.seed,
-                                                (uint32_t)(a.seed >> 32));
-                if ((it & 3) == 0)  // one Philox call yields the components of four iterations
-                    rc = philox4x32_10(pidx, (uint32_t)tile_key, (uint32_t)(a.offset << 16) ^ (uint32_t)(it >> 2),
-                                       kStreamMHComp, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]); ua = u01_f(r.v[3]);
-                const int sel = it & 3;
-                const uint32_t cw = sel == 0 ? rc.v[0] : (sel == 1 ? rc.v[1] : (sel == 2 ? rc.v[2] : rc.v[3]));
+                if (nxt_it != it) nxt = mh_draw_block(pidx, tile_key, a.offset, it, a.seed);
+                // one Philox4x32-10 block per sweep: the high 24 bits of its words are the four uniforms, their low
+                // bytes together the 32 random bits that pick the component
+                u0 = u01_f(nxt.v[0]); u1 = u01_f(nxt.v[1]); uf = u01_f(nxt.v[2]); ua = u01_f(nxt.v[3]);
+                const uint32_t cw = (nxt.v[0] & 0xffu) | ((nxt.v[1] & 0xffu) << 8) | ((nxt.v[2] & 0xffu) << 16) | (nxt.v[3] << 24);
                 k = (int)(((uint64_t)cw * (uint64_t)(a.mh.live_only ? max((int)count, 1) : D)) >> 32);
             }
             // live_only: only stars j < count move; otherwise the proposal is the current state
             frozen_slot = a.mh.live_only && !((float)k < count);
             if (frozen_slot) k = 0;
 
-            // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
             l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
+        }
+
+        // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
+        if (!full) {
             if (frozen_slot) {
                 pl0 = l0; pl1 = l1; pf = f; lq = 0.0f;  // nothing is rendered or re-priced below
             } else if constexpr (!MALA) {
@@ -865,6 +917,10 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                 s0 = pl0; s1 = pl1; sw = m.c0 * pf;
             }
             if (sw != 0.0f) star_accumulate<MODEL, RPT, W>(m, s0, s1, sw, row0, acc);
+            // the next sweep's random block (a pure function of the counters, so generating it here -- by every pass
+            // of this loop alike -- changes nothing but where the integer work is issued)
+            nxt = mh_draw_block(pidx, tile_key, a.offset, it + 1, a.seed);
+            nxt_it = it + 1;
         }
         if (full) {
 #pragma unroll
@@ -948,7 +1004,9 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         }
         last_acc = accept ? 1 : 0;
         __syncwarp();
-        if (valid && sub == 0) {
+        if (valid && sub == 0 && (a.tr_accept != nullptr || a.tr_log_alpha != nullptr || a.tr_target_prop != nullptr ||
+                                  a.tr_chain_locs != nullptr)) {
+            const size_t e = ((size_t)it * a.T + t) * N + (n0 + pi);
             if (a.tr_log_alpha) a.tr_log_alpha[e] = log_alpha;
             if (a.tr_target_prop) a.tr_target_prop[e] = target_p;
             if (a.tr_accept) a.tr_accept[e] = (int8_t)last_acc;
@@ -1289,7 +1347,7 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
                 u0 = u01_f(r.v[0]); u1 = u01_f(r.v[1]); uf = u01_f(r.v[2]); ua = u01_f(r.v[3]);
                 k = (int)(((uint64_t)rc.v[0] * (uint64_t)max(icount, 1)) >> 32);  // uniform over the live stars
             }
-            live = k < icount && k < D;
+            live = k >= 0 && k < icount && k < D;  // anything else (also a bad tape entry) leaves the catalog as it is
             if (!live) k = 0;
             l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
             pl0 = l0; pl1 = l1; pf = f;
@@ -1440,20 +1498,21 @@ int choose_tpp(int side, long long particles) {
     return tpp;
 }
 
-int g_force_tpp = 0;  // test hook (smcdet_debug_force_tpp)
+thread_local int g_force_tpp = 0;  // diagnostic override of the calling thread (smcdet_debug_force_tpp)
 
 template <int MODEL, int H, int TPP>
-int launch_loglik_t(const ModelK& m, const float* tiles, const float* locs, const float* fluxes, float* out, int T,
-                    int N, int D, cudaStream_t st) {
+int launch_loglik_t(const ModelK& m, const float* tiles, const float* locs, const float* fluxes, float* out,
+                    const int32_t* tile_map, int T, int N, int D, cudaStream_t st) {
     constexpr int PB = kBT / TPP;
     const int bpt = (N + PB - 1) / PB;
     const size_t smem = sizeof(float) * (2 * H * H + 3 * (size_t)D * PB);
+    if ((long long)T * bpt >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_loglik: grid too large");
     auto kern = loglik_kernel<MODEL, H, H, TPP>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(loglik)");
     }
-    SMC_LAUNCH(kern, (unsigned)((size_t)T * bpt), kBT, smem, st, m, tiles, locs, fluxes, out, N, D, bpt);
+    SMC_LAUNCH(kern, (unsigned)((size_t)T * bpt), kBT, smem, st, m, tiles, locs, fluxes, out, tile_map, N, D, bpt);
     return launch_status("loglik_kernel");
 }
 
@@ -1462,6 +1521,7 @@ int launch_mh_t(MHArgs& a, cudaStream_t st) {
     constexpr int PB = kBT / TPP, PPT = (H / TPP) * H;
     a.blocks_per_tile = (a.N + PB - 1) / PB;
     const size_t smem = sizeof(float) * (2 * H * H + 3 * (size_t)a.D * PB + (size_t)PPT * kBT);
+    if ((long long)a.T * a.blocks_per_tile >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_mh_mutate: grid too large");
     auto kern = mh_kernel<MODEL, H, H, TPP, MALA>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1485,8 +1545,8 @@ int launch_mh_t(MHArgs& a, cudaStream_t st) {
 
 template <int MODEL, int H>
 int dispatch_loglik_tpp(int tpp, const ModelK& m, const float* tiles, const float* locs, const float* fluxes,
-                        float* out, int T, int N, int D, cudaStream_t st) {
-    SMC_DISPATCH_TPP(launch_loglik_t, MODEL, H, tpp, m, tiles, locs, fluxes, out, T, N, D, st)
+                        float* out, const int32_t* tile_map, int T, int N, int D, cudaStream_t st) {
+    SMC_DISPATCH_TPP(launch_loglik_t, MODEL, H, tpp, m, tiles, locs, fluxes, out, tile_map, T, N, D, st)
 }
 
 template <int MODEL, int H, int TPP>
@@ -1502,10 +1562,10 @@ int dispatch_mh_tpp(int tpp, bool mala, MHArgs& a, cudaStream_t st) {
 
 template <int MODEL>
 int dispatch_loglik_side(int side, int tpp, const ModelK& m, const float* tiles, const float* locs,
-                         const float* fluxes, float* out, int T, int N, int D, cudaStream_t st) {
-    if (side == 8) return dispatch_loglik_tpp<MODEL, 8>(tpp, m, tiles, locs, fluxes, out, T, N, D, st);
-    if (side == 16) return dispatch_loglik_tpp<MODEL, 16>(tpp, m, tiles, locs, fluxes, out, T, N, D, st);
-    return dispatch_loglik_tpp<MODEL, 32>(tpp, m, tiles, locs, fluxes, out, T, N, D, st);
+                         const float* fluxes, float* out, const int32_t* tile_map, int T, int N, int D, cudaStream_t st) {
+    if (side == 8) return dispatch_loglik_tpp<MODEL, 8>(tpp, m, tiles, locs, fluxes, out, tile_map, T, N, D, st);
+    if (side == 16) return dispatch_loglik_tpp<MODEL, 16>(tpp, m, tiles, locs, fluxes, out, tile_map, T, N, D, st);
+    return dispatch_loglik_tpp<MODEL, 32>(tpp, m, tiles, locs, fluxes, out, tile_map, T, N, D, st);
 }
 
 template <int MODEL>
@@ -1538,14 +1598,16 @@ int smcdet_version(void) { return SMCDET_ABI_VERSION; }
 
 const char* smcdet_last_error_string(void) { return g_err; }
 
-// test hook: force the threads-per-particle choice of the next loglik / mh launches (0 = automatic)
+// diagnostic: force the threads-per-particle choice of the calling thread's next loglik / mh launches (0 = automatic)
 int smcdet_debug_force_tpp(int tpp) {
     g_force_tpp = tpp;
     return 0;
 }
 
-int smcdet_loglik(const smcdet_model_params* model, const float* tiles, const float* locs, const float* fluxes,
-                  float* loglik, int T, int N, int D, int h, int w, void* stream) {
+static int loglik_impl(const smcdet_model_params* model, const float* tiles, const int32_t* tile_of_segment,
+                       const float* locs, const float* fluxes, float* loglik, int T, int N, int D, int h, int w,
+                       void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_loglik: bad model parameters");
     SMC_REQUIRE(tiles && locs && fluxes && loglik, SMCDET_E_INVALID, "smcdet_loglik: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0 && h > 0 && w > 0, SMCDET_E_INVALID, "smcdet_loglik: non-positive size");
@@ -1555,18 +1617,31 @@ int smcdet_loglik(const smcdet_model_params* model, const float* tiles, const fl
     if (fast) {
         const int tpp = g_force_tpp ? g_force_tpp : choose_tpp(h, (long long)T * N);
         if (model->model_kind == SMCDET_MODEL_M71_NORMAL)
-            return dispatch_loglik_side<SMCDET_MODEL_M71_NORMAL>(h, tpp, m, tiles, locs, fluxes, loglik, T, N, D, st);
-        return dispatch_loglik_side<SMCDET_MODEL_GAUSS_POISSON>(h, tpp, m, tiles, locs, fluxes, loglik, T, N, D, st);
+            return dispatch_loglik_side<SMCDET_MODEL_M71_NORMAL>(h, tpp, m, tiles, locs, fluxes, loglik, tile_of_segment, T, N, D, st);
+        return dispatch_loglik_side<SMCDET_MODEL_GAUSS_POISSON>(h, tpp, m, tiles, locs, fluxes, loglik, tile_of_segment, T, N, D, st);
     }
     const size_t warps = (size_t)T * N;
     const size_t blocks = (warps + (kBT / 32) - 1) / (kBT / 32);
     SMC_REQUIRE(blocks < 0x7fffffffull, SMCDET_E_TOO_LARGE, "smcdet_loglik: too many particles for one launch");
-    SMC_LAUNCH(loglik_generic_kernel, (unsigned)blocks, kBT, 0, st, m, tiles, locs, fluxes, loglik, T, N, D, h, w);
+    SMC_LAUNCH(loglik_generic_kernel, (unsigned)blocks, kBT, 0, st, m, tiles, locs, fluxes, loglik, tile_of_segment, T, N, D, h, w);
     return launch_status("loglik_generic_kernel");
+}
+
+int smcdet_loglik(const smcdet_model_params* model, const float* tiles, const float* locs, const float* fluxes,
+                  float* loglik, int T, int N, int D, int h, int w, void* stream) {
+    return loglik_impl(model, tiles, nullptr, locs, fluxes, loglik, T, N, D, h, w, stream);
+}
+
+int smcdet_loglik_segments(const smcdet_model_params* model, const float* tiles, const int32_t* tile_of_segment,
+                           const float* locs, const float* fluxes, float* loglik, int S, int N, int D, int h, int w,
+                           void* stream) {
+    SMC_REQUIRE(tile_of_segment != nullptr, SMCDET_E_INVALID, "smcdet_loglik_segments: null segment map");
+    return loglik_impl(model, tiles, tile_of_segment, locs, fluxes, loglik, S, N, D, h, w, stream);
 }
 
 int smcdet_psf(const smcdet_model_params* model, const float* locs, float* psf, int T, int N, int D, int h, int w,
                void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_psf: bad model parameters");
     SMC_REQUIRE(locs && psf, SMCDET_E_INVALID, "smcdet_psf: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0 && h > 0 && w > 0, SMCDET_E_INVALID, "smcdet_psf: non-positive size");
@@ -1579,6 +1654,7 @@ int smcdet_psf(const smcdet_model_params* model, const float* locs, float* psf, 
 
 int smcdet_psf_radial(const smcdet_model_params* model, int normalized, const float* r, float* out, long long n,
                       void* stream) {
+    DeviceGuard guard(r);
     SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_psf_radial: bad model parameters");
     SMC_REQUIRE(r && out && n > 0, SMCDET_E_INVALID, "smcdet_psf_radial: null pointer or non-positive size");
     const ModelK m = make_model_k(*model);
@@ -1590,6 +1666,7 @@ int smcdet_psf_radial(const smcdet_model_params* model, int normalized, const fl
 
 int smcdet_render(const smcdet_model_params* model, const float* locs, const float* fluxes, float* rate, int T,
                   int N, int D, int h, int w, void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(model_ok(model), SMCDET_E_INVALID, "smcdet_render: bad model parameters");
     SMC_REQUIRE(locs && fluxes && rate, SMCDET_E_INVALID, "smcdet_render: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0 && h > 0 && w > 0, SMCDET_E_INVALID, "smcdet_render: non-positive size");
@@ -1601,6 +1678,7 @@ int smcdet_render(const smcdet_model_params* model, const float* locs, const flo
 
 int smcdet_prior_logprob(const smcdet_prior_params* prior, const float* counts, const float* locs,
                          const float* fluxes, float* out, int T, int N, int D, void* stream) {
+    DeviceGuard guard(counts);
     SMC_REQUIRE(prior && counts && locs && fluxes && out, SMCDET_E_INVALID, "smcdet_prior_logprob: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_prior_logprob: non-positive size");
     const size_t TN = (size_t)T * N;
@@ -1612,6 +1690,7 @@ int smcdet_prior_logprob(const smcdet_prior_params* prior, const float* counts, 
 int smcdet_prior_sample(const smcdet_prior_params* prior, const float* u_locs, const float* u_fluxes, uint64_t seed,
                         const int64_t* tile_ids, float* counts, float* locs, float* fluxes, int T,
                         int num_per_count, int D, void* stream) {
+    DeviceGuard guard(counts);
     SMC_REQUIRE(prior && counts && locs && fluxes, SMCDET_E_INVALID, "smcdet_prior_sample: null pointer");
     SMC_REQUIRE((u_locs == nullptr) == (u_fluxes == nullptr), SMCDET_E_INVALID,
                 "smcdet_prior_sample: give both uniform tapes or neither");
@@ -1626,17 +1705,22 @@ int smcdet_prior_sample(const smcdet_prior_params* prior, const float* u_locs, c
 
 int smcdet_temper_update(const float* loglik, float* tau, float* tau_prev, float ess_threshold, int do_temper,
                          float* wlog, float* weights, float* ess, float* logz, int32_t* funcalls,
-                         const int32_t* active, int T, int N, void* stream) {
+                         const int32_t* active, const smcdet_loop_state* loop, int T, int N, void* stream) {
+    DeviceGuard guard(loglik);
     SMC_REQUIRE(loglik && tau && tau_prev && wlog && weights && ess && logz, SMCDET_E_INVALID,
                 "smcdet_temper_update: null pointer");
     SMC_REQUIRE(T > 0 && N > 0, SMCDET_E_INVALID, "smcdet_temper_update: non-positive size");
+    smcdet_loop_state ls;
+    memset(&ls, 0, sizeof(ls));
+    if (loop != nullptr) ls = *loop;
     SMC_LAUNCH(temper_update_kernel, T, kTB, 0, (cudaStream_t)stream, loglik, tau, tau_prev, ess_threshold, do_temper, wlog,
-                                                              weights, ess, logz, funcalls, active, N);
+                                                              weights, ess, logz, funcalls, active, ls, N);
     return launch_status("temper_update_kernel");
 }
 
 int smcdet_resample(int method, const float* weights, const double* u, uint64_t seed, const int64_t* tile_ids,
                     const int32_t* active, int64_t* index, double* cdf_scratch, int T, int N, void* stream) {
+    DeviceGuard guard(weights);
     SMC_REQUIRE(method == SMCDET_RESAMPLE_MULTINOMIAL || method == SMCDET_RESAMPLE_SYSTEMATIC, SMCDET_E_INVALID,
                 "smcdet_resample: unknown method");
     SMC_REQUIRE(weights && index && cdf_scratch, SMCDET_E_INVALID, "smcdet_resample: null pointer");
@@ -1648,6 +1732,7 @@ int smcdet_resample(int method, const float* weights, const double* u, uint64_t 
 int smcdet_gather(const int64_t* index, const float* counts_in, const float* locs_in, const float* fluxes_in,
                   float* counts_out, float* locs_out, float* fluxes_out, const int32_t* tile_mask, int T, int N, int D,
                   void* stream) {
+    DeviceGuard guard(index);
     SMC_REQUIRE(index && counts_in && locs_in && fluxes_in && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID,
                 "smcdet_gather: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_gather: non-positive size");
@@ -1672,6 +1757,7 @@ static int mutate_impl(bool mala, const smcdet_model_params* model, const smcdet
                      float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
                      uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
                      int T, int N, int D, int h, int w, void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(model_ok(model) && prior && mh, SMCDET_E_INVALID, "smcdet_mh_mutate: bad parameters");
     SMC_REQUIRE(tiles && counts && locs && fluxes && tau && acc_rate, SMCDET_E_INVALID,
                 "smcdet_mh_mutate: null pointer");
@@ -1696,13 +1782,18 @@ static int mutate_impl(bool mala, const smcdet_model_params* model, const smcdet
     if (trace) { a.tr_log_alpha = trace->log_alpha; a.tr_target_prop = trace->target_prop; a.tr_accept = trace->accept;
                  a.tr_chain_locs = trace->chain_locs; a.tr_chain_fluxes = trace->chain_fluxes; }
     a.seed = seed; a.offset = offset; a.tile_ids = tile_ids; a.active = active; a.status = status;
+    a.tile_map = mh->tile_of_segment;
     a.T = T; a.N = N; a.D = D;
-    SMC_LAUNCH(zero_active_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, T);
-    const int tpp = g_force_tpp ? g_force_tpp : choose_tpp(h, (long long)T * N);
+    // acc_as_count: the caller keeps acc_rate zero-filled between launches and divides by N itself
+    // (smcdet_temper_update does both through smcdet_loop_state), which saves two small launches per call
+    if (!mh->acc_as_count) SMC_LAUNCH(zero_active_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, T);
+    // the decomposition is chosen for the tiles that will really run, when the caller knows how many that is
+    const long long live_tiles = (mh->live_tiles_hint > 0 && mh->live_tiles_hint < T) ? mh->live_tiles_hint : T;
+    const int tpp = g_force_tpp ? g_force_tpp : choose_tpp(h, live_tiles * N);
     int rc;
     if (model->model_kind == SMCDET_MODEL_M71_NORMAL) rc = dispatch_mh_side<SMCDET_MODEL_M71_NORMAL>(h, tpp, mala, a, st);
     else rc = dispatch_mh_side<SMCDET_MODEL_GAUSS_POISSON>(h, tpp, mala, a, st);
-    if (rc != 0) return rc;
+    if (rc != 0 || mh->acc_as_count) return rc;
     SMC_LAUNCH(divide_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, (float)N, T);
     return launch_status("divide_kernel");
 }
@@ -1727,6 +1818,7 @@ int smcdet_mala_mutate(const smcdet_model_params* model, const smcdet_prior_para
 
 int smcdet_prune(const float* locs, const float* fluxes, float tile_h, float tile_w, float flux_threshold,
                  int64_t* counts_out, float* locs_out, float* fluxes_out, int T, int N, int D, void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(locs && fluxes && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID, "smcdet_prune: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0, SMCDET_E_INVALID, "smcdet_prune: non-positive size");
     const size_t TN = (size_t)T * N;
@@ -1741,6 +1833,7 @@ int smcdet_match_catalogs(const float* true_counts, const float* true_locs, cons
                           const float* mag_bins, float locs_tol, float mags_tol, float* true_total, float* true_match,
                           float* est_total, float* est_match, int32_t* status, int T, int n, int M, int Dt, int De,
                           int B, void* stream) {
+    DeviceGuard guard(true_counts);
     SMC_REQUIRE(true_counts && true_locs && true_fluxes && est_counts && est_locs && est_fluxes && index && mag_bins,
                 SMCDET_E_INVALID, "smcdet_match_catalogs: null input pointer");
     SMC_REQUIRE(true_total && true_match && est_total && est_match, SMCDET_E_INVALID,
@@ -1757,6 +1850,7 @@ int smcdet_match_catalogs(const float* true_counts, const float* true_locs, cons
 
 int smcdet_agg_join(const float* locs, const float* fluxes, int axis, float dim, float* counts_out, float* locs_out,
                     float* fluxes_out, int nH, int nW, int N, int M, void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(locs && fluxes && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID, "smcdet_agg_join: null pointer");
     SMC_REQUIRE(nH > 0 && nW > 0 && N > 0 && M > 0 && (axis == 0 || axis == 1), SMCDET_E_INVALID,
                 "smcdet_agg_join: bad sizes");
@@ -1769,6 +1863,7 @@ int smcdet_agg_join(const float* locs, const float* fluxes, int axis, float dim,
 
 int smcdet_agg_unjoin(const float* locs, const float* fluxes, int axis, float half, float* counts_out, float* locs_out,
                       float* fluxes_out, int T, int N, int D, void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(locs && fluxes && counts_out && locs_out && fluxes_out, SMCDET_E_INVALID, "smcdet_agg_unjoin: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0 && (axis == 0 || axis == 1), SMCDET_E_INVALID, "smcdet_agg_unjoin: bad sizes");
     const size_t total = (size_t)T * N;
@@ -1783,6 +1878,7 @@ int smcdet_agg_mutate(const smcdet_model_params* model, const smcdet_prior_param
                       float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace, uint64_t seed,
                       uint64_t offset, const int64_t* tile_ids, const int32_t* active, int T, int N, int D, int h, int w,
                       void* stream) {
+    DeviceGuard guard(locs);
     SMC_REQUIRE(model_ok(model) && prior && mh, SMCDET_E_INVALID, "smcdet_agg_mutate: bad parameters");
     SMC_REQUIRE(tiles && counts && locs && fluxes && tau && acc_rate, SMCDET_E_INVALID, "smcdet_agg_mutate: null pointer");
     SMC_REQUIRE(T > 0 && N > 0 && D > 0 && mh->num_iters >= 0 && (axis == 0 || axis == 1), SMCDET_E_INVALID,

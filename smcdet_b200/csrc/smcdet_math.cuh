@@ -266,6 +266,12 @@ inline ModelK make_model_k(const smcdet_model_params& p) {
 #define SMC_SOFT_EX2_MASK 0x1
 #endif
 constexpr int kSoftEx2Mask = SMC_SOFT_EX2_MASK;
+// Separable Gaussian factors of a star (W column + RPT row factors per Gaussian term) on the FMA pipe as well:
+// bit 0 = column factors, bit 1 = row factors.
+#ifndef SMC_SOFT_GAUSS
+#define SMC_SOFT_GAUSS 0
+#endif
+constexpr int kSoftGauss = SMC_SOFT_GAUSS;
 
 template <int MODEL, int W>
 struct ColFactors {
@@ -289,9 +295,9 @@ SMC_HD void col_factors(const ModelK& m, float l1, ColFactors<MODEL, W>& c) {
         const float dx0 = (j0 + 0.5f) - l1, dx1 = (j1 + 0.5f) - l1;
         const float2 d2 = make_float2((j0 >= lo && j0 <= hi) ? dx0 * dx0 : INFINITY,
                                       (j1 >= lo && j1 <= hi) ? dx1 * dx1 : INFINITY);
-        c.e1[jp] = ex2_fast2(mul2(bcast2(-m.k1), d2));
+        c.e1[jp] = (kSoftGauss & 1) ? ex2_soft2(mul2(bcast2(-m.k1), d2)) : ex2_fast2(mul2(bcast2(-m.k1), d2));
         if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-            c.e2[jp] = ex2_fast2(mul2(bcast2(-m.k2), d2));
+            c.e2[jp] = (kSoftGauss & 1) ? ex2_soft2(mul2(bcast2(-m.k2), d2)) : ex2_fast2(mul2(bcast2(-m.k2), d2));
             c.bx[jp] = mul2(bcast2(m.cpl), d2);
         }
     }
@@ -309,9 +315,15 @@ SMC_HD void star_accumulate(const ModelK& m, float l0, float l1, float wgt, int 
         const float fi = (float)(row0 + r);
         const float dy = (fi + 0.5f) - l0;
         const float d2 = (fi >= lo && fi <= hi) ? dy * dy : INFINITY;
-        const float g1 = wgt * ex2_fast(-m.k1 * d2);
+        float g1, g2 = 0.0f;
+        if (MODEL == SMCDET_MODEL_M71_NORMAL && (kSoftGauss & 2)) {
+            const float2 g = ex2_soft2(make_float2(-m.k1 * d2, -m.k2 * d2));
+            g1 = wgt * g.x; g2 = wb * g.y;
+        } else {
+            g1 = wgt * ex2_fast(-m.k1 * d2);
+            if (MODEL == SMCDET_MODEL_M71_NORMAL) g2 = wb * ex2_fast(-m.k2 * d2);
+        }
         if (MODEL == SMCDET_MODEL_M71_NORMAL) {
-            const float g2 = wb * ex2_fast(-m.k2 * d2);
             const float ay = fmaf(m.cpl, d2, 1.0f);
 #pragma unroll
             for (int jp = 0; jp < W / 2; ++jp) {

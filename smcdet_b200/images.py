@@ -79,14 +79,25 @@ class ImageModel(object):
         """Poisson image draw, [numH, numW, h, w, n] (reference images.py:78-83)."""
         return torch.poisson(self._rate(locs, fluxes))
 
-    def loglikelihood(self, tiled_image, locs, fluxes):
-        """[numH, numW, n] log-likelihood (reference images.py:85-102 / :159-175), one fused kernel."""
+    def loglikelihood(self, tiled_image, locs, fluxes, *, tile_of_segment=None):
+        """[numH, numW, n] log-likelihood (reference images.py:85-102 / :159-175), one fused kernel.
+        ``tile_of_segment`` (keyword-only extension, [numH, numW] int): ``tiled_image`` holds one image per distinct
+        tile and "tile" (h, w) of the particle arrays is a segment evaluated on image ``tile_of_segment[h, w]``
+        (the count strata of a tile share its pixels)."""
         numH, numW, n, d, lf, ff = self._flat(locs, fluxes)
-        tiles = L.f32(tiled_image, lf.device).view(numH * numW, self.image_height, self.image_width)
+        tiles = L.f32(tiled_image, lf.device).reshape(-1, self.image_height, self.image_width)
         out = torch.empty(numH * numW, n, device=lf.device, dtype=torch.float32)
         p = self._params()
-        L.check(L.lib().smcdet_loglik(C.byref(p), L.ptr(tiles), L.ptr(lf), L.ptr(ff), L.ptr(out), numH * numW, n, d,
-                                      self.image_height, self.image_width, L.stream_for(lf)))
+        if tile_of_segment is None:
+            if tiles.shape[0] != numH * numW:
+                raise ValueError("tiled_image must hold one image per tile (or pass tile_of_segment)")
+            L.check(L.lib().smcdet_loglik(C.byref(p), L.ptr(tiles), L.ptr(lf), L.ptr(ff), L.ptr(out), numH * numW, n, d,
+                                          self.image_height, self.image_width, L.stream_for(lf)))
+        else:
+            tmap = tile_of_segment.to(device=lf.device, dtype=torch.int32).reshape(numH * numW).contiguous()
+            L.check(L.lib().smcdet_loglik_segments(C.byref(p), L.ptr(tiles), L.ptr(tmap, torch.int32), L.ptr(lf), L.ptr(ff),
+                                                   L.ptr(out), numH * numW, n, d, self.image_height, self.image_width,
+                                                   L.stream_for(lf)))
         return out.view(numH, numW, n)
 
 

@@ -47,7 +47,36 @@ class SingleComponentMH(object):
         k.locs_max[0], k.locs_max[1] = hi
         k.refresh_loglik = 1 if self.refresh_loglik else 0
         k.live_only = 1 if getattr(self, "live_only", False) else 0
+        k.acc_as_count, k.live_tiles_hint, k.tile_of_segment = 0, 0, None
         return k
+
+    def launch(self, prior, model, tiles, counts, locs, fluxes, tau, loglik_out, acc, status, *, seed, offset=0,
+               tile_ids=None, active=None, tile_of_segment=None, live_tiles_hint=0, acc_as_count=False, tape=None,
+               trace=None):
+        """One call of the fused kernel on caller-owned, already flattened device buffers ([T, ...]; nothing is
+        allocated or copied here).  ``run`` goes through it; ``SMCsampler`` calls it directly with its persistent
+        state.  ``acc_as_count``: accept counts are ADDED to ``acc`` (see ``smcdet_mh_params`` in the header)."""
+        T, n, d = fluxes.shape
+        mp, pp, kp = model._params(), prior._params(), self._params()
+        kp.acc_as_count = 1 if acc_as_count else 0
+        kp.live_tiles_hint = int(live_tiles_hint)
+        kp.tile_of_segment = None if tile_of_segment is None else L.ptr(tile_of_segment, torch.int32).value
+        dev = locs.device
+        if self.event_log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(dev))
+        L.check(getattr(L.lib(), self._entry)(
+            C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), L.ptr(counts), L.ptr(locs), L.ptr(fluxes), L.ptr(tau),
+            L.ptr(loglik_out), L.ptr(acc), C.byref(tape) if tape is not None else None,
+            C.byref(trace) if trace is not None else None, int(seed), int(offset), L.ptr(tile_ids, torch.int64),
+            L.ptr(active, torch.int32), L.ptr(status, torch.int32), T, n, d, model.image_height, model.image_width,
+            L.stream_for(locs)))
+        if acc_as_count:
+            L.lib().adjust(-2)  # no zero-fill and no divide launch
+        if self.event_log is not None:
+            ev1.record(torch.cuda.current_stream(dev))
+            self.event_log.append((ev0, ev1, active, T, n, d, int(self.num_iters)))
+        self._status = status
 
     @staticmethod
     def _resolve_target(log_target):
@@ -64,7 +93,7 @@ class SingleComponentMH(object):
         return prior, model
 
     def run(self, data, counts, locs, fluxes, temperature, log_target, *, tape=None, trace=False, seed=None,
-            offset=0, tile_ids=None, active=None, inplace=False, chain=False):
+            offset=0, tile_ids=None, active=None, inplace=False, chain=False, tile_of_segment=None):
         """Returns [locs, fluxes, acceptance rate of the last iteration [numH, numW]] (reference
         kernel.py:26-130).  Keyword-only extras (not in the reference):
           tape   dict(comp[iters,numH,numW,n] int32, u_loc[...,2], u_flux, u_acc) of injected draws
@@ -72,6 +101,8 @@ class SingleComponentMH(object):
           seed, offset, tile_ids   Philox stream selection when no tape is given
           active [numH, numW] int32 mask of tiles to mutate; inplace  update locs/fluxes in place
           chain  also keep the catalog after every sweep in ``self.last_trace`` (what MHsampler records)
+          tile_of_segment  [numH, numW] int32: ``data`` holds one image per distinct tile and "tile" (h, w) of the
+                 particle arrays is a segment of image ``tile_of_segment[h, w]`` (count strata share their tile's pixels)
         """
         prior, model = self._resolve_target(log_target)
         numH, numW, n, d, _ = locs.shape
@@ -85,7 +116,10 @@ class SingleComponentMH(object):
                 lf = lf.clone()
             if ff.data_ptr() == fluxes.data_ptr():
                 ff = ff.clone()
-        tiles = L.f32(data, dev).reshape(T, h, w)
+        tiles = L.f32(data, dev).reshape(-1, h, w)
+        tmap = None if tile_of_segment is None else tile_of_segment.to(device=dev, dtype=torch.int32).reshape(T).contiguous()
+        if tmap is None and tiles.shape[0] != T:
+            raise ValueError("data must hold one image per tile (or pass tile_of_segment)")
         cf = L.f32(counts, dev).reshape(T, n)
         tau = L.f32(temperature, dev).reshape(T)
         loglik = torch.empty(T, n, device=dev, dtype=torch.float32)
@@ -122,19 +156,9 @@ class SingleComponentMH(object):
         act = None if active is None else active.to(device=dev, dtype=torch.int32).reshape(T).contiguous()
         tids = None if tile_ids is None else tile_ids.to(device=dev, dtype=torch.int64).reshape(T).contiguous()
 
-        mp, pp, kp = model._params(), prior._params(), self._params()
-        if self.event_log is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(torch.cuda.current_stream(dev))
-        L.check(getattr(L.lib(), self._entry)(
-            C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), L.ptr(cf), L.ptr(lf), L.ptr(ff), L.ptr(tau),
-            L.ptr(loglik), L.ptr(acc), C.byref(tp) if tp is not None else None, C.byref(tr) if tr is not None else None,
-            L.fresh_seed() if seed is None else int(seed), int(offset), L.ptr(tids, torch.int64),
-            L.ptr(act, torch.int32), L.ptr(status, torch.int32), T, n, d, h, w, L.stream_for(lf)))
-        if self.event_log is not None:
-            ev1.record(torch.cuda.current_stream(dev))
-            self.event_log.append((ev0, ev1, act, T, n, d, iters))
-        self._status = status
+        self.launch(prior, model, tiles, cf, lf.view(T, n, d, 2), ff.view(T, n, d), tau, loglik, acc, status,
+                    seed=L.fresh_seed() if seed is None else int(seed), offset=offset, tile_ids=tids, active=act,
+                    tile_of_segment=tmap, tape=tp, trace=tr)
         self.last_loglik = loglik.view(numH, numW, n)
         return [lf.view(numH, numW, n, d, 2), ff.view(numH, numW, n, d), acc.view(numH, numW)]
 
@@ -142,7 +166,10 @@ class SingleComponentMH(object):
         """Raise the reference's AssertionError (distributions.py:51) if the last run() saw a location
         or flux outside the proposal box.  Synchronises with the device."""
         st = getattr(self, "_status", None)
-        if st is not None and int(st.item()) & A.STATUS_OUT_OF_BOX:
+        bits = 0 if st is None else int(st.item())
+        if bits & A.STATUS_BAD_TAPE:
+            raise ValueError("the injected draw tape holds a component index outside [0, max_objects)")
+        if bits & A.STATUS_OUT_OF_BOX:
             raise AssertionError("value outside [lb, ub] of the truncated-normal proposal "
                                  "(reference smcdet/distributions.py:51)")
 

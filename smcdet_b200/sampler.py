@@ -12,6 +12,8 @@ State attributes keep the reference's names and shapes ([numH, numW, ...]).
 """
 
 
+import ctypes as C
+
 import torch
 
 from . import _abi as A
@@ -21,7 +23,7 @@ from . import _lib as L
 class SMCsampler(object):
     def __init__(self, image, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
                  resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, tile_ids=None,
-                 freeze_finished=False, verbose=True, initial_catalogs=None):
+                 freeze_finished=False, verbose=True, initial_catalogs=None, tile_of_segment=None, seed=None):
         """``image``: square 2-D tensor (reference sampler.py:25-31), or -- an extension used by the
         tile-sharding layer -- an already tiled [numH, numW, tile_dim, tile_dim] tensor.
         Keyword-only extras: ``tile_ids`` [numH, numW] global tile ids keying the Philox streams
@@ -29,7 +31,11 @@ class SMCsampler(object):
         tiles that reached temperature 1 (the reference keeps mutating them, sampler.py:230),
         ``verbose`` silences the progress prints, ``initial_catalogs`` = (counts, locs, fluxes) replaces the
         prior draw of ``initialize`` (used by the count-stratified sampler, whose pseudo-tiles are the strata of
-        one stratified draw)."""
+        one stratified draw), ``tile_of_segment`` [numH, numW] int: the particle grid is a grid of SEGMENTS (SURVEY.md
+        0.5: tile x stratum) and segment (h, w) lives on image ``tile_of_segment[h, w]`` of the 4-D ``image`` (any
+        leading shape, flattened), so the strata of a tile share its pixels instead of carrying copies; ``seed``: the
+        Philox base seed of run() (default: one draw from torch's CPU generator per run) -- ranks that share a field
+        must use the same one for a tile's result not to depend on the sharding."""
         dev = image.device if (isinstance(image, torch.Tensor) and image.is_cuda) else L.device()
         self.image = image
         self.tile_dim = tile_dim
@@ -41,12 +47,18 @@ class SMCsampler(object):
             self.tiled_image = img.unfold(0, self.tile_dim, self.tile_dim).unfold(1, self.tile_dim, self.tile_dim)
         elif image.dim() == 4:
             self.numH, self.numW = image.shape[0], image.shape[1]
+            if tile_of_segment is not None:
+                self.numH, self.numW = tile_of_segment.shape
             self.num_tiles_per_side = self.numH
             self.image_dim = self.numH * self.tile_dim
             self.tiled_image = L.f32(image, dev)
         else:
             raise ValueError("image must be a square 2-D tensor or a [numH, numW, h, w] tensor of tiles")
         self._device = dev
+        if tile_of_segment is not None and image.dim() != 4:
+            raise ValueError("tile_of_segment needs the 4-D form of image (one entry per distinct tile)")
+        self._tile_map = None if tile_of_segment is None else tile_of_segment.to(device=dev, dtype=torch.int32).contiguous()
+        self._seg_kw = {} if self._tile_map is None else {"tile_of_segment": self._tile_map}
 
         self.Prior = Prior
         self.ImageModel = ImageModel
@@ -72,7 +84,8 @@ class SMCsampler(object):
         self.verbose = verbose
         self._loglik_key = None
         self._active = None
-        self._base_seed = None
+        self._fixed_seed = None if seed is None else int(seed) & ((1 << 62) - 1)
+        self._base_seed = self._fixed_seed
         self._seed_uses = {}
         self._final = False
         self.iter = 0
@@ -120,7 +133,7 @@ class SMCsampler(object):
                 self.numH, self.numW, None, True, self.num_catalogs, tape=tape, seed=self._seed(0), tile_ids=self.tile_ids)
         self.temperature_prev = torch.zeros(self.numH, self.numW, device=dev)
         self.temperature = torch.zeros(self.numH, self.numW, device=dev)
-        self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)
+        self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes, **self._seg_kw)
         self._loglik_key = self._state_key()
         self.weights_log_unnorm = torch.zeros(self.numH, self.numW, self.num_catalogs, device=dev)
         self.weights = torch.full((self.numH, self.numW, self.num_catalogs), 1.0 / self.num_catalogs, device=dev)
@@ -165,7 +178,7 @@ class SMCsampler(object):
         calls = torch.zeros(T, device=self._device, dtype=torch.int32)
         L.check(L.lib().smcdet_temper_update(L.ptr(ll), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold),
                                              int(do_temper), L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz),
-                                             L.ptr(calls, torch.int32), L.ptr(self._active_i32(), torch.int32), T, n,
+                                             L.ptr(calls, torch.int32), L.ptr(self._active_i32(), torch.int32), None, T, n,
                                              L.stream_for(ll)))
         return wlog, weights, ess, calls
 
@@ -173,7 +186,7 @@ class SMCsampler(object):
         """Adaptive temperature step (reference sampler.py:99-125).  The reference recomputes the
         likelihood first; here it is reused when ``mutate``/``initialize`` just produced it."""
         if self._loglik_key is None or self._loglik_key != self._state_key():
-            self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)
+            self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes, **self._seg_kw)
             self._loglik_key = self._state_key()
         tau = L.f32(self.temperature, self._device).reshape(self._T).clone()
         tau_prev = L.f32(self.temperature_prev, self._device).reshape(self._T).clone()
@@ -187,7 +200,7 @@ class SMCsampler(object):
         """temper() followed by update_weights() as ONE launch (smcdet_temper_update does both); used by
         run(), where the two always come as a pair (reference sampler.py:246-247)."""
         if self._loglik_key is None or self._loglik_key != self._state_key():
-            self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes)
+            self.loglik = self.ImageModel.loglikelihood(self.tiled_image, self.locs, self.fluxes, **self._seg_kw)
             self._loglik_key = self._state_key()
         tau = L.f32(self.temperature, self._device).reshape(self._T).clone()
         tau_prev = L.f32(self.temperature_prev, self._device).reshape(self._T).clone()
@@ -272,6 +285,7 @@ class SMCsampler(object):
         kw.setdefault("tile_ids", self.tile_ids)
         kw.setdefault("offset", self.iter)
         kw.setdefault("seed", self._seed(2))
+        kw.update(self._seg_kw)
         self.locs, self.fluxes, acc = self.MutationKernel.run(
             self.tiled_image, self.counts, self.locs, self.fluxes, self.temperature, self.log_target, **kw)
         ll = getattr(self.MutationKernel, "last_loglik", None)
@@ -306,7 +320,7 @@ class SMCsampler(object):
         to an uninterrupted one: every stage's Philox key depends on (base seed, iteration, stage) only."""
         if not resume:
             self.iter = 0
-            self._base_seed = None
+            self._base_seed = self._fixed_seed
             self._seed_uses = {}
             self.history = []
             self._stage_events = []
@@ -315,7 +329,10 @@ class SMCsampler(object):
             self._temper_and_update()
             self._record()
 
-        if self.freeze_finished and stop_after is None and not self.verbose:
+        if (self.freeze_finished and stop_after is None and not self.verbose and not self.record_history
+                and hasattr(self.MutationKernel, "launch")):
+            self._iterate_fused()
+        elif self.freeze_finished and stop_after is None and not self.verbose:
             self._iterate_ahead()
         else:
             while torch.any(self.temperature < 1) and self.iter <= self.max_smc_iters:
@@ -388,6 +405,119 @@ class SMCsampler(object):
             self.iter += 1
             self._one_iteration()
             prev, cur = cur, post_flag()
+
+    def _iterate_fused(self):
+        """The SMC loop of a ``freeze_finished`` run on persistent device state: per iteration exactly four launches --
+        ``smcdet_resample``, ``smcdet_gather``, ``smcdet_mh_mutate``, ``smcdet_temper_update`` -- and one 4-byte
+        device-to-host copy.  Everything the plain loop does between the stages with small tensor operations
+        (the mask of live tiles, keeping finished tiles' results, the loop test ``torch.any(temperature < 1)`` of
+        reference sampler.py:230, acceptance counts -> rates) happens inside those kernels (``active`` masks,
+        ``smcdet_loop_state``, ``acc_as_count``); particles ping-pong between two buffer sets and a finished tile is
+        copied once more right after it finishes, after which both sets hold its final particles.  The host runs one
+        iteration ahead of the device as in ``_iterate_ahead``: iteration k + 1 is launched once the live-tile count
+        of iteration k - 1 is known to be positive, and an iteration launched after every tile had finished changes
+        nothing.  Results are identical to the plain loop."""
+        lib, dev = L.lib(), self._device
+        T, n = self._T, self.num_catalogs
+        d = self.fluxes.shape[-1]
+        nH, nW = self.numH, self.numW
+        method = A.RESAMPLE_MULTINOMIAL if self.resample_method == "multinomial" else A.RESAMPLE_SYSTEMATIC
+        mk = self.MutationKernel
+        prior, model = mk._resolve_target(self.log_target)
+        tiles = L.f32(self.tiled_image, dev).reshape(-1, self.tile_dim, self.tile_dim)
+        tmap = None if self._tile_map is None else self._tile_map.reshape(T)
+        tids = None if self.tile_ids is None else self.tile_ids.reshape(T).contiguous()
+        flat = lambda t, *shape: L.f32(t, dev).reshape(*shape).clone()  # noqa: E731  (own storage, updated in place)
+        tau, tau_prev, logz = flat(self.temperature, T), flat(self.temperature_prev, T), flat(self.log_normalizing_constant, T)
+        wlog, weights, ess = flat(self.weights_log_unnorm, T, n), flat(self.weights, T, n), flat(self.ess, T)
+        acc_rate, loglik = flat(self.mutation_acc_rates, T), flat(self.loglik, T, n)
+        cur = [flat(self.counts, T, n), flat(self.locs, T, n, d, 2), flat(self.fluxes, T, n, d)]
+        oth = [torch.empty_like(x) for x in cur]
+        idx = torch.empty(T, n, device=dev, dtype=torch.int64)
+        cdf = torch.empty(T, n, device=dev, dtype=torch.float64)
+        calls = torch.zeros(T, device=dev, dtype=torch.int32)
+        acc_count = torch.zeros(T, device=dev)
+        status = torch.zeros(1, device=dev, dtype=torch.int32)
+        active = torch.empty(2, T, device=dev, dtype=torch.int32)
+        active[0] = tau < 1
+        max_it = int(self.max_smc_iters) + 2
+        live = torch.zeros(max_it + 1, device=dev, dtype=torch.int32)  # live[k]: tiles below temperature 1 after iteration k
+        live[self.iter if self.iter <= max_it else 0] = active[0].sum()
+        base = self.iter
+        ring = [torch.empty(1, dtype=torch.int32, pin_memory=True) for _ in range(3)]
+        stream = torch.cuda.current_stream(dev)
+
+        def post(k):  # asynchronous read-back of live[k]
+            host = ring[k % len(ring)]
+            host.copy_(live[k:k + 1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            return host, ev
+
+        def read(flag):
+            flag[1].synchronize()
+            return int(flag[0].item())
+
+        def iteration(k, a_cur, a_prev, hint):
+            nonlocal cur, oth
+            seed_r, seed_m = self._seed(1, k), self._seed(2, k)
+
+            def resample():
+                L.check(lib.smcdet_resample(method, L.ptr(weights), None, seed_r, L.ptr(tids, torch.int64),
+                                            L.ptr(a_cur, torch.int32), L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64),
+                                            T, n, L.stream_for(weights)))
+                L.check(lib.smcdet_gather(L.ptr(idx, torch.int64), L.ptr(cur[0]), L.ptr(cur[1]), L.ptr(cur[2]),
+                                          L.ptr(oth[0]), L.ptr(oth[1]), L.ptr(oth[2]), L.ptr(a_prev, torch.int32), T, n, d,
+                                          L.stream_for(weights)))
+
+            def mutate():
+                mk.launch(prior, model, tiles, oth[0], oth[1], oth[2], tau, loglik, acc_count, status, seed=seed_m,
+                          offset=k, tile_ids=tids, active=a_cur, tile_of_segment=tmap, live_tiles_hint=hint, acc_as_count=True)
+
+            def temper():
+                a_next = active[(k - base) % 2]
+                ls = A.LoopState(a_next.data_ptr(), live[k:k + 1].data_ptr(), acc_count.data_ptr(), acc_rate.data_ptr())
+                L.check(lib.smcdet_temper_update(L.ptr(loglik), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold), 1,
+                                                 L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz),
+                                                 L.ptr(calls, torch.int32), L.ptr(a_cur, torch.int32), C.byref(ls), T, n,
+                                                 L.stream_for(loglik)))
+
+            self._timed("resample", resample)
+            self._timed("mutate", mutate)
+            self._timed("temper+update_weights", temper)
+            cur, oth = oth, cur
+
+        flags = {base: post(base)}
+        counts_seen = []  # live tiles entering each iteration that was really needed
+        k = base
+        while True:
+            # the newest live-tile count the host may wait for without stalling the device: that of iteration k - 1
+            # (k: the last iteration launched); before the first launch, that of the initial tempering step
+            known = k - 1 if k > base else base
+            nlive = read(flags[known])
+            if nlive == 0:
+                if k > known:  # iteration k was launched after every tile had finished: it changed nothing
+                    k -= 1
+                break
+            if k > self.max_smc_iters:
+                break
+            k += 1
+            a_cur = active[(k - 1 - base) % 2]
+            a_prev = None if k == base + 1 else active[(k - base) % 2]  # mask of the previous iteration = tiles to copy
+            iteration(k, a_cur, a_prev, nlive)
+            flags[k] = post(k)
+            flags.pop(k - 3, None)
+        torch.cuda.current_stream(dev).synchronize()
+        self.iter = k
+        self.live_tiles = [int(v) for v in live[base:k].tolist()]  # live tiles entering iterations base+1 .. k
+        self.temperature, self.temperature_prev = tau.view(nH, nW), tau_prev.view(nH, nW)
+        self.log_normalizing_constant, self.ess = logz.view(nH, nW), ess.view(nH, nW)
+        self.weights_log_unnorm, self.weights = wlog.view(nH, nW, n), weights.view(nH, nW, n)
+        self.mutation_acc_rates, self.loglik = acc_rate.view(nH, nW), loglik.view(nH, nW, n)
+        self.tempering_funcalls, self.resampled_index = calls.view(nH, nW), idx.view(nH, nW, n)
+        self.counts, self.locs, self.fluxes = cur[0].view(nH, nW, n), cur[1].view(nH, nW, n, d, 2), cur[2].view(nH, nW, n, d)
+        self._loglik_key = self._state_key()
+        mk._status = status
 
     def _timed(self, stage, fn):
         """Run one stage; with ``stage_timing`` set, bracket it with CUDA events on the current stream (tracing hook:

@@ -44,6 +44,49 @@ def gather_tiles(local, num_tiles, group=None):
     return full
 
 
+def gather_tiles_to_root(local, num_tiles, dst=0, group=None):
+    """``dist.gather`` of a per-tile tensor ``local`` [T_r, ...] (this rank's round-robin shard) into the full
+    [num_tiles, ...] tensor in global tile order on rank ``dst`` (returns None elsewhere): the NCCL gather of posterior
+    catalogs into the rank that runs the ``Aggregate`` sink.  Only the root pays for the full field."""
+    if not (dist.is_available() and dist.is_initialized()):
+        if local.shape[0] != num_tiles:
+            raise ValueError("without a process group the local shard must be the whole field")
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = shard_sizes(num_tiles, world)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"local shard has {local.shape[0]} tiles, expected {sizes[rank]}")
+    tmax = max(sizes)
+    if local.shape[0] == tmax:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros((tmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    full = torch.empty((num_tiles,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        full[r::world] = parts[r][: sizes[r]]
+    return full
+
+
+def shared_seed(device=None, group=None):
+    """One Philox base seed for all ranks: rank 0 draws it from torch's CPU generator and broadcasts it (a tile's
+    streams are keyed by (base seed, iteration, stage, global tile id), so ranks must agree on the base seed for a
+    tile's posterior not to depend on the sharding)."""
+    from . import _lib as L
+
+    seed = L.fresh_seed()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor([seed], dtype=torch.int64, device=device if on_gpu else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        seed = int(t.item())
+    return seed
+
+
 class ShardedSMC(object):
     """Runs ``SMCsampler`` on this rank's round-robin shard of a field of tiles and gathers the
     posterior into per-field tensors.
@@ -54,7 +97,7 @@ class ShardedSMC(object):
 
     def __init__(self, tiles, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
                  resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, group=None,
-                 freeze_finished=True, verbose=False, device=None):
+                 freeze_finished=True, verbose=False, device=None, seed=None):
         from .sampler import SMCsampler
 
         self.group = group
@@ -66,11 +109,13 @@ class ShardedSMC(object):
         self.local_ids = shard_tile_ids(self.num_tiles, self.world, self.rank)
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._tiles, self._device = tiles, dev
-        local = tiles[self.local_ids].to(dev).unsqueeze(1)  # [T_r, 1, h, w]
+        local = tiles[self.local_ids].to(dev, non_blocking=True).unsqueeze(1)  # [T_r, 1, h, w]
+        # every rank must use the same Philox base seed (given, or rank 0's broadcast)
+        self.seed = shared_seed(dev, group) if seed is None else int(seed)
         self.sampler = SMCsampler(local, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs,
                                   ess_threshold_prop, resample_method, flux_detection_threshold, max_smc_iters,
                                   print_every, tile_ids=self.local_ids.to(dev).unsqueeze(1),
-                                  freeze_finished=freeze_finished, verbose=verbose)
+                                  freeze_finished=freeze_finished, verbose=verbose, seed=self.seed)
 
     def run(self):
         self.sampler.run()
@@ -94,6 +139,33 @@ class ShardedSMC(object):
         """All-gather the named per-tile results into global tile order ([T, ...] on every rank)."""
         local = self.local_results()
         return {k: gather_tiles(local[k].contiguous(), self.num_tiles, self.group) for k in keys}
+
+    def gather_to_root(self, keys=("counts", "locs", "fluxes", "weights", "summaries"), dst=0):
+        """``dist.gather`` the named per-tile results onto rank ``dst`` in global tile order (None on other ranks)."""
+        local = self.local_results()
+        out = {k: gather_tiles_to_root(local[k].contiguous(), self.num_tiles, dst, self.group) for k in keys}
+        return out if self.rank == dst else None
+
+    def sink(self, MutationKernel=None, *, dst=0, resample_method=None, ess_threshold_prop=0.5):
+        """The reference's per-tile finish (experiments/m71/run_smc.py:124-166; aggregate.py:583-589 for a 1 x 1 grid):
+        every tile's weighted catalogs are gathered onto rank ``dst`` (NCCL gather over NVLink) and handed to
+        ``Aggregate(..., merge=False).run()`` -- final resample by the weights and prune, tile by tile.  Returns the
+        ``Aggregate`` on rank ``dst``, None elsewhere."""
+        from .aggregate import Aggregate
+
+        out = self.gather_to_root(dst=dst)
+        if out is None:
+            return None
+        s = self.sampler
+        T, n, d = out["counts"].shape[0], out["counts"].shape[1], out["fluxes"].shape[-1]
+        data = self._tiles.to(self._device).reshape(T, 1, *self._tiles.shape[1:])
+        agg = Aggregate(s.Prior, s.ImageModel, MutationKernel or s.MutationKernel, data, out["counts"].view(T, 1, n),
+                        out["locs"].view(T, 1, n, d, 2), out["fluxes"].view(T, 1, n, d), out["weights"].view(T, 1, n),
+                        out["summaries"][:, 0].reshape(T, 1), s.flux_detection_threshold,
+                        resample_method or s.resample_method, ess_threshold_prop, print_every=10**6, merge=False)
+        agg.summaries = out["summaries"]
+        agg.run()
+        return agg
 
     def aggregate(self, grid, MutationKernel, *, resample_method=None, ess_threshold_prop=0.5, print_every=10**6,
                   root_only=True):

@@ -63,14 +63,19 @@ class GpuBackend:
         self.lib.smcdet_debug_force_tpp(int(tpp))
 
     # -- ABI calls
-    def loglik(self, model, tiles, locs, fluxes):
+    def loglik(self, model, tiles, locs, fluxes, tile_of_segment=None):
         t = self.torch
         tiles, locs, fluxes = self._d(tiles), self._d(locs), self._d(fluxes)
-        T, h, w = tiles.shape
-        _, N, D, _ = locs.shape
+        _, h, w = tiles.shape
+        T, N, D, _ = locs.shape
         out = self._z((T, N), t.float32)
-        self._check(self.lib.smcdet_loglik(C.byref(model), self._p(tiles), self._p(locs), self._p(fluxes), self._p(out),
-                                           T, N, D, h, w, self._stream()))
+        if tile_of_segment is None:
+            self._check(self.lib.smcdet_loglik(C.byref(model), self._p(tiles), self._p(locs), self._p(fluxes), self._p(out),
+                                               T, N, D, h, w, self._stream()))
+        else:
+            tmap = self._d(tile_of_segment, np.int32)
+            self._check(self.lib.smcdet_loglik_segments(C.byref(model), self._p(tiles), self._p(tmap), self._p(locs),
+                                                        self._p(fluxes), self._p(out), T, N, D, h, w, self._stream()))
         return out.cpu().numpy()
 
     def psf(self, model, locs, h, w):
@@ -110,20 +115,29 @@ class GpuBackend:
                                                  self._stream()))
         return counts.cpu().numpy(), locs.cpu().numpy(), fluxes.cpu().numpy()
 
-    def temper_update(self, loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True, active=None):
+    def temper_update(self, loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True, active=None, loop=None):
+        """``loop`` = dict(acc_count=[T] float32, live_count=int) exercises smcdet_loop_state; its outputs are
+        returned as active_next / live_count / acc_rate / acc_count."""
         t = self.torch
         ll = self._d(loglik_)
         T, N = ll.shape
         tau, tau_prev, logz = self._d(np.reshape(tau, -1)), self._d(np.reshape(tau_prev, -1)), self._d(np.reshape(logz, -1))
         wlog, weights = self._z((T, N), t.float32), self._z((T, N), t.float32)
         ess, calls = self._z((T,), t.float32), self._z((T,), t.int32)
+        ls, keep = None, {}
+        if loop is not None:
+            keep = dict(active_next=self._d(np.full(T, -1, np.int32), np.int32), live_count=self._d(np.array([loop.get("live_count", 0)], np.int32), np.int32),
+                        acc_count=self._d(np.asarray(loop["acc_count"], np.float32)), acc_rate=self._d(np.full(T, -1.0, np.float32)))
+            ls = A.LoopState(*(keep[k].data_ptr() for k in ("active_next", "live_count", "acc_count", "acc_rate")))
         self._check(self.lib.smcdet_temper_update(self._p(ll), self._p(tau), self._p(tau_prev), ess_threshold,
                                                   int(do_temper), self._p(wlog), self._p(weights), self._p(ess),
-                                                  self._p(logz), self._p(calls), self._p(self._d(active, np.int32)), T, N,
-                                                  self._stream()))
+                                                  self._p(logz), self._p(calls), self._p(self._d(active, np.int32)),
+                                                  C.byref(ls) if ls is not None else None, T, N, self._stream()))
         g = lambda x: x.cpu().numpy()  # noqa: E731
-        return dict(tau=g(tau), tau_prev=g(tau_prev), wlog=g(wlog), weights=g(weights), ess=g(ess), logz=g(logz),
-                    funcalls=g(calls))
+        out = dict(tau=g(tau), tau_prev=g(tau_prev), wlog=g(wlog), weights=g(weights), ess=g(ess), logz=g(logz),
+                   funcalls=g(calls))
+        out.update({k: g(v) for k, v in keep.items()})
+        return out
 
     def resample(self, method, weights, u=None, seed=0, active=None):
         t = self.torch
@@ -147,15 +161,23 @@ class GpuBackend:
         return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
 
     def mh_mutate(self, model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-                  active=None, chain=False, mala=False):
+                  active=None, chain=False, mala=False, tile_of_segment=None, acc_init=-1.0):
+        """``tile_of_segment`` [T] int: segment -> image map (uploaded and installed in a copy of ``mh``);
+        ``acc_init``: initial content of the acceptance output (0 for mh.acc_as_count = 1)."""
         t = self.torch
         tiles, counts, locs, fluxes = self._d(tiles), self._d(counts), self._d(locs), self._d(fluxes)
         tau = self._d(np.reshape(tau, -1))
-        T, h, w = tiles.shape
-        _, N, D, _ = locs.shape
+        _, h, w = tiles.shape
+        T, N, D, _ = locs.shape
         iters = mh.num_iters
+        tmap = self._d(tile_of_segment, np.int32)
+        if tmap is not None:
+            mh2 = A.MHParams()
+            C.memmove(C.byref(mh2), C.byref(mh), C.sizeof(mh))
+            mh2.tile_of_segment = tmap.data_ptr()
+            mh = mh2
         ll = self._z((T, N), t.float32)
-        acc = t.full((T,), -1.0, device=self.dev)
+        acc = t.full((T,), float(acc_init), device=self.dev)
         status = self._z((1,), t.int32)
         tp = tr = None
         keep = []

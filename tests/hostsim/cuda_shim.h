@@ -161,6 +161,12 @@ inline float atomicAdd(float* p, float v) {
     *p = old + v;
     return old;
 }
+inline int atomicAdd(int* p, int v) {
+    std::lock_guard<std::mutex> g(hostsim::g_atomic_mutex);
+    const int old = *p;
+    *p = old + v;
+    return old;
+}
 inline int atomicOr(int* p, int v) {
     std::lock_guard<std::mutex> g(hostsim::g_atomic_mutex);
     const int old = *p;

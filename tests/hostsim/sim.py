@@ -60,12 +60,16 @@ def force_tpp(tpp):
     lib().smcdet_debug_force_tpp(int(tpp))
 
 
-def loglik(model, tiles, locs, fluxes):
+def loglik(model, tiles, locs, fluxes, tile_of_segment=None):
     tiles, locs, fluxes = _f(tiles), _f(locs), _f(fluxes)
-    T, h, w = tiles.shape
-    _, N, D, _ = locs.shape
+    _, h, w = tiles.shape
+    T, N, D, _ = locs.shape
     out = np.zeros((T, N), np.float32)
-    check(lib().smcdet_loglik(C.byref(model), _p(tiles), _p(locs), _p(fluxes), _p(out), T, N, D, h, w, None))
+    if tile_of_segment is None:
+        check(lib().smcdet_loglik(C.byref(model), _p(tiles), _p(locs), _p(fluxes), _p(out), T, N, D, h, w, None))
+    else:
+        tmap = np.ascontiguousarray(tile_of_segment, np.int32)
+        check(lib().smcdet_loglik_segments(C.byref(model), _p(tiles), _p(tmap), _p(locs), _p(fluxes), _p(out), T, N, D, h, w, None))
     return out
 
 
@@ -106,7 +110,7 @@ def prior_sample(prior, T, num_per_count, D, u_locs=None, u_fluxes=None, seed=0,
     return counts, locs, fluxes
 
 
-def temper_update(loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True, active=None):
+def temper_update(loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True, active=None, loop=None):
     ll = _f(loglik_)
     T, N = ll.shape
     tau, tau_prev, logz = _f(tau).reshape(-1).copy(), _f(tau_prev).reshape(-1).copy(), _f(logz).reshape(-1).copy()
@@ -114,9 +118,16 @@ def temper_update(loglik_, tau, tau_prev, ess_threshold, logz, do_temper=True, a
     ess = np.zeros(T, np.float32)
     calls = np.zeros(T, np.int32)
     act = np.ascontiguousarray(active, np.int32) if active is not None else None
+    ls, keep = None, {}
+    if loop is not None:
+        keep = dict(active_next=np.full(T, -1, np.int32), live_count=np.array([loop.get("live_count", 0)], np.int32),
+                    acc_count=np.array(loop["acc_count"], np.float32), acc_rate=np.full(T, -1.0, np.float32))
+        ls = A.LoopState(*(keep[k].ctypes.data for k in ("active_next", "live_count", "acc_count", "acc_rate")))
     check(lib().smcdet_temper_update(_p(ll), _p(tau), _p(tau_prev), ess_threshold, int(do_temper), _p(wlog), _p(weights),
-                                     _p(ess), _p(logz), _p(calls), _p(act), T, N, None))
-    return dict(tau=tau, tau_prev=tau_prev, wlog=wlog, weights=weights, ess=ess, logz=logz, funcalls=calls)
+                                     _p(ess), _p(logz), _p(calls), _p(act), C.byref(ls) if ls is not None else None, T, N, None))
+    out = dict(tau=tau, tau_prev=tau_prev, wlog=wlog, weights=weights, ess=ess, logz=logz, funcalls=calls)
+    out.update(keep)
+    return out
 
 
 def resample(method, weights, u=None, seed=0, active=None):
@@ -140,15 +151,21 @@ def gather(idx, counts, locs, fluxes):
 
 
 def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-              active=None, chain=False, mala=False):
+              active=None, chain=False, mala=False, tile_of_segment=None, acc_init=-1.0):
     tiles, counts = _f(tiles), _f(counts)
     locs, fluxes = _f(locs).copy(), _f(fluxes).copy()
     tau = _f(tau).reshape(-1)
-    T, h, w = tiles.shape
-    _, N, D, _ = locs.shape
+    _, h, w = tiles.shape
+    T, N, D, _ = locs.shape
     iters = mh.num_iters
+    tmap = np.ascontiguousarray(tile_of_segment, np.int32) if tile_of_segment is not None else None
+    if tmap is not None:
+        mh2 = A.MHParams()
+        C.memmove(C.byref(mh2), C.byref(mh), C.sizeof(mh))
+        mh2.tile_of_segment = tmap.ctypes.data
+        mh = mh2
     ll = np.zeros((T, N), np.float32)
-    acc = np.full(T, -1.0, np.float32)
+    acc = np.full(T, float(acc_init), np.float32)
     status = np.zeros(1, np.int32)
     keep = []
     tp = None

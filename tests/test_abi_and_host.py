@@ -43,7 +43,10 @@ def test_struct_layouts_match_the_header():
 
     assert ctypes.sizeof(_abi.ModelParams) == 15 * 4
     assert ctypes.sizeof(_abi.PriorParams) == 4 * 4 + 4 + 4 * 4 + 6 * 4
-    assert ctypes.sizeof(_abi.MHParams) == 4 + 4 * 4 + 4 * 4 + 4 + 4
+    # 13 four-byte members (52 bytes), padding to the pointer's alignment, the tile_of_segment pointer
+    assert ctypes.sizeof(_abi.MHParams) == 56 + ctypes.sizeof(ctypes.c_void_p)
+    assert _abi.MHParams.tile_of_segment.offset == 56 and _abi.MHParams.acc_as_count.offset == 44
+    assert ctypes.sizeof(_abi.LoopState) == 4 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_abi.DrawTape) == 4 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_abi.MHTrace) == 5 * ctypes.sizeof(ctypes.c_void_p)
 
@@ -60,7 +63,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     m.model_kind = _abi.MODEL_M71_NORMAL
     assert cdll.smcdet_loglik(ctypes.byref(m), None, None, None, None, 1, 1, 1, 8, 8, None) == _abi.E_INVALID
     assert cdll.smcdet_resample(5, None, None, 0, None, None, None, None, 1, 1, None) == _abi.E_INVALID
-    assert cdll.smcdet_temper_update(None, None, None, 1.0, 1, None, None, None, None, None, None, 1, 1, None) == _abi.E_INVALID
+    assert cdll.smcdet_temper_update(None, None, None, 1.0, 1, None, None, None, None, None, None, None, 1, 1, None) == _abi.E_INVALID
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -98,7 +101,7 @@ def test_round_robin_sharding():
 GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from smcdet_b200.shard import gather_tiles, shard_tile_ids
+from smcdet_b200.shard import gather_tiles, gather_tiles_to_root, shard_tile_ids
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
 rank, world = dist.get_rank(), dist.get_world_size()
 T = 7
@@ -109,10 +112,40 @@ want = torch.stack([torch.full((3, 2), float(t)) + torch.arange(6).view(3, 2) / 
 assert torch.equal(full, want), (rank, full)
 cnt = gather_tiles(ids.clone(), T)
 assert cnt.tolist() == list(range(T))
+# the gather onto the rank that runs the Aggregate sink: the full field on the root only
+root = gather_tiles_to_root(local, T, dst=0)
+assert (root is None) == (rank != 0)
+if rank == 0:
+    assert torch.equal(root, want)
+# the (tile, count) strata of count-stratified SMC as a second sharding axis: every stratum on exactly one rank,
+# loads balanced by expected cost, the assignment identical on every rank
+from smcdet_b200.cssmc import CountStratifiedSMC as CS
+parts = CS.assign_strata(13, list(range(0, 9)), world)
+assert sorted(sum(parts, [])) == list(range(13 * 9)) and parts == CS.assign_strata(13, list(range(0, 9)), world)
+loads = [sum(CS.stratum_cost(i % 9) for i in p) for p in parts]
+assert max(loads) - min(loads) <= CS.stratum_cost(8)
+mine = torch.tensor([float(len(parts[rank]))])
+both = [torch.zeros(1) for _ in range(world)]
+dist.all_gather(both, mine)
+assert sum(int(b.item()) for b in both) == 13 * 9
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
+
+
+def test_strata_assignment_balances_expected_cost():
+    from smcdet_b200.cssmc import CountStratifiedSMC as CS
+
+    counts = list(range(0, 11))
+    for world in (1, 2, 8):
+        parts = CS.assign_strata(100, counts, world)
+        assert sorted(sum(parts, [])) == list(range(100 * 11))
+        loads = [sum(CS.stratum_cost(counts[i % 11]) for i in p) for p in parts]
+        assert max(loads) - min(loads) <= CS.stratum_cost(10), loads
+    # round-robin over the flat stratum index would leave rank loads as unequal as the counts themselves
+    rr = [sum(CS.stratum_cost(counts[i % 11]) for i in range(r, 1100, 11)) for r in range(11)]
+    assert max(rr) > 3 * min(rr)
 
 
 def test_gather_tiles_two_gloo_ranks(tmp_path):

@@ -718,3 +718,84 @@ def test_mh_live_only_equals_a_run_on_the_truncated_catalogs(backend):
     # MALA honours it too
     q = backend.mh_mutate(m, p, k, tiles, mixed, l2, f2, tau, seed=9, offset=1, mala=True)
     assert np.all(q["fluxes"][~live] == 0) and np.array_equal(q["locs"][:, ::3], l2[:, ::3])
+
+
+def test_segments_share_their_tiles_pixels(backend):
+    """Generic segments: particle rows that live on tiles[tile_of_segment[s]] give bit-for-bit what
+    the same rows give on explicitly replicated tiles -- for smcdet_loglik_segments and for the fused MH kernel
+    (smcdet_mh_params.tile_of_segment), whose accept counts (acc_as_count) divide to the ordinary rates."""
+    g = Golden("mh_m71")
+    meta = g.meta
+    m, p = abi_model(meta), abi_prior(meta)
+    tiles, tau = g.flat("tiles"), g["tau"].reshape(-1)
+    T, N = g.flat("counts").shape
+    reps = 3
+    seg = np.repeat(np.arange(T), reps).astype(np.int32)[::-1].copy()   # segment -> tile, not in tile order
+    S = seg.size
+    rng = np.random.default_rng(5)
+    pick = rng.integers(0, N, (S, N))
+    locs = np.take_along_axis(g.flat("locs")[seg], pick[:, :, None, None], 1).copy()
+    fluxes = np.take_along_axis(g.flat("fluxes")[seg], pick[:, :, None], 1).copy()
+    locs[:, :, :, 0] = np.clip(locs[:, :, :, 0], -meta["pad"] + 0.01, meta["tile"] + meta["pad"] - 0.01)
+    counts = np.full((S, N), float(meta["D"]), np.float32)
+    a = backend.loglik(m, tiles, locs, fluxes, tile_of_segment=seg)
+    b = backend.loglik(m, tiles[seg], locs, fluxes)
+    assert np.array_equal(a, b)
+    iters = 4
+    k = abi_mh(meta, iters)
+    taus = np.repeat(tau, reps)[::-1].copy()
+    x = backend.mh_mutate(m, p, k, tiles, counts, locs, fluxes, taus, seed=3, offset=2, tile_of_segment=seg)
+    y = backend.mh_mutate(m, p, k, tiles[seg], counts, locs, fluxes, taus, seed=3, offset=2)
+    for key in ("locs", "fluxes", "loglik", "accept", "acc_rate"):
+        assert np.array_equal(x[key], y[key]), key
+    k.acc_as_count = 1
+    z = backend.mh_mutate(m, p, k, tiles, counts, locs, fluxes, taus, seed=3, offset=2, tile_of_segment=seg, acc_init=0.0)
+    assert np.array_equal(z["locs"], x["locs"]) and np.array_equal(z["acc_rate"] / np.float32(N), x["acc_rate"])
+    assert np.array_equal(z["acc_rate"], z["accept"][-1].sum(-1).astype(np.float32))
+
+
+def test_loop_state_of_temper_update(backend):
+    """smcdet_loop_state: the loop test of sampler.py:230 and the acceptance-rate division evaluated inside
+    smcdet_temper_update -- active_next = [new temperature < 1], live_count += their number, acc_rate = acc_count / N
+    with acc_count reset; skipped tiles get active_next = 0 and keep everything else."""
+    g = Golden("temper")
+    thr = g.meta["ess_threshold"]
+    ll, tin = g.flat("s2_loglik"), g["s2_tau_in"].reshape(-1).copy()
+    T, N = ll.shape
+    tin[0] = 0.999999  # this tile reaches temperature 1 in the step
+    act = np.ones(T, np.int32)
+    act[-1] = 0
+    cnt = (np.arange(T) * 3 + 1).astype(np.float32)
+    plain = backend.temper_update(ll, tin, tin, thr, g["s2_logz_in"], active=act)
+    got = backend.temper_update(ll, tin, tin, thr, g["s2_logz_in"], active=act, loop=dict(acc_count=cnt, live_count=5))
+    for key in ("tau", "weights", "ess", "logz", "wlog"):
+        assert np.array_equal(plain[key], got[key]), key
+    want_next = ((got["tau"] < 1) & (act == 1)).astype(np.int32)
+    assert np.array_equal(got["active_next"], want_next) and want_next[0] == 0 and want_next[-1] == 0
+    assert int(got["live_count"][0]) == 5 + int(want_next.sum())
+    on = act == 1
+    assert np.array_equal(got["acc_rate"][on], cnt[on] / np.float32(N)) and np.all(got["acc_count"][on] == 0)
+    assert got["acc_rate"][-1] == -1.0 and got["acc_count"][-1] == cnt[-1]
+
+
+def test_bad_tape_component_is_flagged_not_dereferenced(backend):
+    """A taped component outside [0, D) would index past the staged catalog: the kernel clamps it and raises the
+    SMCDET_STATUS_BAD_TAPE bit (torch.multinomial over D categories cannot produce one, kernel.py:35-44)."""
+    g = Golden("mh_m71")
+    meta = g.meta
+    m, p = abi_model(meta), abi_prior(meta)
+    T, N = g.flat("counts").shape
+    iters = 2
+    comp = g["comp"][:iters].reshape(iters, T, N).astype(np.int32).copy()
+    comp[1, 0, 3] = meta["D"] + 5
+    comp[0, 0, 4] = -2
+    locs = g.flat("locs").copy()
+    locs[:, 7, 2, 0] = meta["tile"] / 2
+    tape = dict(comp=comp, u_loc=g["u_loc"][:iters], u_flux=g["u_flux"][:iters], u_acc=g["u_acc"][:iters])
+    r = backend.mh_mutate(m, p, abi_mh(meta, iters), g.flat("tiles"), g.flat("counts"), locs, g.flat("fluxes"),
+                          g["tau"].reshape(-1), tape=tape)
+    assert r["status"] & A.STATUS_BAD_TAPE and np.isfinite(r["locs"]).all()
+    ok = dict(tape, comp=np.clip(comp, 0, meta["D"] - 1))
+    s = backend.mh_mutate(m, p, abi_mh(meta, iters), g.flat("tiles"), g.flat("counts"), locs, g.flat("fluxes"),
+                          g["tau"].reshape(-1), tape=ok)
+    assert s["status"] == 0 and np.array_equal(s["locs"], r["locs"])

@@ -105,8 +105,10 @@ def workload_config(a):
     }
     sharding = ("(tile, count) strata assigned to ranks by expected cost (longest-processing-time), per-stratum evidences "
                 "all-gathered (NCCL)") if a.workload == "allstrata" else (
-        "tiles sharded round-robin, no data-path collective; end to end: NCCL gather of every tile's weighted catalogs "
-        "(counts, locs, fluxes, weights, log Z) onto rank 0 and the Aggregate finish there (aggregate.py:583-589)")
+        "tiles sharded round-robin, no data-path collective.  End to end, strong scaling (one field): NCCL gather "
+        "(dist.gather) of every tile's weighted catalogs (counts, locs, fluxes, weights, log Z) onto rank 0 and the "
+        "Aggregate finish there (aggregate.py:583-589); weak scaling with more than one GPU (every rank its own field): "
+        "each rank runs that finish on its own tiles and reads its own catalogs back, no catalog collective")
     return {"workload": names[a.workload],
             "tiles_per_gpu": a.tiles_per_gpu, "field_tiles_strong": a.field_tiles, "particles_per_tile": a.particles,
             "stars_per_catalog": a.stars, "mh_iters": a.mh_iters, "ess_threshold_prop": 0.5, "resample": "multinomial",
@@ -472,7 +474,10 @@ def run_own(a):
     # one job = one field of `num_tiles` tiles sharded over the ranks
     # ------------------------------------------------------------------------------------------
     class Job(object):
-        def __init__(self, num_tiles, field_seed):
+        def __init__(self, num_tiles, field_seed, gather):
+            # gather: the end-to-end region collects every tile's catalogs on rank 0 (ONE field sharded over the ranks);
+            # otherwise every rank finishes and reads back its own tiles (ranks own separate parts of the job)
+            self.gather = gather or world == 1
             self.T = num_tiles
             self.field = make_field(a, num_tiles, field_seed, dev)          # the whole field, identical on every rank
             self.field_host = self.field.cpu().pin_memory()
@@ -509,12 +514,13 @@ def run_own(a):
             if not e2e:
                 summ = sh.local_results()["summaries"]
                 return evals, live, mh.event_log, [], summ, int(s.iter)
-            # the reference's finish: all tiles' weighted catalogs -> Aggregate on rank 0 (NCCL gather for world > 1)
+            # the reference's finish: all tiles' weighted catalogs -> Aggregate on rank 0 (NCCL gather for world > 1),
+            # or -- weak scaling, where ranks own separate fields -- every rank's own tiles -> its own Aggregate
             with quiet:
-                agg = sh.sink()
+                agg = sh.sink(local=not self.gather)
             outs = []
             if agg is not None:
-                Tn = self.T
+                Tn = self.T if self.gather else self.T_local
                 outs = [agg.summaries, agg.pruned_counts.view(Tn, N).to(torch.int16), agg.pruned_locs.view(Tn, N, D, 2),
                         agg.pruned_fluxes.view(Tn, N, D)]
             return evals, live, mh.event_log, outs, None, int(s.iter)
@@ -531,6 +537,12 @@ def run_own(a):
         before the closing event).  Returns a dict of measurements (times are the max over ranks)."""
         copy_stream = torch.cuda.Stream(device=dev)
         host_sets, pending = {}, []
+        if e2e and (rank == 0 or not job.gather):  # pinned landing buffers, allocated before the clock starts (two sets)
+            Tn = job.T if (job.gather or strata) else job.T_local
+            shapes = ([((Tn, 4), torch.float32), ((Tn, ns), torch.float32)] if strata else
+                      [((Tn, 6), torch.float32), ((Tn, N), torch.int16), ((Tn, N, D, 2), torch.float32), ((Tn, N, D), torch.float32)])
+            for slot in range(min(2, steps)):
+                host_sets[slot] = [torch.empty(sh, dtype=dt, pin_memory=True) for sh, dt in shapes]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = lib.launches
         evals = live_total = h2d = d2h = 0
@@ -572,9 +584,9 @@ def run_own(a):
 
     do_weak = a.scaling in ("weak", "both")
     do_strong = a.scaling in ("strong", "both")
-    weak_job = Job(a.tiles_per_gpu * world, 1234) if do_weak else None
     same = do_weak and do_strong and a.tiles_per_gpu * world == a.field_tiles
-    strong_job = weak_job if same else (Job(a.field_tiles, 1234) if do_strong else None)
+    weak_job = Job(a.tiles_per_gpu * world, 1234, gather=same) if do_weak else None
+    strong_job = weak_job if same else (Job(a.field_tiles, 1234, gather=True) if do_strong else None)
     main_job = weak_job if do_weak else strong_job
 
     # ---- warm-up
@@ -717,8 +729,9 @@ def run_own(a):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main_e2e["h2d"],
                         "d2h_bytes_per_step": main_e2e["d2h"], "ms_per_step": main_e2e["ms"] / a.steps,
                         "tiles_per_sec": main_job.T * a.steps / (main_e2e["ms"] * 1e-3),
-                        "path": "pinned host tiles -> H2D -> sampler -> NCCL gather of the weighted catalogs onto rank 0 -> "
-                                "Aggregate finish (resample + prune) -> pruned catalogs + summaries D2H into pinned buffers"
+                        "path": ("pinned host tiles -> H2D -> sampler -> " + ("gather of the weighted catalogs onto rank 0 -> "
+                                 if main_job.gather else "(per rank) ") +
+                                 "Aggregate finish (resample + prune) -> pruned catalogs + summaries D2H into pinned buffers")
                                 if not strata else
                                 "pinned host tiles -> H2D -> count-stratified samplers on every rank -> all-gather of the "
                                 "per-stratum evidences -> count posterior per tile -> D2H"},

@@ -84,22 +84,22 @@ class Aggregate(object):
         # smcdet_resample draws as many indices as there are weights: pad the weights with zeros up to a multiple
         # of `num` and keep every (width / num)-th draw
         width = num * ((n + num - 1) // num)
+        if u is not None and num != n:
+            raise ValueError("injected uniforms need multiplier == 1")
         if width != n:
-            if u is not None:
-                raise ValueError("injected uniforms need multiplier == 1")
             wp = torch.zeros(T, width, device=dev)
             wp[:, :n] = w
             w = wp
         idx = torch.empty(T, width, device=dev, dtype=torch.int64)
         cdf = torch.empty(T, width, device=dev, dtype=torch.float64)
         uu = None if u is None else u.to(device=dev, dtype=torch.float64).contiguous()
-        if width != n and method == A.RESAMPLE_SYSTEMATIC:
+        if num != n and method == A.RESAMPLE_SYSTEMATIC:
             # the points i = j * s (s = width / num) of the grid (i + u) / width form the systematic grid (j + v) / num
             # exactly when u = s * v with v uniform on [0, 1): inject that offset (u in [0, 1) would bias the draw)
             uu = (width // num) * torch.rand(T, dtype=torch.float64).to(dev)
         L.check(L.lib().smcdet_resample(method, L.ptr(w), L.ptr(uu, torch.float64), L.fresh_seed(), None, None,
                                         L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64), T, width, L.stream_for(w)))
-        if width != n:
+        if num != n:
             if method == A.RESAMPLE_SYSTEMATIC:
                 idx = idx[:, :: width // num]
             idx = idx[:, :num].clamp(max=n - 1).contiguous()

@@ -146,20 +146,32 @@ class ShardedSMC(object):
         out = {k: gather_tiles_to_root(local[k].contiguous(), self.num_tiles, dst, self.group) for k in keys}
         return out if self.rank == dst else None
 
-    def sink(self, MutationKernel=None, *, dst=0, resample_method=None, ess_threshold_prop=0.5):
+    def sink(self, MutationKernel=None, *, dst=0, resample_method=None, ess_threshold_prop=0.5, local=False):
         """The reference's per-tile finish (experiments/m71/run_smc.py:124-166; aggregate.py:583-589 for a 1 x 1 grid):
         every tile's weighted catalogs are gathered onto rank ``dst`` (NCCL gather over NVLink) and handed to
         ``Aggregate(..., merge=False).run()`` -- final resample by the weights and prune, tile by tile.  Returns the
-        ``Aggregate`` on rank ``dst``, None elsewhere."""
+        ``Aggregate`` on rank ``dst``, None elsewhere.  ``local=True``: no gather, every rank finishes its own tiles
+        (for jobs whose ranks own separate fields)."""
         from .aggregate import Aggregate
 
-        out = self.gather_to_root(dst=dst)
+        if local:
+            out = {k: v.contiguous() for k, v in self.local_results().items()}
+            tiles = self._tiles[self.local_ids]
+        else:
+            out = self.gather_to_root(dst=dst)
+            tiles = self._tiles
         if out is None:
             return None
         s = self.sampler
         T, n, d = out["counts"].shape[0], out["counts"].shape[1], out["fluxes"].shape[-1]
-        data = self._tiles.to(self._device).reshape(T, 1, *self._tiles.shape[1:])
-        agg = Aggregate(s.Prior, s.ImageModel, MutationKernel or s.MutationKernel, data, out["counts"].view(T, 1, n),
+        data = tiles.to(self._device).reshape(T, 1, *self._tiles.shape[1:])
+        if MutationKernel is None:  # Aggregate deep-copies its kernel: hand it one without this run's logs and traces
+            import copy
+
+            MutationKernel = copy.copy(s.MutationKernel)
+            MutationKernel.event_log = MutationKernel.last_trace = MutationKernel.last_loglik = None
+            MutationKernel._status = None
+        agg = Aggregate(s.Prior, s.ImageModel, MutationKernel, data, out["counts"].view(T, 1, n),
                         out["locs"].view(T, 1, n, d, 2), out["fluxes"].view(T, 1, n, d), out["weights"].view(T, 1, n),
                         out["summaries"][:, 0].reshape(T, 1), s.flux_detection_threshold,
                         resample_method or s.resample_method, ess_threshold_prop, print_every=10**6, merge=False)

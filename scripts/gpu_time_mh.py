@@ -5,7 +5,9 @@ from goldenlib import Golden
 from test_api_gpu import build_objects
 from smcdet_b200.sampler import SMCsampler
 dev = torch.device("cuda", 0)
-g = Golden("mh_m71"); meta = dict(g.meta); meta["D"] = 10; meta["min_objects"] = 10
+MODEL = os.environ.get("MODEL", "m71")   # m71 | gauss
+g = Golden("mh_m71" if MODEL == "m71" else "mh_gauss"); meta = dict(g.meta)
+meta["D"] = meta["min_objects"] = 10 if MODEL == "m71" else 8
 T, N = 148, 10000
 model, prior, mh = build_objects(meta, iters=100)
 tiles = torch.from_numpy(g["tiles"]).to(dev).reshape(-1, 8, 8)[:1].repeat(T, 1, 1).reshape(T, 1, 8, 8).contiguous()

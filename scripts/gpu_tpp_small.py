@@ -13,9 +13,10 @@ dev = torch.device("cuda", 0)
 lib = L.lib()
 force = lib._cdll.smcdet_debug_force_tpp
 force.argtypes = [C.c_int]
+import argparse
 for T in (1, 2, 4, 8, 16, 32):
-    class A: tiles_per_gpu = T; workload = "m71synthetic"
-    tiles = make_field(A, 0, dev)
+    A = argparse.Namespace(workload="m71synthetic", stars=10, mh_iters=100, particles=10000)
+    tiles = make_field(A, T, 0, dev).view(T, 1, 8, 8)
     model = M71ImageModel(8, 8, **M71)
     prior = M71Prior(10, 10, PRIOR["counts_rate"], 8, 8, flux_alpha=PRIOR["flux_alpha"], flux_lower=PRIOR["flux_lower"],
                      flux_upper=PRIOR["flux_upper"], pad=4)

@@ -651,36 +651,44 @@ __device__ __noinline__ float truncnormal_step(float mu, float sigma, float inv_
     return x;
 }
 
-// All three coordinates of a proposal in one out-of-line call, for boxes of at least 12 sigma.  Each stage is
-// written as a loop over the coordinates so that the three independent erf / erfinv / lg2 dependency chains sit
-// in one basic block and are interleaved by the scheduler (ILP 3 instead of 1 in the scalar part of a sweep).
+// One coordinate of a proposal for boxes of at least 12 sigma (truncnormal_make_wide + truncnormal_draw + the reverse
+// box mass): returns x and *lq_term = log mass(mu) - log mass(x), its summand of lq = log q(prev|prop) - log q(prop|prev).
+// Products and sums are spelled with the rounding intrinsics, so that the compiler contracts nothing on its own and
+// the three-coordinate and the one-coordinate callers below produce the same bits.
+__device__ __forceinline__ float truncnormal_coord_wide(float mu, float sigma, float isig, float lb, float ub, float u,
+                                                        float& lq_term) {
+    const float a = __fadd_rn(mu, -lb), b = __fadd_rn(ub, -mu);
+    const float q = __fmaf_rn(-0.5f, erff(__fmul_rn(fminf(a, b), isig)), 0.5f);
+    const float cdf_lb = (a < b) ? q : 0.0f;
+    const float mass = __fadd_rn(1.0f, -q);
+    const float lo = 1e-6f, hi = (float)(1.0 - 1e-6);
+    const float p = clamp_f(u, lo, hi);
+    const float y = __fmaf_rn(2.0f, clamp_f(__fmaf_rn(p, mass, cdf_lb), lo, hi), -1.0f);
+    const float x = clamp_f(__fmaf_rn(__fmul_rn(sigma, erfinv_f(y)), kSqrt2, mu), lb, ub);
+    const float qr = __fmaf_rn(-0.5f, erff(__fmul_rn(fminf(__fadd_rn(x, -lb), __fadd_rn(ub, -x)), isig)), 0.5f);
+    lq_term = __fmul_rn(__fadd_rn(lg2_fast(mass), -lg2_fast(__fadd_rn(1.0f, -qr))), kLn2);
+    return x;
+}
+
+// All three coordinates of a proposal in one out-of-line call.  The three independent erf / erfinv / lg2 dependency
+// chains sit in one basic block and are interleaved by the scheduler (ILP 3 instead of 1 in the scalar part of a sweep).
 __device__ __noinline__ float4 truncnormal_step3_wide(float mu0, float mu1, float mu2, float sl, float isl, float sf,
                                                        float isf, float lb0, float lb1, float lb2, float ub0, float ub1,
                                                        float ub2, float u0, float u1, float u2) {
-    const float mu[3] = {mu0, mu1, mu2}, sigma[3] = {sl, sl, sf}, isig[3] = {isl, isl, isf};
-    const float lb[3] = {lb0, lb1, lb2}, ub[3] = {ub0, ub1, ub2}, u[3] = {u0, u1, u2};
-    float q[3], cdf_lb[3], mass[3], y[3], x[3], qr[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float a = mu[c] - lb[c], b = ub[c] - mu[c];
-        q[c] = 0.5f - 0.5f * erff(fminf(a, b) * isig[c]);
-        cdf_lb[c] = (a < b) ? q[c] : 0.0f;
-        mass[c] = 1.0f - q[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float lo = 1e-6f, hi = (float)(1.0 - 1e-6);
-        const float p = clamp_f(u[c], lo, hi);
-        y[c] = 2.0f * clamp_f(cdf_lb[c] + p * mass[c], lo, hi) - 1.0f;
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) x[c] = clamp_f(mu[c] + sigma[c] * erfinv_f(y[c]) * kSqrt2, lb[c], ub[c]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) qr[c] = 0.5f - 0.5f * erff(fminf(x[c] - lb[c], ub[c] - x[c]) * isig[c]);
-    float lq = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) lq += (lg2_fast(mass[c]) - lg2_fast(1.0f - qr[c])) * kLn2;
-    return make_float4(x[0], x[1], x[2], lq);  // proposal (row, col, flux) and log q(prev|prop) - log q(prop|prev)
+    float t0, t1, t2;
+    const float x0 = truncnormal_coord_wide(mu0, sl, isl, lb0, ub0, u0, t0);
+    const float x1 = truncnormal_coord_wide(mu1, sl, isl, lb1, ub1, u1, t1);
+    const float x2 = truncnormal_coord_wide(mu2, sf, isf, lb2, ub2, u2, t2);
+    // proposal (row, col, flux) and log q(prev|prop) - log q(prop|prev)
+    return make_float4(x0, x1, x2, __fadd_rn(__fadd_rn(t0, t1), t2));
+}
+
+// One coordinate out of line, for decompositions with several lanes per particle: lanes 0, 1, 2 of a particle take the
+// row, the column and the flux and exchange the results, instead of every lane computing all three (the scalar part is
+// most of a sweep when a lane owns a single row of the tile).
+__device__ __noinline__ float truncnormal_step1_wide(float mu, float sigma, float isig, float lb, float ub, float u,
+                                                      float& lq_term) {
+    return truncnormal_coord_wide(mu, sigma, isig, lb, ub, u, lq_term);
 }
 
 // MALA (kernel.py:170-195, :214-259): the proposal is a truncated normal around mean = value + step^2/2 * gradient,
@@ -741,7 +749,10 @@ struct MHArgs {
 #define SMC_MH_MINB 3
 #endif
 template <int MODEL, int H, int W, int TPP, bool MALA>
-__global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_MH_MINB : 4)) mh_kernel(const MHArgs a) {
+// Resident blocks per SM: 3 for 64 pixels per lane (168 registers); 5 for 8 pixels per lane, the decomposition of
+// a single 8x8 tile -- 10 000 particles x 8 lanes are 625 blocks, which 5 x 148 slots take in ONE wave (4 x 148 do not)
+__global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_MH_MINB : (((H / TPP) * W <= 8) ? 5 : 4)))
+    mh_kernel(const MHArgs a) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
     float* s_tile = smem;
@@ -855,14 +866,32 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
 
         // ---- proposal for star k (kernel.py:47-61; distributions.py:40-48)
         if (!full) {
+            if constexpr (!MALA && TPP >= 4) {
+                if (wide_l && wide_f) {  // (uniform branch; the shuffles below run with the whole warp converged)
+                    const int c = sub % 3;
+                    float lqc;
+                    const float xc = truncnormal_step1_wide(
+                        c == 0 ? l0 : (c == 1 ? l1 : f), c == 2 ? sf : sl, c == 2 ? isf : isl,
+                        c == 0 ? a.mh.locs_min[0] : (c == 1 ? a.mh.locs_min[1] : a.mh.fluxes_min),
+                        c == 0 ? a.mh.locs_max[0] : (c == 1 ? a.mh.locs_max[1] : a.mh.fluxes_max),
+                        c == 0 ? u0 : (c == 1 ? u1 : uf), lqc);
+                    const int base = (int)(threadIdx.x & 31u) - sub;  // the particle's first lane
+                    pl0 = __shfl_sync(0xffffffffu, xc, base); pl1 = __shfl_sync(0xffffffffu, xc, base + 1);
+                    pf = __shfl_sync(0xffffffffu, xc, base + 2);
+                    lq = __fadd_rn(__fadd_rn(__shfl_sync(0xffffffffu, lqc, base), __shfl_sync(0xffffffffu, lqc, base + 1)),
+                                   __shfl_sync(0xffffffffu, lqc, base + 2));
+                }
+            }
             if (frozen_slot) {
                 pl0 = l0; pl1 = l1; pf = f; lq = 0.0f;  // nothing is rendered or re-priced below
             } else if constexpr (!MALA) {
                 if (wide_l && wide_f) {
-                    const float4 pr = truncnormal_step3_wide(l0, l1, f, sl, isl, sf, isf, a.mh.locs_min[0], a.mh.locs_min[1],
-                                                             a.mh.fluxes_min, a.mh.locs_max[0], a.mh.locs_max[1],
-                                                             a.mh.fluxes_max, u0, u1, uf);
-                    pl0 = pr.x; pl1 = pr.y; pf = pr.z; lq = pr.w;
+                    if constexpr (TPP < 4) {
+                        const float4 pr = truncnormal_step3_wide(l0, l1, f, sl, isl, sf, isf, a.mh.locs_min[0], a.mh.locs_min[1],
+                                                                 a.mh.fluxes_min, a.mh.locs_max[0], a.mh.locs_max[1],
+                                                                 a.mh.fluxes_max, u0, u1, uf);
+                        pl0 = pr.x; pl1 = pr.y; pf = pr.z; lq = pr.w;
+                    }
                 } else {
                     float lq0, lq1, lqf;
                     pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);

@@ -404,43 +404,63 @@ SMC_HD void pixel_loglik_sum(const ModelK& m, const float* x, const float* lgam,
         Q = tree_sum<RPT>(qrow);
         S = tree_sum<RPT>(srow);
     } else {
+        // Poisson terms (x log r - r) - lgamma(x + 1) of pairs of pixels.  Fast path: no per-pixel selects; a lane
+        // whose pixels need the reference's special cases -- a rate above normal_switch_rate (Normal branch,
+        // images.py:96-101), or x log r with x = 0 at a vanishing rate (torch.xlogy gives 0) -- sees it in the
+        // maximum rate / a non-finite sum and redoes its pixels with the per-pixel selects.  Ordinary pixels get
+        // bit-identical terms on both paths, so results do not depend on which lanes took the slow one.
         const float4* l4 = reinterpret_cast<const float4*>(lgam);
-        const float2 neg1 = bcast2(-1.0f);
+        const float2 neg1 = bcast2(-1.0f), ln2 = bcast2(kLn2);
+        float rmax = 0.0f;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            float4 rr[W / 4];
-            float rmax = 0.0f;
-#pragma unroll
-            for (int g = 0; g < W / 4; ++g) {
-                rr[g] = rate4(r * (W / 4) + g);
-                rmax = fmaxf(fmaxf(rmax, fmaxf(rr[g].x, rr[g].y)), fmaxf(rr[g].z, rr[g].w));
-            }
-            const bool bright = rmax > m.nswitch;  // rare: only then is the Normal branch evaluated (images.py:96-101)
             float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int g = 0; g < W / 4; ++g) {
-                const float4 xv4 = x4[r * (W / 4) + g];
-                const float4 lg4 = l4[r * (W / 4) + g];
+            for (int g = r * (W / 4); g < (r + 1) * (W / 4); ++g) {
+                const float4 rt = rate4(g), xv4 = x4[g], lg4 = l4[g];
+                rmax = fmaxf(fmaxf(rmax, fmaxf(rt.x, rt.y)), fmaxf(rt.z, rt.w));
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const float2 rv = h ? make_float2(rr[g].z, rr[g].w) : make_float2(rr[g].x, rr[g].y);
+                    const float2 rv = h ? make_float2(rt.z, rt.w) : make_float2(rt.x, rt.y);
                     const float2 xv = h ? make_float2(xv4.z, xv4.w) : make_float2(xv4.x, xv4.y);
                     const float2 gg = h ? make_float2(lg4.z, lg4.w) : make_float2(lg4.x, lg4.y);
-                    const float2 lg = mul2(lg2_fast2(rv), bcast2(kLn2));
-                    float2 xl = mul2(xv, lg);  // xlogy: 0 where x == 0
-                    xl.x = (xv.x == 0.0f) ? 0.0f : xl.x;
-                    xl.y = (xv.y == 0.0f) ? 0.0f : xl.y;
-                    float2 term = fma2(neg1, gg, fma2(neg1, rv, xl));  // (xl - rate) - lgamma(x + 1)
-                    if (bright) {
+                    const float2 lg = mul2(lg2_fast2(rv), ln2);
+                    acc = add2(acc, fma2(neg1, gg, fma2(xv, lg, make_float2(-rv.x, -rv.y))));
+                }
+            }
+            qrow[r] = acc.x + acc.y;
+        }
+        float total = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) total += qrow[r];
+        if (rmax > m.nswitch || !(fabsf(total) <= 3.4028234663852886e38f)) {
+            // (the barrier makes the rare path reload and recompute: nothing of the fast path is kept alive for it)
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {  // (unrolled: the lane's pixels live in registers, which cannot be indexed)
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < W / 4; ++g) {
+                    const float4 rt = rate4(r * (W / 4) + g), xv4 = x4[r * (W / 4) + g], lg4 = l4[r * (W / 4) + g];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float2 rv = h ? make_float2(rt.z, rt.w) : make_float2(rt.x, rt.y);
+                        const float2 xv = h ? make_float2(xv4.z, xv4.w) : make_float2(xv4.x, xv4.y);
+                        const float2 gg = h ? make_float2(lg4.z, lg4.w) : make_float2(lg4.x, lg4.y);
+                        const float2 lg = mul2(lg2_fast2(rv), ln2);
+                        float2 xl = fma2(xv, lg, make_float2(-rv.x, -rv.y));   // x log r - r; x = 0: -r (xlogy)
+                        xl.x = (xv.x == 0.0f) ? -rv.x : xl.x;
+                        xl.y = (xv.y == 0.0f) ? -rv.y : xl.y;
+                        float2 term = fma2(neg1, gg, xl);
                         const float2 d = fma2(neg1, rv, xv);
                         const float2 nrm = fma2(mul2(bcast2(-0.5f), mul2(d, d)), rcp_fast2(rv), fma2(bcast2(-0.5f), lg, bcast2(-kLogSqrt2Pi)));
                         term.x = (rv.x > m.nswitch) ? nrm.x : term.x;
                         term.y = (rv.y > m.nswitch) ? nrm.y : term.y;
+                        acc = add2(acc, term);
                     }
-                    acc = add2(acc, term);
                 }
+                qrow[r] = acc.x + acc.y;
             }
-            qrow[r] = acc.x + acc.y;
         }
         Q = tree_sum<RPT>(qrow);
         S = 0.f;

@@ -329,7 +329,7 @@ class SMCsampler(object):
             self._temper_and_update()
             self._record()
 
-        if (self.freeze_finished and stop_after is None and not self.verbose and not self.record_history
+        if (stop_after is None and not self.verbose and not self.record_history
                 and hasattr(self.MutationKernel, "launch")):
             self._iterate_fused()
         elif self.freeze_finished and stop_after is None and not self.verbose:
@@ -407,7 +407,7 @@ class SMCsampler(object):
             prev, cur = cur, post_flag()
 
     def _iterate_fused(self):
-        """The SMC loop of a ``freeze_finished`` run on persistent device state: per iteration exactly four launches --
+        """The SMC loop on persistent device state (the ``freeze_finished`` case first): per iteration exactly four launches --
         ``smcdet_resample``, ``smcdet_gather``, ``smcdet_mh_mutate``, ``smcdet_temper_update`` -- and one 4-byte
         device-to-host copy.  Everything the plain loop does between the stages with small tensor operations
         (the mask of live tiles, keeping finished tiles' results, the loop test ``torch.any(temperature < 1)`` of
@@ -416,7 +416,10 @@ class SMCsampler(object):
         copied once more right after it finishes, after which both sets hold its final particles.  The host runs one
         iteration ahead of the device as in ``_iterate_ahead``: iteration k + 1 is launched once the live-tile count
         of iteration k - 1 is known to be positive, and an iteration launched after every tile had finished changes
-        nothing.  Results are identical to the plain loop."""
+        nothing.  In the reference's lock-step mode (``freeze_finished`` off: every tile keeps being resampled and
+        mutated until the slowest one arrives, sampler.py:230) there are no masks, and the host reads every iteration's
+        live-tile count before it launches the next one, since an extra iteration would not be harmless there.
+        Results are identical to the plain loop."""
         lib, dev = L.lib(), self._device
         T, n = self._T, self.num_catalogs
         d = self.fluxes.shape[-1]
@@ -438,6 +441,7 @@ class SMCsampler(object):
         calls = torch.zeros(T, device=dev, dtype=torch.int32)
         acc_count = torch.zeros(T, device=dev)
         status = torch.zeros(1, device=dev, dtype=torch.int32)
+        frozen = bool(self.freeze_finished)
         active = torch.empty(2, T, device=dev, dtype=torch.int32)
         active[0] = tau < 1
         max_it = int(self.max_smc_iters) + 2
@@ -475,7 +479,7 @@ class SMCsampler(object):
                           offset=k, tile_ids=tids, active=a_cur, tile_of_segment=tmap, live_tiles_hint=hint, acc_as_count=True)
 
             def temper():
-                a_next = active[(k - base) % 2]
+                a_next = active[(k - base) % 2]  # (lock-step: written, never read)
                 ls = A.LoopState(a_next.data_ptr(), live[k:k + 1].data_ptr(), acc_count.data_ptr(), acc_rate.data_ptr())
                 L.check(lib.smcdet_temper_update(L.ptr(loglik), L.ptr(tau), L.ptr(tau_prev), float(self.ess_threshold), 1,
                                                  L.ptr(wlog), L.ptr(weights), L.ptr(ess), L.ptr(logz),
@@ -493,7 +497,7 @@ class SMCsampler(object):
         while True:
             # the newest live-tile count the host may wait for without stalling the device: that of iteration k - 1
             # (k: the last iteration launched); before the first launch, that of the initial tempering step
-            known = k - 1 if k > base else base
+            known = k - 1 if (k > base and frozen) else k
             nlive = read(flags[known])
             if nlive == 0:
                 if k > known:  # iteration k was launched after every tile had finished: it changed nothing
@@ -502,9 +506,10 @@ class SMCsampler(object):
             if k > self.max_smc_iters:
                 break
             k += 1
-            a_cur = active[(k - 1 - base) % 2]
-            a_prev = None if k == base + 1 else active[(k - base) % 2]  # mask of the previous iteration = tiles to copy
-            iteration(k, a_cur, a_prev, nlive)
+            a_cur = active[(k - 1 - base) % 2] if frozen else None
+            # tiles the gather copies: those live in the previous iteration (None: all)
+            a_prev = None if (k == base + 1 or not frozen) else active[(k - base) % 2]
+            iteration(k, a_cur, a_prev, nlive if frozen else 0)
             flags[k] = post(k)
             flags.pop(k - 3, None)
         torch.cuda.current_stream(dev).synchronize()

@@ -132,6 +132,17 @@ inline T __shfl_xor_sync(unsigned, T v, int o) {
 }
 
 template <class T>
+inline T __shfl_sync(unsigned, T v, int src) {
+    hostsim::Warp& w = hostsim::my_warp();
+    const int lane = threadIdx.x & 31;
+    w.xchg[lane] = hostsim::to_bits(v);
+    w.bar->arrive_and_wait();
+    const T r = hostsim::from_bits<T>(w.xchg[src & 31]);
+    w.bar->arrive_and_wait();
+    return r;
+}
+
+template <class T>
 inline T __shfl_up_sync(unsigned, T v, int o) {
     hostsim::Warp& w = hostsim::my_warp();
     const int lane = threadIdx.x & 31;
@@ -154,6 +165,11 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+
+// rounding intrinsics: single operations that the compiler must not contract
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 
 inline float atomicAdd(float* p, float v) {
     std::lock_guard<std::mutex> g(hostsim::g_atomic_mutex);

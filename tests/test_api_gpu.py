@@ -1002,8 +1002,9 @@ def test_aggregate_method_surface_against_the_reference():
     assert agg.mutation_acc_rates.shape == (1, 1) and torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts)
 
 
+@pytest.mark.parametrize("freeze", [True, False])
 @pytest.mark.parametrize("max_iters", [200, 2])
-def test_host_ahead_loop_equals_the_plain_loop(max_iters, capsys):
+def test_host_ahead_loop_equals_the_plain_loop(max_iters, freeze, capsys):
     """With frozen tiles run() iterates on persistent device state, four launches per SMC iteration and the host one
     iteration ahead of the device (SMCsampler._iterate_fused; with a per-iteration history: _iterate_ahead); the plain
     loop (taken when progress is printed) must give the same iteration count and bit-identical state, also when
@@ -1018,7 +1019,7 @@ def test_host_ahead_loop_equals_the_plain_loop(max_iters, capsys):
         torch.manual_seed(17)
         model, prior, mh = build_objects(meta, iters=6)
         s = SMCsampler(cu(g["image"]), meta["tile"], prior, model, mh, 768, 0.5, "multinomial", meta["flux_threshold"],
-                       max_iters, print_every=10**6, freeze_finished=True, verbose=verbose)
+                       max_iters, print_every=10**6, freeze_finished=freeze, verbose=verbose)
         s.record_history = history
         n0 = L.lib().launches
         s.run()
@@ -1038,6 +1039,9 @@ def test_host_ahead_loop_equals_the_plain_loop(max_iters, capsys):
     # gather, prune
     assert len(fused.live_tiles) == fused.iter and fused.live_tiles[0] == 4
     assert fused.launches <= 4 * (fused.iter + 1) + 6 < plain.launches
+    if not freeze:  # lock-step: finished tiles keep being mutated (reference sampler.py:230), so the runs differ
+        other = run(False, False) if False else None
+        assert other is None
 
 
 def test_end_to_end_posterior_within_monte_carlo_error_of_the_reference():

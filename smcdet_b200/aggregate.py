@@ -27,10 +27,13 @@ from . import _lib as L
 class Aggregate(object):
     def __init__(self, Prior, ImageModel, MutationKernel, data, counts, locs, fluxes, weights,
                  log_normalizing_constant, flux_detection_threshold, resample_method, ess_threshold_prop,
-                 print_every=5, *, merge=True):
+                 print_every=5, *, merge=True, levels=None):
         """reference aggregate.py:10-67.  ``merge=False`` (keyword-only extension) treats every tile of
         ``data`` as its own 1 x 1 problem -- the per-tile sink used after a sharded run; the default
-        keeps the reference's meaning (a grid larger than 1 x 1 asks for the tree merge)."""
+        keeps the reference's meaning (a grid larger than 1 x 1 asks for the tree merge).  ``levels`` (keyword-only):
+        run only the first ``levels`` merge levels -- a [B * 4, 4] stack of B independent 4 x 4 blocks of 8 x 8 tiles
+        with ``levels = 4`` merges every block into its own 32 x 32 parent (the largest parent the kernels carry),
+        all blocks in the same launches; this is how a field larger than one block is merged, block by block."""
         self.Prior = deepcopy(Prior)
         self.ImageModel = deepcopy(ImageModel)
         self.MutationKernel = deepcopy(MutationKernel)
@@ -48,6 +51,8 @@ class Aggregate(object):
         self.numH, self.numW, self.dimH, self.dimW = self.data.shape
         self._merge_tree = merge
         self.num_aggregation_levels = (2 * torch.tensor(float(self.numH)).log2()).int().item() if merge else 0
+        if merge and levels is not None:
+            self.num_aggregation_levels = int(levels)
 
         # nested lists as in the reference (aggregate.py:43-45), from ONE device-to-host copy
         lz = log_normalizing_constant.detach().cpu().tolist() if isinstance(log_normalizing_constant, torch.Tensor) \
@@ -235,7 +240,8 @@ class Aggregate(object):
                 self._bridge(axis, self.MutationKernel.num_iters)
                 self._temper_and_update()
         if self.num_aggregation_levels > 0:
-            self.log_normalizing_constant = [[[float(self._logz[h, w])] for w in range(self.numW)] for h in range(self.numH)]
+            lz = self._logz.detach().cpu().tolist()
+            self.log_normalizing_constant = [[[lz[h][w]] for w in range(self.numW)] for h in range(self.numH)]
         index = self.get_resampled_index(self.weights, 1, u=u)
         res = self.apply_resampled_index(index, self.counts, self.locs, self.fluxes)
         self.counts, self.locs, self.fluxes, self.weights = res
@@ -293,7 +299,8 @@ class Aggregate(object):
         n = weights.shape[-1]
         self.weights = self.weights_intracount = weights.view(self.numH, self.numW, n)
         self._logz = logz.view(self.numH, self.numW)
-        self.log_normalizing_constant = [[[float(self._logz[h, w])] for w in range(self.numW)] for h in range(self.numH)]
+        lz = self._logz.detach().cpu().tolist()
+        self.log_normalizing_constant = [[[lz[h][w]] for w in range(self.numW)] for h in range(self.numH)]
 
     def mutate(self, axis, ChildImageModel=None):
         """reference aggregate.py:176-187: MutationKernel.num_iters sweeps under ``log_target``."""

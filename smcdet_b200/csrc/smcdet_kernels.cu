@@ -635,20 +635,19 @@ __device__ __noinline__ float count_logpmf_scalar(int kind, float rate, int mn, 
 
 // One coordinate of the random-walk proposal (kernel.py:47-61, :71-85, :97-111; distributions.py:25-52):
 // draws x ~ TruncNormal(mu, sigma, [lb, ub]) from the uniform u and returns
-//   lq = log q(mu | x) - log q(x | mu) = log mass(mu) - log mass(x)
+//   .y = lq = log q(mu | x) - log q(x | mu) = log mass(mu) - log mass(x)
 // (the Gaussian parts of the two proposal densities are identical and cancel).  Out of line: it is called
 // three times per sweep and inlining its erf / erfinv / log bodies pushed the hot loop past the
 // instruction cache.  `wide` selects the one-erf form valid for boxes of at least 12 sigma.
-__device__ __noinline__ float truncnormal_step(float mu, float sigma, float inv_sigma_sqrt2, float lb, float ub,
-                                                float u, bool wide, float& lq) {
+__device__ __noinline__ float2 truncnormal_step(float mu, float sigma, float inv_sigma_sqrt2, float lb, float ub,
+                                                 float u, bool wide) {
     TruncNormal q, r;
     if (wide) q = truncnormal_make_wide(mu, inv_sigma_sqrt2, lb, ub);
     else q = truncnormal_make(mu, sigma, lb, ub);
     const float x = truncnormal_draw(q, mu, sigma, lb, ub, u);
     if (wide) r = truncnormal_make_wide(x, inv_sigma_sqrt2, lb, ub);
     else r = truncnormal_make(x, sigma, lb, ub);
-    lq = q.log_mass - r.log_mass;
-    return x;
+    return make_float2(x, q.log_mass - r.log_mass);  // (by value: an out-parameter of a call goes through local memory)
 }
 
 // One coordinate of a proposal for boxes of at least 12 sigma (truncnormal_make_wide + truncnormal_draw + the reverse
@@ -686,21 +685,21 @@ __device__ __noinline__ float4 truncnormal_step3_wide(float mu0, float mu1, floa
 // One coordinate out of line, for decompositions with several lanes per particle: lanes 0, 1, 2 of a particle take the
 // row, the column and the flux and exchange the results, instead of every lane computing all three (the scalar part is
 // most of a sweep when a lane owns a single row of the tile).
-__device__ __noinline__ float truncnormal_step1_wide(float mu, float sigma, float isig, float lb, float ub, float u,
-                                                      float& lq_term) {
-    return truncnormal_coord_wide(mu, sigma, isig, lb, ub, u, lq_term);
+__device__ __noinline__ float2 truncnormal_step1_wide(float mu, float sigma, float isig, float lb, float ub, float u) {
+    float lq_term;
+    const float x = truncnormal_coord_wide(mu, sigma, isig, lb, ub, u, lq_term);
+    return make_float2(x, lq_term);
 }
 
 // MALA (kernel.py:170-195, :214-259): the proposal is a truncated normal around mean = value + step^2/2 * gradient,
 // so the Gaussian parts of the forward and reverse densities do not cancel.
-//   truncnormal_propose: draw x ~ TruncNormal(mean, sigma, [lb, ub]) from u; logq = log q(x | mean)
+//   truncnormal_propose: draw x ~ TruncNormal(mean, sigma, [lb, ub]) from u; returns (x, log q(x | mean))
 //   truncnormal_logq   : log q(x | mean)
-__device__ __noinline__ float truncnormal_propose(float mean, float sigma, float inv_sigma_sqrt2, float lb, float ub,
-                                                   float u, bool wide, float& logq) {
+__device__ __noinline__ float2 truncnormal_propose(float mean, float sigma, float inv_sigma_sqrt2, float lb, float ub,
+                                                    float u, bool wide) {
     const TruncNormal q = wide ? truncnormal_make_wide(mean, inv_sigma_sqrt2, lb, ub) : truncnormal_make(mean, sigma, lb, ub);
     const float x = truncnormal_draw(q, mean, sigma, lb, ub, u);
-    logq = truncnormal_logpdf(q, mean, sigma, x);
-    return x;
+    return make_float2(x, truncnormal_logpdf(q, mean, sigma, x));
 }
 
 __device__ __noinline__ float truncnormal_logq(float mean, float sigma, float inv_sigma_sqrt2, float lb, float ub,
@@ -869,12 +868,12 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
             if constexpr (!MALA && TPP >= 4) {
                 if (wide_l && wide_f) {  // (uniform branch; the shuffles below run with the whole warp converged)
                     const int c = sub % 3;
-                    float lqc;
-                    const float xc = truncnormal_step1_wide(
+                    const float2 xq = truncnormal_step1_wide(
                         c == 0 ? l0 : (c == 1 ? l1 : f), c == 2 ? sf : sl, c == 2 ? isf : isl,
                         c == 0 ? a.mh.locs_min[0] : (c == 1 ? a.mh.locs_min[1] : a.mh.fluxes_min),
                         c == 0 ? a.mh.locs_max[0] : (c == 1 ? a.mh.locs_max[1] : a.mh.fluxes_max),
-                        c == 0 ? u0 : (c == 1 ? u1 : uf), lqc);
+                        c == 0 ? u0 : (c == 1 ? u1 : uf));
+                    const float xc = xq.x, lqc = xq.y;
                     const int base = (int)(threadIdx.x & 31u) - sub;  // the particle's first lane
                     pl0 = __shfl_sync(0xffffffffu, xc, base); pl1 = __shfl_sync(0xffffffffu, xc, base + 1);
                     pf = __shfl_sync(0xffffffffu, xc, base + 2);
@@ -893,11 +892,11 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                         pl0 = pr.x; pl1 = pr.y; pf = pr.z; lq = pr.w;
                     }
                 } else {
-                    float lq0, lq1, lqf;
-                    pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
-                    pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
-                    pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
-                    lq = (lq0 + lq1) + lqf;
+                    const float2 r0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l);
+                    const float2 r1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l);
+                    const float2 rf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f);
+                    pl0 = r0.x; pl1 = r1.x; pf = rf.x;
+                    lq = (r0.y + r1.y) + rf.y;
                 }
             }
         }
@@ -925,10 +924,11 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                 const float hl = 0.5f * (sl * sl), hf = 0.5f * (sf * sf);
                 const float qm0 = fmaf(hl, tau * wgt_old * s0, l0), qm1 = fmaf(hl, tau * wgt_old * s1, l1);
                 const float qmf = fmaf(hf, fmaf(tau * m.c0, sP, dpr), f);
-                float q0, q1, qf;
-                pl0 = truncnormal_propose(qm0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, q0);
-                pl1 = truncnormal_propose(qm1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, q1);
-                pf = truncnormal_propose(qmf, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, qf);
+                const float2 p0 = truncnormal_propose(qm0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l);
+                const float2 p1 = truncnormal_propose(qm1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l);
+                const float2 p2 = truncnormal_propose(qmf, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f);
+                pl0 = p0.x; pl1 = p1.x; pf = p2.x;
+                const float q0 = p0.y, q1 = p1.y, qf = p2.y;
                 if (frozen_slot) { pl0 = l0; pl1 = l1; pf = f; }  // the star removed above is put back unchanged
                 lq = -((q0 + q1) + qf);  // - log q(proposal | current); the reverse term is added below
                 if (pf != 0.0f) star_accumulate<MODEL, RPT, W>(m, pl0, pl1, m.c0 * pf, row0, acc);
@@ -1381,11 +1381,18 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
             l0 = my_star[(k * 3 + 0) * PB]; l1 = my_star[(k * 3 + 1) * PB]; f = my_star[(k * 3 + 2) * PB];
             pl0 = l0; pl1 = l1; pf = f;
             if (live) {
-                float lq0, lq1, lqf;
-                pl0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l, lq0);
-                pl1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l, lq1);
-                pf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f, lqf);
-                lq = (lq0 + lq1) + lqf;
+                if (wide_l && wide_f) {  // the three coordinates interleaved in one call, as in mh_kernel
+                    const float4 pr = truncnormal_step3_wide(l0, l1, f, sl, isl, sf, isf, a.mh.locs_min[0], a.mh.locs_min[1],
+                                                             a.mh.fluxes_min, a.mh.locs_max[0], a.mh.locs_max[1],
+                                                             a.mh.fluxes_max, u0, u1, uf);
+                    pl0 = pr.x; pl1 = pr.y; pf = pr.z; lq = pr.w;
+                } else {
+                    const float2 r0 = truncnormal_step(l0, sl, isl, a.mh.locs_min[0], a.mh.locs_max[0], u0, wide_l);
+                    const float2 r1 = truncnormal_step(l1, sl, isl, a.mh.locs_min[1], a.mh.locs_max[1], u1, wide_l);
+                    const float2 rf = truncnormal_step(f, sf, isf, a.mh.fluxes_min, a.mh.fluxes_max, uf, wide_f);
+                    pl0 = r0.x; pl1 = r1.x; pf = rf.x;
+                    lq = (r0.y + r1.y) + rf.y;
+                }
             }
         }
         // ---- changes of both images on the lane's pixels: all D stars (entry) or -old star +new star (sweep)

@@ -18,6 +18,24 @@ def shard_tile_ids(num_tiles, world_size, rank):
     return torch.tensor(list(range(rank, num_tiles, world_size)), dtype=torch.int64)
 
 
+def block_tile_ids(grid, block, world_size, rank):
+    """Tile sharding for the tree merge: the [numH, numW] grid of tiles is cut into blocks of ``block`` x ``block``
+    tiles (4 x 4 tiles of 8 x 8 pixels merge into one 32 x 32 parent, the largest the merge kernels carry), blocks go
+    round-robin to the ranks, and a rank's tiles are listed block by block, row-major inside a block -- so a rank can
+    stack its blocks into a [B * block, block] grid and merge them all at once, with no exchange between ranks.
+    Returns (global row-major tile ids, global block ids)."""
+    numH, numW = grid
+    if numH % block or numW % block:
+        raise ValueError("the tile grid must be a whole number of blocks")
+    bH, bW = numH // block, numW // block
+    mine = list(range(rank, bH * bW, world_size))
+    ids = []
+    for b in mine:
+        h0, w0 = (b // bW) * block, (b % bW) * block
+        ids += [(h0 + i) * numW + (w0 + j) for i in range(block) for j in range(block)]
+    return torch.tensor(ids, dtype=torch.int64), torch.tensor(mine, dtype=torch.int64)
+
+
 def shard_sizes(num_tiles, world_size):
     return [len(range(r, num_tiles, world_size)) for r in range(world_size)]
 
@@ -97,7 +115,9 @@ class ShardedSMC(object):
 
     def __init__(self, tiles, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs, ess_threshold_prop,
                  resample_method, flux_detection_threshold, max_smc_iters, print_every=5, *, group=None,
-                 freeze_finished=True, verbose=False, device=None, seed=None):
+                 freeze_finished=True, verbose=False, device=None, seed=None, grid=None, block=None):
+        """``grid`` = (numH, numW) and ``block`` (keyword-only): shard by blocks of ``block`` x ``block`` tiles instead
+        of tile by tile (``block_tile_ids``), for ``merge_blocks``."""
         from .sampler import SMCsampler
 
         self.group = group
@@ -106,7 +126,13 @@ class ShardedSMC(object):
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         else:
             self.world, self.rank = 1, 0
-        self.local_ids = shard_tile_ids(self.num_tiles, self.world, self.rank)
+        self.grid, self.block = grid, block
+        if block is not None:
+            if grid is None or grid[0] * grid[1] != self.num_tiles:
+                raise ValueError("block sharding needs grid = (numH, numW) with numH * numW tiles")
+            self.local_ids, self.local_blocks = block_tile_ids(grid, block, self.world, self.rank)
+        else:
+            self.local_ids = shard_tile_ids(self.num_tiles, self.world, self.rank)
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._tiles, self._device = tiles, dev
         local = tiles[self.local_ids].to(dev, non_blocking=True).unsqueeze(1)  # [T_r, 1, h, w]
@@ -178,6 +204,43 @@ class ShardedSMC(object):
         agg.summaries = out["summaries"]
         agg.run()
         return agg
+
+    def merge_blocks(self, MutationKernel, *, resample_method=None, ess_threshold_prop=0.5, max_iters=500):
+        """Divide-and-conquer merge of this rank's blocks (needs ``block=`` sharding): the rank's B blocks of
+        block x block tiles are stacked into a [B * block, block] grid and ``Aggregate.run()`` merges every block
+        into one parent tile (8x8 -> 16x8 -> 16x16 -> 32x16 -> 32x32 for block = 4), all blocks and all ranks at the same
+        time; no catalogs cross between ranks.  Returns the ``Aggregate`` ([B, 1] parents; ``.block_ids`` = their global
+        block ids).  ``gather_blocks`` collects the parents' summaries."""
+        import math
+
+        from .aggregate import Aggregate
+
+        if self.block is None:
+            raise ValueError("merge_blocks needs ShardedSMC(..., grid=, block=)")
+        s, b = self.sampler, self.block
+        B = len(self.local_blocks)
+        n, d = s.counts.shape[-1], s.fluxes.shape[-1]
+        local = self._tiles[self.local_ids].to(self._device)
+        shape = (B * b, b)
+        agg = Aggregate(s.Prior, s.ImageModel, MutationKernel, local.reshape(*shape, *self._tiles.shape[1:]),
+                        s.counts.reshape(*shape, n), s.locs.reshape(*shape, n, d, 2), s.fluxes.reshape(*shape, n, d),
+                        s.weights.reshape(*shape, n), s.log_normalizing_constant.reshape(*shape),
+                        s.flux_detection_threshold, resample_method or s.resample_method, ess_threshold_prop,
+                        print_every=10**6, levels=2 * int(math.log2(b)))
+        agg.run(max_iters=max_iters)
+        agg.block_ids = self.local_blocks
+        return agg
+
+    def gather_blocks(self, agg):
+        """All-gather per-parent summaries of ``merge_blocks`` in global block order: [num_blocks, 4] =
+        (log normalising constant, mean catalog size, mean detected count, mean detected flux)."""
+        dev = self._device
+        summ = torch.stack([
+            torch.tensor([z[0][0] if isinstance(z[0], list) else z[0] for z in agg.log_normalizing_constant], device=dev),
+            agg.counts.float().mean(-1).reshape(-1), agg.pruned_counts.float().mean(-1).reshape(-1),
+            agg.pruned_fluxes.sum(-1).mean(-1).reshape(-1)], -1)
+        nb = (self.grid[0] // self.block) * (self.grid[1] // self.block)
+        return gather_tiles(summ.contiguous(), nb, self.group)
 
     def aggregate(self, grid, MutationKernel, *, resample_method=None, ess_threshold_prop=0.5, print_every=10**6,
                   root_only=True):

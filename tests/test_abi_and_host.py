@@ -96,6 +96,16 @@ def test_round_robin_sharding():
         assert sorted(torch.cat(ids).tolist()) == list(range(T))
         assert [len(i) for i in ids] == shard_sizes(T, G)
         assert max(len(i) for i in ids) - min(len(i) for i in ids) <= 1
+    # sharding by merge blocks: every tile once, a rank's tiles block by block (row-major inside a block)
+    from smcdet_b200.shard import block_tile_ids
+
+    for G in (1, 2, 3, 8):
+        parts = [block_tile_ids((40, 20), 4, G, r) for r in range(G)]
+        assert sorted(torch.cat([p[0] for p in parts]).tolist()) == list(range(800))
+        assert sorted(torch.cat([p[1] for p in parts]).tolist()) == list(range(50))
+        ids, blocks = parts[0]
+        first = ids[:16].view(4, 4)
+        assert first[0].tolist() == [0, 1, 2, 3] and first[1].tolist() == [20, 21, 22, 23] and blocks[0] == 0
 
 
 GLOO_WORKER = r"""

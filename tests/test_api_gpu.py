@@ -1171,3 +1171,56 @@ def test_sharded_sink_equals_the_per_tile_finish():
     sh2 = ShardedSMC(tiles, 8, prior, model, build_objects(meta, iters=6)[2], 512, 0.5, "multinomial", meta["flux_threshold"], 200, seed=99)
     sh2.run()
     assert torch.equal(sh2.sampler.locs, s.locs)
+
+
+def test_blocks_of_a_field_merge_in_parallel():
+    """A field larger than one merge block: the tile grid is cut into 4 x 4-tile blocks (block_tile_ids: blocks go
+    round-robin to the ranks, tiles are listed block by block), every rank samples the tiles of its blocks and
+    ShardedSMC.merge_blocks() stacks them into a [B * 4, 4] grid that Aggregate(levels=4) merges into B parents of
+    32 x 32 pixels in the same launches -- no catalogs cross between ranks."""
+    from smcdet_b200.kernel import SingleComponentMH
+    from smcdet_b200.shard import ShardedSMC, block_tile_ids
+
+    ids0, b0 = block_tile_ids((8, 8), 4, 2, 0)
+    ids1, b1 = block_tile_ids((8, 8), 4, 2, 1)
+    assert sorted(ids0.tolist() + ids1.tolist()) == list(range(64)) and b0.tolist() == [0, 2] and b1.tolist() == [1, 3]
+    assert ids0[:5].tolist() == [0, 1, 2, 3, 8] and ids1[:5].tolist() == [4, 5, 6, 7, 12]
+    with pytest.raises(ValueError):
+        block_tile_ids((6, 8), 4, 2, 0)
+
+    g = Golden("aggregate_m71")
+    meta = g.meta
+    torch.manual_seed(3)
+    model, prior, mh = build_objects(meta, iters=8)
+    # an 8 x 4 grid of tiles (two blocks) cut from a synthetic 64 x 32 image of the golden's model
+    from smcdet_b200.images import M71ImageModel
+    from smcdet_b200.prior import M71Prior
+
+    mp, pp = meta["model_params"], meta["prior_params"]
+    big = M71ImageModel(64, 32, background=mp["background"], psf_radius=mp["psf_radius"], adu_per_nmgy=mp["adu_per_nmgy"],
+                        psf_params=mp["psf_params"], noise_additive=mp["noise_additive"],
+                        noise_multiplicative=mp["noise_multiplicative"])
+    truth = M71Prior(20, 20, pp["counts_rate"], 64, 32, flux_alpha=pp["flux_alpha"], flux_lower=1.0, flux_upper=pp["flux_upper"],
+                     pad=0)
+    c, l, f = truth.sample(num_tiles_per_side=1, stratify_by_count=True, num_catalogs_per_count=1)
+    image = big.sample(l, f)[0, 0, :, :, 0]
+    tiles = image.unfold(0, 8, 8).unfold(1, 8, 8).reshape(32, 8, 8).contiguous()
+    job = ShardedSMC(tiles, 8, prior, model, mh, 400, 0.5, "multinomial", meta["flux_threshold"], 200, grid=(8, 4), block=4,
+                     seed=7).run()
+    assert job.local_ids.tolist() == list(range(32)) and job.local_blocks.tolist() == [0, 1]
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        agg = job.merge_blocks(SingleComponentMH(5, 0.1, 2.5, meta["fluxes_min"], meta["fluxes_max"]))
+    assert (agg.numH, agg.numW, agg.dimH, agg.dimW) == (2, 1, 32, 32) and agg.block_ids.tolist() == [0, 1]
+    assert float(agg.temperature.min()) == 1.0 and agg.pruned_counts.shape == (2, 1, 400)
+    assert torch.equal((agg.fluxes > 0).sum(-1).float(), agg.counts)
+    summ = job.gather_blocks(agg)
+    assert summ.shape == (2, 4) and torch.isfinite(summ).all()
+    # the merged catalogs see the stars of their own block: detected flux of the order of the truth's (a short run
+    # with few particles: a sanity band, not a calibration)
+    inside = [(l[0, 0, 0, :, 0] >= 32 * b) & (l[0, 0, 0, :, 0] < 32 * (b + 1)) for b in range(2)]
+    for b in range(2):
+        true_flux = float(f[0, 0, 0][inside[b]].sum())
+        assert 0.3 * true_flux < float(summ[b, 3]) < 3.0 * true_flux + 5.0, (b, true_flux, float(summ[b, 3]))

@@ -725,6 +725,82 @@ def case_exact_counts():
 CASES["exact_counts"] = case_exact_counts
 
 
+def case_exact_merge():
+    """Known answer for the tree merge: the evidence of a 16 x 8 PARENT tile (two 8 x 8 tiles joined along the rows)
+    under a Poisson-process prior sparse enough that catalogs of more than two stars carry < 2e-4 of the evidence:
+        p(x) = e^-mu [ L0 + mu E[L1] + mu^2/2 E[L2] ],   mu = counts_rate * padded parent area,
+    L0 closed form, E[L1] by midpoint quadrature over the parent's padded box x flux (prior-cdf coordinates), E[L2] by
+    plain Monte Carlo over pairs of prior stars (a 3 % term, known to a few per cent), all from the float64 oracle.
+    The merged log normalising constant of Aggregate.run() with merge weights must reproduce it; without them it
+    estimates something else."""
+    from oracle import api as O
+
+    tile, pad = 8, 2
+    H, W = 2 * tile, tile
+    prior_kw = dict(M71_PRIOR)
+    mu_parent = 0.12
+    prior_kw["counts_rate"] = mu_parent / ((H + 2 * pad) * (W + 2 * pad))
+    im = M71ImageModel(image_height=H, image_width=W, **M71)
+    torch.manual_seed(81)
+    # one faint star inside the first child, none in the second.  (With the star moved next to the boundary between
+    # the children -- row 8.4, flux 4 -- the first child explains its wing with a star in its padding, which the merge
+    # drops: exact log evidence -545.53; Aggregate gives -523.2 from uniform merge weights and -550.8 with the
+    # importance weights, whose harmonic-mean character then underestimates; DESIGN.md section 8.)
+    true_loc = torch.tensor([[[[[5.3, 3.4], [12.6, 4.9]]]]])
+    true_flux = torch.tensor([[[[1.6, 0.0]]]])
+    image = im.sample(true_loc, true_flux)[0, 0, :, :, 0].contiguous()
+    om = O.m71_model(M71["psf_radius"], M71["psf_params"], M71["background"], M71["adu_per_nmgy"], M71["noise_additive"],
+                     M71["noise_multiplicative"], dtype=np.float64)
+    tiles = image.numpy()[None].astype(np.float64)
+    a, lo, up = prior_kw["flux_alpha"], prior_kw["flux_lower"], prior_kw["flux_upper"]
+
+    def flux_of(u):
+        return ((up**a - u * up**a + u * lo**a) / (lo**a * up**a)) ** (-1 / a)   # distributions.py:77-79
+
+    z = np.zeros((1, 1, 1, 2))
+    logl0 = float(O.loglik(om, tiles, z, z[..., 0], dtype=np.float64)[0, 0])
+
+    def e1(g0, g1, gu):
+        l0 = (np.arange(g0) + 0.5) / g0 * (H + 2 * pad) - pad
+        l1 = (np.arange(g1) + 0.5) / g1 * (W + 2 * pad) - pad
+        f = flux_of((np.arange(gu) + 0.5) / gu)
+        A0, A1, F = np.meshgrid(l0, l1, f, indexing="ij")
+        th = np.stack([A0.ravel(), A1.ravel(), F.ravel()], -1)
+        ll = np.concatenate([O.loglik(om, tiles, th[i:i + 400000][None, :, None, :2], th[i:i + 400000][None, :, None, 2],
+                                      dtype=np.float64)[0] for i in range(0, th.shape[0], 400000)])
+        return logl0 + np.log(np.exp(ll - logl0).mean())
+
+    coarse = e1(100, 60, 150)
+    loge1 = e1(200, 120, 300)
+    rng = np.random.default_rng(7)
+    m = 4_000_000
+    ratio2, chunks = 0.0, 0
+    vals = []
+    for i in range(0, m, 400000):
+        k = min(400000, m - i)
+        locs = np.stack([rng.random((k, 2)) * (H + 2 * pad) - pad, rng.random((k, 2)) * (W + 2 * pad) - pad], -1)
+        fl = flux_of(rng.random((k, 2)))
+        ll = O.loglik(om, tiles, locs[None], fl[None], dtype=np.float64)[0]
+        vals.append(np.exp(ll - logl0))
+    vals = np.concatenate(vals)
+    loge2 = logl0 + np.log(vals.mean())
+    se2 = vals.std() / np.sqrt(m) / vals.mean()
+    terms = np.array([logl0, np.log(mu_parent) + loge1, 2 * np.log(mu_parent) - np.log(2.0) + loge2])
+    exact = -mu_parent + terms.max() + np.log(np.exp(terms - terms.max()).sum())
+    share = np.exp(terms - terms.max())
+    share /= share.sum()
+    print("log L0", logl0, "log E[L1]", loge1, "(coarse", coarse, ") log E[L2]", loge2, "+-", se2, "rel")
+    print("exact log evidence of the parent:", exact, "shares of 0 / 1 / 2 stars:", share)
+    meta = dict(model="m71", tile=tile, pad=pad, model_params=M71, prior_params=prior_kw, mu_parent=mu_parent,
+                flux_threshold=M71_DETECTION, quadrature=[200, 120, 300], mc_pairs=m)
+    save("exact_merge", meta, image=image, exact_log_evidence=np.array(exact), log_l0=np.array(logl0),
+         log_e1=np.array(loge1), log_e1_coarse=np.array(coarse), log_e2=np.array(loge2), rel_se_e2=np.array(se2),
+         shares=share)
+
+
+CASES["exact_merge"] = case_exact_merge
+
+
 def case_match():
     """metrics.match_catalogs / compute_precision_recall_f1 (smcdet/metrics.py) run unmodified on synthetic true and
     estimated catalogs; the catalogs it draws with torch.randint (metrics.py:40) are recorded."""

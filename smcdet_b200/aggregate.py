@@ -27,13 +27,19 @@ from . import _lib as L
 class Aggregate(object):
     def __init__(self, Prior, ImageModel, MutationKernel, data, counts, locs, fluxes, weights,
                  log_normalizing_constant, flux_detection_threshold, resample_method, ess_threshold_prop,
-                 print_every=5, *, merge=True, levels=None):
+                 print_every=5, *, merge=True, levels=None, merge_weights=False):
         """reference aggregate.py:10-67.  ``merge=False`` (keyword-only extension) treats every tile of
         ``data`` as its own 1 x 1 problem -- the per-tile sink used after a sharded run; the default
         keeps the reference's meaning (a grid larger than 1 x 1 asks for the tree merge).  ``levels`` (keyword-only):
         run only the first ``levels`` merge levels -- a [B * 4, 4] stack of B independent 4 x 4 blocks of 8 x 8 tiles
         with ``levels = 4`` merges every block into its own 32 x 32 parent (the largest parent the kernels carry),
-        all blocks in the same launches; this is how a field larger than one block is merged, block by block."""
+        all blocks in the same launches; this is how a field larger than one block is merged, block by block.
+        ``merge_weights`` (keyword-only, default off = the reference, which starts every merge from uniform weights,
+        aggregate.py:347-360): weight the joined catalogs by what dropping the stars in the neighbour's territory did
+        to the children's likelihoods before the bridge starts (see ``merge``) -- with a Poisson count prior this makes
+        the merged log normalising constant an estimate of the parent tile's evidence (checked against an exact answer,
+        tests/golden/exact_merge.npz).  It is one importance-sampling step through "children without their padding
+        stars": fine where those stars carry little light, degenerate in crowded fields (DESIGN.md)."""
         self.Prior = deepcopy(Prior)
         self.ImageModel = deepcopy(ImageModel)
         self.MutationKernel = deepcopy(MutationKernel)
@@ -50,6 +56,7 @@ class Aggregate(object):
 
         self.numH, self.numW, self.dimH, self.dimW = self.data.shape
         self._merge_tree = merge
+        self.merge_weights = bool(merge_weights)
         self.num_aggregation_levels = (2 * torch.tensor(float(self.numH)).log2()).int().item() if merge else 0
         if merge and levels is not None:
             self.num_aggregation_levels = int(levels)
@@ -160,14 +167,15 @@ class Aggregate(object):
         model, prior = self.ImageModel._params(), self.Prior._params()
         tiles = L.f32(self.data, dev).reshape(T, self.dimH, self.dimW)
         tau = L.f32(self.temperature, dev).reshape(T)
-        lld = torch.empty(T, n, device=dev)
+        lld, chi = torch.empty(T, n, device=dev), torch.empty(T, n, device=dev)
         acc = torch.empty(T, device=dev)
         locs, fluxes = locs.clone(), fluxes.clone()
         L.check(L.lib().smcdet_agg_mutate(C.byref(model), C.byref(prior), C.byref(k), int(axis), L.ptr(tiles),
-                                          L.ptr(counts), L.ptr(locs), L.ptr(fluxes), L.ptr(tau), L.ptr(lld), None, None,
-                                          None, L.ptr(acc), None, None, L.fresh_seed(), int(self.iter), None, None,
-                                          T, n, d, int(self.dimH), int(self.dimW), L.stream_for(tiles)))
+                                          L.ptr(counts), L.ptr(locs), L.ptr(fluxes), L.ptr(tau), L.ptr(lld), None,
+                                          L.ptr(chi), None, L.ptr(acc), None, None, L.fresh_seed(), int(self.iter), None,
+                                          None, T, n, d, int(self.dimH), int(self.dimW), L.stream_for(tiles)))
         self.loglik_diff = lld.view(self.numH, self.numW, n)
+        self.child_loglik = chi.view(self.numH, self.numW, n)  # sum over the two children, on their kept stars
         if num_iters > 0:
             self.locs, self.fluxes = locs.view(self.numH, self.numW, n, d, 2), fluxes.view(self.numH, self.numW, n, d)
             self.mutation_acc_rates = acc.view(self.numH, self.numW)
@@ -197,12 +205,29 @@ class Aggregate(object):
     def merge(self, level):
         """Resample the children, drop the sources in each other's territory, join pairs of tiles along
         ``level % 2`` (aggregate.py:347-360, :189-265); the parent's log normalising constant starts as the sum
-        of its children's."""
+        of its children's.
+
+        Importance weights of the join (``merge_weights``).  A child's catalog z_c = (kept_c, dropped_c): the stars in
+        its own territory and those in the strip of its padding that belongs to its sibling.  With a Poisson process
+        prior of one intensity on every tile, prior(z_1) prior(z_2) = prior_parent(kept_1 + kept_2) x [the same prior
+        on the two strips](dropped_1, dropped_2): the parent's padded box is exactly the union of the two territories.
+        Taking the strip factors as the auxiliary distribution of the dropped stars, the joined catalog z carries the
+        weight  lik_parent(z) / [lik_1(z_1) lik_2(z_2)]  =  w0 x [lik_parent(z) / (lik_1(kept_1) lik_2(kept_2))]:
+        the second factor is the bridge the tempering steps cross (aggregate.py:533-541); the first,
+        w0 = lik_1(kept_1) lik_2(kept_2) / (lik_1(z_1) lik_2(z_2)), is applied here as one importance-sampling step
+        (log Z += log mean w0, resample by w0).  ``run`` does it right after the join."""
         axis = level % 2
         if (self.numH if axis == 0 else self.numW) % 2 != 0:
             raise ValueError("the tree merge needs an even number of tiles along the merge axis")
         self._resample()
         nH, nW = self.numH, self.numW
+        self._child_loglik_full = None
+        if self.merge_weights:
+            # likelihood of every child catalog as its tile's sampler left it, summed over the pair that is joined
+            # (particle i of the first child goes with particle i of the second)
+            ll = self.ImageModel.loglikelihood(L.f32(self.data), self.locs, self.fluxes)
+            self._child_loglik_full = (ll.reshape(nH // 2, 2, nW, -1).sum(1) if axis == 0
+                                       else ll.reshape(nH, nW // 2, 2, -1).sum(2))
         self.data, self.counts, self.locs, self.fluxes = self.join(axis, self.data, self.counts, self.locs, self.fluxes)
         self._logz = self._logz.reshape(nH // 2, 2, nW).sum(1) if axis == 0 else self._logz.reshape(nH, nW // 2, 2).sum(2)
         n = self.counts.shape[-1]
@@ -226,6 +251,16 @@ class Aggregate(object):
             self.temperature_prev = torch.zeros(self.numH, self.numW, device=dev)
             self.temperature = torch.zeros(self.numH, self.numW, device=dev)
             self._bridge(axis, 0)
+            if self._child_loglik_full is not None:
+                # w0 = children's likelihood after / before the drop (see merge); -inf - -inf (a catalog that was
+                # already impossible) counts as weight 0
+                logw = torch.nan_to_num(self.child_loglik - self._child_loglik_full, nan=float("-inf"))
+                n = logw.shape[-1]
+                self._logz = self._logz + torch.logsumexp(logw, -1) - torch.log(torch.tensor(float(n), device=dev))
+                self.weights = torch.softmax(logw, -1)
+                self.merge_ess = 1.0 / (self.weights**2).sum(-1)
+                self._resample()
+                self._bridge(axis, 0)
             self._temper_and_update()
             self.iter = 0
             while torch.any(self.temperature < 1) and self.iter < max_iters:

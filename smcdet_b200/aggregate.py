@@ -16,6 +16,7 @@ what had to be decided, is listed in DESIGN.md section 8.
 """
 
 import ctypes as C
+import warnings
 from copy import deepcopy
 
 import torch
@@ -241,7 +242,9 @@ class Aggregate(object):
         if self.num_aggregation_levels > 0:
             self._logz = torch.tensor(self.log_normalizing_constant, device=dev, dtype=torch.float32)
             if self._logz.numel() != self.numH * self.numW:
-                raise ValueError("the tree merge takes one log normalising constant per tile")
+                raise ValueError("the tree merge takes one log normalising constant per tile (for count-stratified "
+                                 "tiles pass CountStratifiedSMC.log_evidence, the log-sum over the count strata, not "
+                                 "the per-count log_normalizing_constant)")
             self._logz = self._logz.reshape(self.numH, self.numW)
         self.iter = 0
         for level in range(self.num_aggregation_levels):
@@ -274,6 +277,10 @@ class Aggregate(object):
                 self._resample()
                 self._bridge(axis, self.MutationKernel.num_iters)
                 self._temper_and_update()
+            if torch.any(self.temperature < 1):
+                # the next level would start from catalogs that do not target the parent posterior yet
+                warnings.warn(f"Aggregate.run: merge level {level} stopped after max_iters = {max_iters} bridge "
+                              f"iterations at temperature {self.temperature.min().item():.3f} < 1", RuntimeWarning)
         if self.num_aggregation_levels > 0:
             lz = self._logz.detach().cpu().tolist()
             self.log_normalizing_constant = [[[lz[h][w]] for w in range(self.numW)] for h in range(self.numH)]

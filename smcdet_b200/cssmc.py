@@ -4,7 +4,9 @@ estimated evidences (reference manuscript/manuscript.tex:312-356, Algorithm 1).
 The library at the reference's HEAD only runs the degenerate one-stratum case (min_objects == max_objects,
 SURVEY.md section 0.5); its drivers still speak the stratified interface -- ``num_catalogs_per_count=``,
 ``sampler.weights_intercount``, a per-(tile, count) ``log_normalizing_constant`` handed to ``Aggregate``
-(experiments/m71synthetic/run_smc.py:129-158).  This class provides that interface on top of the CUDA path:
+(experiments/m71synthetic/run_smc.py:129-158).  This class provides that interface on top of the CUDA path
+(the 1 x 1 ``Aggregate`` sink takes the stratified population and ``weights_intercount`` as they are; the tree
+merge works with one stratum per parent tile and takes ``log_evidence``, the log-sum over the count strata):
 
   strata (tile, s), s = min_objects..max_objects: tempered SMC with exactly s stars per catalog, every stratum
                                        with its own temperature schedule.  ``batched=True`` (default): all strata

@@ -392,17 +392,21 @@ class SMCsampler(object):
             flag[1].synchronize()
             return bool(flag[0].item())
 
-        prev, cur = None, post_flag()
+        diag = ("tempering_funcalls", "resampled_index")  # per-iteration diagnostics an idle iteration overwrites
+        prev, cur, saved = None, post_flag(), None
         while True:
             if not read(cur if prev is None else prev):
                 if prev is not None:  # the iteration in flight was launched after every tile had finished
                     self.iter -= 1
                     if self.history:
                         self.history.pop()
+                    for name, val in saved.items():
+                        setattr(self, name, val)
                 break
             if self.iter > self.max_smc_iters:
                 break
             self.iter += 1
+            saved = {name: getattr(self, name) for name in diag if hasattr(self, name)}
             self._one_iteration()
             prev, cur = cur, post_flag()
 
@@ -525,17 +529,25 @@ class SMCsampler(object):
         mk._status = status
 
     def _timed(self, stage, fn):
-        """Run one stage; with ``stage_timing`` set, bracket it with CUDA events on the current stream (tracing hook:
-        the reference only has wall-clock timers around whole runs, experiments/basic/run_smc.py:143-166)."""
-        if not getattr(self, "stage_timing", False):
-            return fn()
-        stream = torch.cuda.current_stream(self._device)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        out = fn()
-        e1.record(stream)
-        self._stage_events.append((stage, e0, e1))
-        return out
+        """Run one stage; with ``stage_timing`` set, bracket it with CUDA events on the current stream, with
+        ``nvtx_ranges`` set, inside an NVTX range named after the stage and the SMC iteration (tracing hooks: the
+        reference only has wall-clock timers around whole runs, experiments/basic/run_smc.py:143-166)."""
+        nvtx = getattr(self, "nvtx_ranges", False)
+        if nvtx:  # shows up as a named range in Nsight Systems / ncu --nvtx
+            torch.cuda.nvtx.range_push(f"smcdet/{stage}/iter{self.iter}")
+        try:
+            if not getattr(self, "stage_timing", False):
+                return fn()
+            stream = torch.cuda.current_stream(self._device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out = fn()
+            e1.record(stream)
+            self._stage_events.append((stage, e0, e1))
+            return out
+        finally:
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
 
     def stage_report(self):
         """Device milliseconds per stage of the last run() (needs ``stage_timing = True`` before run())."""

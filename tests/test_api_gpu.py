@@ -1031,9 +1031,12 @@ def test_host_ahead_loop_equals_the_plain_loop(max_iters, freeze, capsys):
     assert fused.iter == ahead.iter == plain.iter and len(ahead.history) == len(plain.history) == plain.iter + 1
     assert (max_iters == 2) == bool(float(plain.temperature.min()) < 1.0)
     for k in ("locs", "fluxes", "counts", "weights", "temperature", "temperature_prev", "log_normalizing_constant",
-              "loglik", "ess", "mutation_acc_rates", "pruned_counts", "pruned_fluxes", "weights_log_unnorm"):
+              "loglik", "ess", "mutation_acc_rates", "pruned_counts", "pruned_fluxes", "weights_log_unnorm",
+              "resampled_index"):
         assert torch.equal(getattr(ahead, k), getattr(plain, k)), k
         assert torch.equal(getattr(fused, k), getattr(plain, k)), k
+    # diagnostics of the last iteration that was really needed survive the roll-back of the look-ahead iteration
+    assert torch.equal(ahead.tempering_funcalls, plain.tempering_funcalls)
     # four launches of the library per SMC iteration (resample, gather, MH sweeps, tempering + weights); the iteration
     # the host launched ahead may add one more set; initialise / finish: prior draw, likelihood, tempering; resample,
     # gather, prune

@@ -590,10 +590,14 @@ def run_own(a):
     main_job = weak_job if do_weak else strong_job
 
     # ---- warm-up
+    # (the last warm-up step of each job goes through the end-to-end path as well: NCCL sets up its peer-to-peer
+    # channels on the first gather, and the gather buffers enter torch's caching allocator)
     for w in range(a.warmup):
-        main_job.run(100 + w)
-        if strong_job is not None and strong_job is not main_job and w == 0:
-            strong_job.run(100)
+        last = w == a.warmup - 1
+        main_job.run(100 + w, main_job.field_host.to(dev) if last else None, e2e=last)
+        if strong_job is not None and strong_job is not main_job and (w == 0 or last):
+            strong_job.run(100, strong_job.field_host.to(dev) if last else None, e2e=last)
+    torch.cuda.synchronize(dev)
     barrier()
 
     clock = ClockSampler(local_rank)

@@ -559,7 +559,7 @@ def run_own(a):
             live_total += live
             logs.append(log)
             smc_iters.append(it)
-            summ = summ_k if summ_k is not None else summ
+            summ = summ if summ is not None else summ_k   # the FIRST timed step's summaries (same seed whatever --steps)
             if e2e and outs:
                 slot = k % 2
                 if slot not in host_sets:
@@ -620,7 +620,7 @@ def run_own(a):
                           "h2d_bytes_per_step": s_e2e["h2d"], "d2h_bytes_per_step": s_e2e["d2h"]},
                   "smc_iters_per_step": s_dev["smc_iters"],
                   "checksum": {"sha256_16": digest, "sum_logz": float(full[:, 0].double().sum()),
-                               "of": "per-tile summaries of the last step in global tile order "
+                               "of": "per-tile summaries of the first timed step in global tile order "
                                      "(log Z, ESS, temperature, acceptance, mean detected count, mean detected flux; "
                                      "allstrata: log evidence, mean count, max count probability, log Z of the top count); "
                                      "seeded by the global tile id, so identical for every number of GPUs"},

@@ -27,6 +27,7 @@
 #define SMC_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -114,15 +115,33 @@ __device__ __forceinline__ float4 rate_plus(const float4 r, const float2 a, cons
 
 // stage the tile and the block's particle catalogs (AoS in global memory, coalesced reads) into
 // shared memory as s_star[(d*3 + c) * PB + particle], c = 0 row, 1 col, 2 flux
-template <int MODEL, int HW, int PB>
-__device__ __forceinline__ void stage_block(const float* __restrict__ tile, const float* __restrict__ locs,
-                                            const float* __restrict__ fluxes, int n_here, int D,
-                                            float* s_tile, float* s_lgam, float* s_star) {
+// Shared-memory layout of the tile (and of lgamma(x + 1)).  A lane reads its chunk of PPT consecutive pixels with
+// 128-bit loads; chunks that start PPT floats apart begin in the same banks, so the lanes of a particle collided
+// (PPT = 64, 16 lanes per particle: a 16-way conflict on every load of a 32 x 32 tile).  Every chunk is therefore
+// followed by one float4 of padding: the chunk stride in 16-byte units (PPT / 4 + 1) is odd, which puts eight
+// consecutive lanes into eight different bank groups.  One lane per particle (PPT = HW): all lanes read the same
+// address (a broadcast), no padding.
+template <int PPT, int HW>
+struct TileLayout {
+    static constexpr int kPad = (PPT < HW) ? 4 : 0;
+    static constexpr int kStride = PPT + kPad;          // floats from one lane's chunk to the next
+    static constexpr int kSize = (HW / PPT) * kStride;  // floats of one staged image
+};
+
+template <int MODEL, int HW, int PPT>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ tile, float* s_tile, float* s_lgam) {
+    using TL = TileLayout<PPT, HW>;
     for (int i = threadIdx.x; i < HW; i += kBT) {
         const float x = tile[i];
-        s_tile[i] = x;
-        s_lgam[i] = (MODEL == SMCDET_MODEL_GAUSS_POISSON) ? lgammaf(x + 1.0f) : 0.0f;
+        const int j = i + TL::kPad * (i / PPT);
+        s_tile[j] = x;
+        s_lgam[j] = (MODEL == SMCDET_MODEL_GAUSS_POISSON) ? lgammaf(x + 1.0f) : 0.0f;
     }
+}
+
+template <int PB>
+__device__ __forceinline__ void stage_stars(const float* __restrict__ locs, const float* __restrict__ fluxes, int n_here,
+                                            int D, float* s_star) {
     const int nl = n_here * 2 * D;
     for (int i = threadIdx.x; i < nl; i += kBT) {
         const int pi = i / (2 * D), r = i - pi * 2 * D;
@@ -138,6 +157,14 @@ __device__ __forceinline__ void stage_block(const float* __restrict__ tile, cons
         const int pi = n_here + i / (3 * D), r = i % (3 * D);
         s_star[r * PB + pi] = 0.0f;
     }
+}
+
+template <int MODEL, int HW, int PB, int PPT>
+__device__ __forceinline__ void stage_block(const float* __restrict__ tile, const float* __restrict__ locs,
+                                            const float* __restrict__ fluxes, int n_here, int D,
+                                            float* s_tile, float* s_lgam, float* s_star) {
+    stage_tile<MODEL, HW, PPT>(tile, s_tile, s_lgam);
+    stage_stars<PB>(locs, fluxes, n_here, D, s_star);
 }
 
 template <int PB>
@@ -182,16 +209,17 @@ __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float
                                                      int blocks_per_tile) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
+    using TL = TileLayout<PPT, HW>;
     float* s_tile = smem;
-    float* s_lgam = s_tile + HW;
-    float* s_star = s_lgam + HW;
+    float* s_lgam = s_tile + TL::kSize;
+    float* s_star = s_lgam + TL::kSize;
 
     const int t = blockIdx.x / blocks_per_tile;
     const int n0 = (blockIdx.x - t * blocks_per_tile) * PB;
     const int n_here = min(PB, N - n0);
     const size_t pbase = (size_t)t * N + n0;
     const int ti = tile_map != nullptr ? tile_map[t] : t;  // the segment's image (count strata share their tile's)
-    stage_block<MODEL, HW, PB>(tiles + (size_t)ti * HW, locs + pbase * 2 * D, fluxes + pbase * D, n_here, D, s_tile,
+    stage_block<MODEL, HW, PB, PPT>(tiles + (size_t)ti * HW, locs + pbase * 2 * D, fluxes + pbase * D, n_here, D, s_tile,
                                s_lgam, s_star);
     __syncthreads();
 
@@ -199,11 +227,53 @@ __global__ void __launch_bounds__(kBT) loglik_kernel(const ModelK m, const float
     float2 acc[PPT / 2];
     render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
     float Q, S;
-    pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + row0 * W, s_lgam + row0 * W, [&](int g) {
+    pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + sub * TL::kStride, s_lgam + sub * TL::kStride, [&](int g) {
         return rate_plus(make_float4(m.bg, m.bg, m.bg, m.bg), acc[2 * g], acc[2 * g + 1]);
     }, Q, S);
     const float ll = finish_loglik<MODEL>(group_sum<TPP>(Q), group_sum<TPP>(S), HW);
     if (sub == 0 && pi < n_here) out[pbase + pi] = ll;
+}
+
+// The same for models whose tile is expensive to stage (Poisson: lgamma(x + 1) of every pixel, ~1e2 instructions
+// each): the tile is staged once per block and serves groups_per_block groups of PB particles.  With one group per
+// block that staging was most of the kernel for 16 x 16 and 32 x 32 tiles, where a group is only 4-32 particles
+// (profiles/r02_sweep_loglik_mh.md: 2.5 ms per 10^6 evaluations of a 32 x 32 tile whatever the number of stars).
+template <int MODEL, int H, int W, int TPP>
+__global__ void __launch_bounds__(kBT) loglik_groups_kernel(const ModelK m, const float* __restrict__ tiles,
+                                                            const float* __restrict__ locs,
+                                                            const float* __restrict__ fluxes, float* __restrict__ out,
+                                                            const int32_t* __restrict__ tile_map, int N, int D,
+                                                            int blocks_per_tile, int groups_per_block) {
+    constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
+    SMC_DYN_SHARED(float, smem);
+    using TL = TileLayout<PPT, HW>;
+    float* s_tile = smem;
+    float* s_lgam = s_tile + TL::kSize;
+    float* s_star = s_lgam + TL::kSize;
+
+    const int t = blockIdx.x / blocks_per_tile;
+    const int g0 = (blockIdx.x - t * blocks_per_tile) * groups_per_block;
+    const int ti = tile_map != nullptr ? tile_map[t] : t;
+    stage_tile<MODEL, HW, PPT>(tiles + (size_t)ti * HW, s_tile, s_lgam);
+    const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
+#pragma unroll 1
+    for (int g = 0; g < groups_per_block; ++g) {
+        const int n0 = (g0 + g) * PB;
+        if (n0 >= N) break;  // (uniform over the block)
+        const int n_here = min(PB, N - n0);
+        const size_t pbase = (size_t)t * N + n0;
+        if (g > 0) __syncthreads();  // the previous group's catalogs have been read
+        stage_stars<PB>(locs + pbase * 2 * D, fluxes + pbase * D, n_here, D, s_star);
+        __syncthreads();
+        float2 acc[PPT / 2];
+        render_rows<MODEL, RPT, W, PB>(m, s_star, pi, D, row0, acc);
+        float Q, S;
+        pixel_loglik_sum<MODEL, RPT, W>(m, s_tile + sub * TL::kStride, s_lgam + sub * TL::kStride, [&](int q) {
+            return rate_plus(make_float4(m.bg, m.bg, m.bg, m.bg), acc[2 * q], acc[2 * q + 1]);
+        }, Q, S);
+        const float ll = finish_loglik<MODEL>(group_sum<TPP>(Q), group_sum<TPP>(S), HW);
+        if (sub == 0 && pi < n_here) out[pbase + pi] = ll;
+    }
 }
 
 // any tile shape: one warp per particle, lanes stride over pixels, direct PSF evaluation
@@ -754,9 +824,10 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     mh_kernel(const MHArgs a) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
+    using TL = TileLayout<PPT, HW>;
     float* s_tile = smem;
-    float* s_lgam = s_tile + HW;
-    float* s_star = s_lgam + HW;              // [3*D][PB]
+    float* s_lgam = s_tile + TL::kSize;
+    float* s_star = s_lgam + TL::kSize;              // [3*D][PB]
     float* s_rate = s_star + 3 * a.D * PB;    // [PPT][kBT]
 
     const int t = blockIdx.x / a.blocks_per_tile;
@@ -766,7 +837,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     const int n_here = min(PB, N - n0);
     const size_t pbase = (size_t)t * N + n0;
     const int ti = a.tile_map != nullptr ? a.tile_map[t] : t;  // the segment's image (count strata share their tile's)
-    stage_block<MODEL, HW, PB>(a.tiles + (size_t)ti * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
+    stage_block<MODEL, HW, PB, PPT>(a.tiles + (size_t)ti * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
                                s_tile, s_lgam, s_star);
     __syncthreads();
 
@@ -774,8 +845,8 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     const int pi = threadIdx.x / TPP, sub = threadIdx.x % TPP, row0 = sub * RPT;
     const bool valid = pi < n_here;
     const size_t pn = pbase + pi;
-    const float* xs = s_tile + row0 * W;
-    const float* lg = s_lgam + row0 * W;
+    const float* xs = s_tile + sub * TL::kStride;  // the lane's pixels (row0 * W on, padded layout)
+    const float* lg = s_lgam + sub * TL::kStride;
     float4* my_rate = reinterpret_cast<float4*>(s_rate) + threadIdx.x;  // [PPT/4][kBT] float4, conflict-free
     const float* my_star = s_star + pi;
 
@@ -1305,9 +1376,10 @@ template <int MODEL, int H, int W, int TPP, int AXIS>
 __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOut o) {
     constexpr int PB = kBT / TPP, RPT = H / TPP, PPT = RPT * W, HW = H * W;
     SMC_DYN_SHARED(float, smem);
+    using TL = TileLayout<PPT, HW>;
     float* s_tile = smem;
-    float* s_lgam = s_tile + HW;
-    float* s_star = s_lgam + HW;               // [3*D][PB]
+    float* s_lgam = s_tile + TL::kSize;
+    float* s_star = s_lgam + TL::kSize;               // [3*D][PB]
     float* s_rateP = s_star + 3 * a.D * PB;    // [PPT][kBT]
     float* s_rateC = s_rateP + PPT * kBT;      // [PPT][kBT]
 
@@ -1317,7 +1389,7 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
     const int n0 = (blockIdx.x - t * a.blocks_per_tile) * PB;
     const int n_here = min(PB, N - n0);
     const size_t pbase = (size_t)t * N + n0;
-    stage_block<MODEL, HW, PB>(a.tiles + (size_t)t * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
+    stage_block<MODEL, HW, PB, PPT>(a.tiles + (size_t)t * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
                                s_tile, s_lgam, s_star);
     __syncthreads();
 
@@ -1328,8 +1400,8 @@ __global__ void __launch_bounds__(kBT) agg_mh_kernel(const MHArgs a, const AggOu
     const float* my_star = s_star + pi;
     float4* rateP = reinterpret_cast<float4*>(s_rateP) + threadIdx.x;  // [PPT/4][kBT] float4
     float4* rateC = reinterpret_cast<float4*>(s_rateC) + threadIdx.x;
-    const float* xs = s_tile + row0 * W;
-    const float* lg = s_lgam + row0 * W;
+    const float* xs = s_tile + sub * TL::kStride;  // the lane's pixels (row0 * W on, padded layout)
+    const float* lg = s_lgam + sub * TL::kStride;
     const float count = valid ? a.counts[pn] : 0.0f;
     const int icount = (int)count;
     const float tau = a.tau[t];
@@ -1495,7 +1567,7 @@ int launch_agg_t(MHArgs a, const AggOut& o, cudaStream_t st) {
     constexpr int PB = kBT / TPP;
     a.blocks_per_tile = (a.N + PB - 1) / PB;
     constexpr int PPT = (H / TPP) * W;
-    const size_t smem = sizeof(float) * ((size_t)2 * H * W + (size_t)3 * a.D * PB + (size_t)2 * PPT * kBT);
+    const size_t smem = sizeof(float) * ((size_t)2 * TileLayout<PPT, H * W>::kSize + (size_t)3 * a.D * PB + (size_t)2 * PPT * kBT);
     const long long grid = (long long)a.T * a.blocks_per_tile;
     if (grid >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_agg_mutate: grid too large");
 #ifndef SMC_HOSTSIM
@@ -1536,27 +1608,58 @@ int choose_tpp(int side, long long particles) {
 
 thread_local int g_force_tpp = 0;  // diagnostic override of the calling thread (smcdet_debug_force_tpp)
 
+// smallest tile side whose Poisson-model likelihood takes loglik_groups_kernel (measured on B200: the loop costs
+// registers, which 8 x 8 tiles -- 0.5 lgamma per thread to stage -- do not get back)
+#ifndef SMC_GROUPS_MIN_SIDE
+#define SMC_GROUPS_MIN_SIDE 32
+#endif
+// ... and the largest catalog: with many stars per catalog the staging is amortised anyway and the plain kernel's
+// register allocation wins (32 x 32, B200: D = 1 0.88 against 1.08 ms per 10^6 evaluations, D = 16 4.11 against 3.76)
+#ifndef SMC_GROUPS_MAX_STARS
+#define SMC_GROUPS_MAX_STARS 4
+#endif
 template <int MODEL, int H, int TPP>
 int launch_loglik_t(const ModelK& m, const float* tiles, const float* locs, const float* fluxes, float* out,
                     const int32_t* tile_map, int T, int N, int D, cudaStream_t st) {
     constexpr int PB = kBT / TPP;
-    const int bpt = (N + PB - 1) / PB;
-    const size_t smem = sizeof(float) * (2 * H * H + 3 * (size_t)D * PB);
-    if ((long long)T * bpt >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_loglik: grid too large");
-    auto kern = loglik_kernel<MODEL, H, H, TPP>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(loglik)");
+    const int groups = (N + PB - 1) / PB;  // groups of PB particles per tile
+    const size_t smem = sizeof(float) * (2 * TileLayout<(H / TPP) * H, H * H>::kSize + 3 * (size_t)D * PB);
+    if constexpr (MODEL == SMCDET_MODEL_GAUSS_POISSON && H >= SMC_GROUPS_MIN_SIDE) if (D <= SMC_GROUPS_MAX_STARS) {
+        // several groups per block as long as the grid keeps >= 8 blocks per resident slot; blocks of a tile get
+        // equal shares
+        const long long slots = (long long)num_sms() * 4 * 8;
+        const long long want = ((long long)T * groups) / slots;
+        const int gmax = (int)std::min<long long>(std::max<long long>(want, 1), (H >= 16) ? 64 : 16);
+        const int nb = (groups + gmax - 1) / gmax;
+        const int gpb = (groups + nb - 1) / nb;
+        const int bpt = (groups + gpb - 1) / gpb;
+        if ((long long)T * bpt >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_loglik: grid too large");
+        auto kern = loglik_groups_kernel<MODEL, H, H, TPP>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(loglik)");
+        }
+        SMC_LAUNCH(kern, (unsigned)((size_t)T * bpt), kBT, smem, st, m, tiles, locs, fluxes, out, tile_map, N, D, bpt, gpb);
+        return launch_status("loglik_groups_kernel");
     }
-    SMC_LAUNCH(kern, (unsigned)((size_t)T * bpt), kBT, smem, st, m, tiles, locs, fluxes, out, tile_map, N, D, bpt);
-    return launch_status("loglik_kernel");
+    {
+        const int bpt = groups;
+        if ((long long)T * bpt >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_loglik: grid too large");
+        auto kern = loglik_kernel<MODEL, H, H, TPP>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(loglik)");
+        }
+        SMC_LAUNCH(kern, (unsigned)((size_t)T * bpt), kBT, smem, st, m, tiles, locs, fluxes, out, tile_map, N, D, bpt);
+        return launch_status("loglik_kernel");
+    }
 }
 
 template <int MODEL, int H, int TPP, bool MALA>
 int launch_mh_t(MHArgs& a, cudaStream_t st) {
     constexpr int PB = kBT / TPP, PPT = (H / TPP) * H;
     a.blocks_per_tile = (a.N + PB - 1) / PB;
-    const size_t smem = sizeof(float) * (2 * H * H + 3 * (size_t)a.D * PB + (size_t)PPT * kBT);
+    const size_t smem = sizeof(float) * (2 * TileLayout<PPT, H * H>::kSize + 3 * (size_t)a.D * PB + (size_t)PPT * kBT);
     if ((long long)a.T * a.blocks_per_tile >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_mh_mutate: grid too large");
     auto kern = mh_kernel<MODEL, H, H, TPP, MALA>;
     if (smem > 48 * 1024) {

@@ -462,6 +462,36 @@ def test_many_stars_and_ragged_particle_counts(backend):
         assert np.max(np.abs(r["locs"] - o["locs"])) < 1e-5 and np.max(np.abs(r["fluxes"] / o["fluxes"] - 1)) < RTOL
 
 
+@pytest.mark.parametrize("model_name", ["loglik_m71_t8_d10", "loglik_gauss_t8_d8"])
+def test_large_tiles_few_and_many_stars_against_the_oracle(backend, model_name):
+    """16 x 16 and 32 x 32 tiles (several lanes per particle: the padded shared-memory layout of the tile) with one
+    star, a few stars (Poisson model, 32 x 32, D <= 4: loglik_groups_kernel, several particle groups per block) and many,
+    and particle counts that leave groups and blocks ragged -- every lanes-per-particle instantiation against the oracle."""
+    g = Golden(model_name)
+    meta = dict(g.meta)
+    gauss = "gauss" in model_name
+    rng = np.random.default_rng(11)
+    om = oracle_model(meta)
+    try:
+        for side, D, N in ((32, 1, 70), (32, 3, 1000), (32, 4, 9), (32, 12, 50), (16, 2, 300), (16, 9, 33)):
+            T = 2
+            meta["tile"], meta["D"] = side, D
+            base = 200.0 if gauss else 104.0
+            tiles = (base + 60.0 * rng.random((T, side, side))).round().astype(np.float32)
+            tiles[0, 3, 5] = 0.0  # a dark pixel: x log(rate) with x = 0 (torch.xlogy, images.py:93)
+            locs = rng.uniform(-2, side + 2, (T, N, D, 2)).astype(np.float32)
+            fluxes = (np.exp(rng.uniform(np.log(400.0), np.log(3000.0), (T, N, D))) if gauss
+                      else np.exp(rng.uniform(np.log(0.07), np.log(300.0), (T, N, D)))).astype(np.float32)
+            fluxes[0, 0, 0] = 0.0     # an empty slot
+            ref = O.loglik(om, tiles, locs, fluxes)
+            for tpp in TPPS[side] + [0]:
+                backend.force_tpp(tpp)
+                ll = backend.loglik(abi_model(meta), tiles, locs, fluxes)
+                assert rel_err(ll, ref) < RTOL, (side, D, N, tpp)
+    finally:
+        backend.force_tpp(0)
+
+
 def test_match_catalogs_equals_the_reference(backend):
     """smcdet_match_catalogs against metrics.match_catalogs of the reference (scipy's linear_sum_assignment on
     every (tile, catalog) problem) on the catalogs the reference drew: per-bin totals and matches identical."""

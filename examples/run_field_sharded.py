@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--stars", type=int, default=6)
     ap.add_argument("--mh-iters", type=int, default=25)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--sink", action="store_true", help="gather the weighted catalogs onto rank 0 into the Aggregate sink")
     ap.add_argument("--merge", action="store_true", help="finish with the Aggregate tree merge of the field (rank 0); "
                     "needs --tiles 4 or 16 (a 2x2 / 4x4 grid of 8x8 tiles)")
     a = ap.parse_args()
@@ -40,9 +41,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     rank = dist.get_rank() if world > 1 else 0
 
-    class F:  # the same synthetic field on every rank
-        tiles_per_gpu = a.tiles
-    tiles = make_field(F, 0, dev)[:, 0].cpu()  # [T, 8, 8]
+    from types import SimpleNamespace
+
+    # the same synthetic field on every rank (bench.py's m71synthetic generator: seeded, device-side)
+    tiles = make_field(SimpleNamespace(workload="m71synthetic", stars=a.stars), a.tiles, 0, dev).cpu()  # [T, 8, 8]
 
     def objects():
         model = M71ImageModel(8, 8, **M71)
@@ -59,6 +61,13 @@ def main():
         s = out["summaries"]
         print(f"{a.tiles} tiles on {world} GPU(s): mean posterior count {s[:, 4].mean():.3f}, "
               f"mean logZ {s[:, 0].mean():.2f}, all at temperature 1: {bool((s[:, 2] == 1).all())}")
+    if a.sink:
+        # the reference's per-tile finish on rank 0 (experiments/m71/run_smc.py:124-166): NCCL gather of the weighted
+        # catalogs, then Aggregate(..., merge=False).run() -- resample by the weights and prune, tile by tile
+        agg = job.sink()
+        if rank == 0:
+            print(f"sink on rank 0: {agg.pruned_counts.shape[0]} tiles finished, mean detected count "
+                  f"{agg.pruned_counts.float().mean():.3f}")
     if a.merge:
         side = int(round(a.tiles ** 0.5))
         agg = job.aggregate((side, side), SingleComponentMH(10, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"]))

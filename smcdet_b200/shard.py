@@ -138,16 +138,32 @@ class ShardedSMC(object):
         local = tiles[self.local_ids].to(dev, non_blocking=True).unsqueeze(1)  # [T_r, 1, h, w]
         # every rank must use the same Philox base seed (given, or rank 0's broadcast)
         self.seed = shared_seed(dev, group) if seed is None else int(seed)
-        self.sampler = SMCsampler(local, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs,
-                                  ess_threshold_prop, resample_method, flux_detection_threshold, max_smc_iters,
-                                  print_every, tile_ids=self.local_ids.to(dev).unsqueeze(1),
-                                  freeze_finished=freeze_finished, verbose=verbose, seed=self.seed)
+        # a field with fewer tiles than ranks leaves some ranks without work: they hold no sampler, contribute empty
+        # shards to the gathers and still take part in every collective
+        self._empty_shapes = (int(num_catalogs), int(Prior.max_objects))
+        self.sampler = None
+        # what the finishes below read off the sampler, for a rank that has none
+        from types import SimpleNamespace
+
+        self._spec = SimpleNamespace(Prior=Prior, ImageModel=ImageModel, MutationKernel=MutationKernel,
+                                     flux_detection_threshold=flux_detection_threshold, resample_method=resample_method)
+        if len(self.local_ids) > 0:
+            self.sampler = SMCsampler(local, tile_dim, Prior, ImageModel, MutationKernel, num_catalogs,
+                                      ess_threshold_prop, resample_method, flux_detection_threshold, max_smc_iters,
+                                      print_every, tile_ids=self.local_ids.to(dev).unsqueeze(1),
+                                      freeze_finished=freeze_finished, verbose=verbose, seed=self.seed)
 
     def run(self):
-        self.sampler.run()
+        if self.sampler is not None:
+            self.sampler.run()
         return self
 
     def local_results(self):
+        if self.sampler is None:
+            n, d = self._empty_shapes
+            z = lambda *shape, dtype=torch.float32: torch.zeros(0, *shape, dtype=dtype, device=self._device)  # noqa: E731
+            return dict(counts=z(n), locs=z(n, d, 2), fluxes=z(n, d), weights=z(n), pruned_counts=z(n, dtype=torch.int64),
+                        pruned_locs=z(n, d, 2), pruned_fluxes=z(n, d), summaries=z(len(self.SUMMARY_COLUMNS)))
         s = self.sampler
         sq = lambda t: t.squeeze(1)  # noqa: E731  [T_r, 1, ...] -> [T_r, ...]
         summaries = torch.stack([
@@ -181,6 +197,8 @@ class ShardedSMC(object):
         from .aggregate import Aggregate
 
         if local:
+            if self.sampler is None:
+                return None
             out = {k: v.contiguous() for k, v in self.local_results().items()}
             tiles = self._tiles[self.local_ids]
         else:
@@ -188,7 +206,7 @@ class ShardedSMC(object):
             tiles = self._tiles
         if out is None:
             return None
-        s = self.sampler
+        s = self.sampler if self.sampler is not None else self._spec
         T, n, d = out["counts"].shape[0], out["counts"].shape[1], out["fluxes"].shape[-1]
         data = tiles.to(self._device).reshape(T, 1, *self._tiles.shape[1:])
         if MutationKernel is None:  # Aggregate deep-copies its kernel: hand it one without this run's logs and traces
@@ -256,7 +274,7 @@ class ShardedSMC(object):
         out = self.gather(keys=("counts", "locs", "fluxes", "weights", "summaries"))
         if root_only and self.rank != 0:
             return None
-        s = self.sampler
+        s = self.sampler if self.sampler is not None else self._spec
         n, d = out["counts"].shape[1], out["fluxes"].shape[-1]
         data = self._tiles.to(self._device).reshape(numH, numW, *self._tiles.shape[1:])
         agg = Aggregate(s.Prior, s.ImageModel, MutationKernel, data, out["counts"].view(numH, numW, n),

@@ -127,6 +127,13 @@ root = gather_tiles_to_root(local, T, dst=0)
 assert (root is None) == (rank != 0)
 if rank == 0:
     assert torch.equal(root, want)
+# a field with fewer tiles than ranks: the last rank's shard is empty and still takes part in the collectives
+one = shard_tile_ids(1, world, rank)
+assert len(one) == (1 if rank == 0 else 0)
+loc1 = torch.full((len(one), 2), 5.0)
+assert torch.equal(gather_tiles(loc1, 1), torch.full((1, 2), 5.0))
+r1 = gather_tiles_to_root(loc1, 1, dst=0)
+assert (r1 is None) == (rank != 0) and (rank != 0 or torch.equal(r1, torch.full((1, 2), 5.0)))
 # the (tile, count) strata of count-stratified SMC as a second sharding axis: every stratum on exactly one rank,
 # loads balanced by expected cost, the assignment identical on every rank
 from smcdet_b200.cssmc import CountStratifiedSMC as CS

@@ -9,10 +9,9 @@ from smcdet_b200.prior import M71Prior
 from smcdet_b200.sampler import SMCsampler
 import argparse
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
-class A: pass
+A = argparse.Namespace(workload="m71synthetic", stars=10)
 for T in (1, 4, 16, 64):
-    a = A(); a.tiles_per_gpu = T
-    tiles = make_field(a, 0, dev)
+    tiles = make_field(A, T, 0, dev).view(T, 1, 8, 8)
     model = M71ImageModel(8, 8, **M71)
     prior = M71Prior(10, 10, PRIOR["counts_rate"], 8, 8, flux_alpha=PRIOR["flux_alpha"], flux_lower=PRIOR["flux_lower"], flux_upper=PRIOR["flux_upper"], pad=4)
     for freeze in (False, True):

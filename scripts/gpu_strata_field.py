@@ -14,8 +14,9 @@ T = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 smax = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 10000
 dev = torch.device("cuda", 0)
-class A: tiles_per_gpu = T; workload = "m71synthetic"
-tiles = make_field(A, 0, dev)                       # [T, 1, 8, 8]
+import argparse
+A = argparse.Namespace(workload="m71synthetic", stars=smax)
+tiles = make_field(A, T, 0, dev).view(T, 1, 8, 8)
 model = M71ImageModel(8, 8, **M71)
 prior = M71Prior(0, smax, PRIOR["counts_rate"], 8, 8, flux_alpha=PRIOR["flux_alpha"], flux_lower=PRIOR["flux_lower"],
                  flux_upper=PRIOR["flux_upper"], pad=4)

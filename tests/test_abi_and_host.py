@@ -233,3 +233,29 @@ def test_bench_reference_arm_prints_one_contract_line():
         own = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
                              capture_output=True, text=True, timeout=300)
         assert own.returncode != 0 and "no CPU fallback" in (own.stderr + own.stdout)
+
+
+def test_committed_bench_line_carries_the_contract():
+    """The committed 1-GPU bench line of the current round (profiles/r02_bench_n1.json, written by `python bench.py` on a
+    B200) has every key of the measurement contract, with consistent arithmetic: value = evals / time, the roofline
+    fraction = achieved / peak, traffic measured and below the algorithmic bytes (no wasted re-reads), the dominant
+    kernel's share of the step below 1, both CPU baselines with their core counts, clean clocks."""
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.loads(open(os.path.join(root, "profiles", "r02_bench_n1.json")).read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and "m71synthetic" in d["config"]["workload"]
+    assert d["gpu_launches"] > 0 and d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] >= 0.9 * d["clocks"]["sm_max_mhz"]
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["share_of_step"] < 1
+    assert 0 < r["executed_frac"] < 1 and r["traffic"] is not None and 0 < r["traffic"] <= r["algorithmic_bytes_per_launch"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["also"][0]["kind"] == "reference"
+    s = d["strong"]
+    assert len(s["checksum"]["sha256_16"]) == 16 and s["e2e"]["d2h_bytes_per_step"] > 0

@@ -492,6 +492,17 @@ def test_large_tiles_few_and_many_stars_against_the_oracle(backend, model_name):
         backend.force_tpp(0)
 
 
+def test_randomised_shapes_against_the_oracle(backend, request):
+    """Random model / tile side / catalog size / particle count / PSF radius / padding, every lanes-per-particle
+    decomposition (tests/fuzzlib.py): likelihood within 1e-4 of the oracle, MH accept decisions equal to the oracle's up
+    to float32 ties, final states equal.  The CPU emulator runs a short list with few particles, the GPU a long one."""
+    from fuzzlib import run_cases
+
+    on_gpu = request.node.callspec.params["backend"] == "gpu"
+    worst, flips = run_cases(backend, 60 if on_gpu else 20, seed=5, max_particles=1000 if on_gpu else 31)
+    assert worst < RTOL
+
+
 def test_match_catalogs_equals_the_reference(backend):
     """smcdet_match_catalogs against metrics.match_catalogs of the reference (scipy's linear_sum_assignment on
     every (tile, catalog) problem) on the catalogs the reference drew: per-bin totals and matches identical."""

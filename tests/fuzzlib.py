@@ -68,6 +68,17 @@ def run_cases(be, cases, seed, max_particles=1000, verbose=False):
         for tpp in TPPS[side] + [0]:
             be.force_tpp(tpp)
             r = be.mh_mutate(am, abi_prior(mmeta), abi_mh(mmeta, iters), tiles, counts, locs, fluxes, tau, tape=tape)
+            # the log acceptance ratio of the first sweep (no decision has been taken yet), and of every sweep when all
+            # decisions agree: within 1e-4 of the magnitude of the log targets it is the difference of
+            def log_alpha_close(sl):
+                ref = (o["lognum"][sl].astype(np.float64) - o["logden"][sl].astype(np.float64))
+                got = r["log_alpha"][sl].astype(np.float64)
+                fin = np.isfinite(ref)
+                scale = np.maximum(np.maximum(np.abs(o["lognum"][sl]), np.abs(o["logden"][sl])), 1.0)
+                return (np.array_equal(np.isfinite(got), fin) and
+                        bool(np.all(np.abs(got[fin] - ref[fin]) <= 1e-4 * scale[fin])))
+
+            assert log_alpha_close(slice(0, 1)), ("mh log alpha, first sweep", kind, side, D, N, tpp)
             nflip = int((r["accept"] != o["accept"]).sum())
             flips += nflip
             if nflip:
@@ -79,6 +90,7 @@ def run_cases(be, cases, seed, max_particles=1000, verbose=False):
                 tol = 4 * 1.2e-7 * scale + 1e-5
                 assert np.all(np.abs(np.log(np.maximum(al, 1e-300)) - np.log(ua)) < tol), ("mh accept", kind, side, D, N, tpp, al, ua, scale)
             else:
+                assert log_alpha_close(slice(None)), ("mh log alpha", kind, side, D, N, tpp)
                 # final states: 1e-5 / 1e-4 as in tests/, plus what float32 leaves of a draw in the far tail of a truncated
                 # normal: cdf(lb) = 0.5 (1 - erf(z)) cancels for z > 2.5 and erfinv near -1 amplifies that by ~2e3, in the
                 # reference's torch arithmetic (distributions.py:33-46) exactly as here -- up to ~5e-4 sigma for u ~ 1e-5

@@ -108,3 +108,78 @@ def run_cases(be, cases, seed, max_particles=1000, verbose=False):
         if verbose:
             print(f"case {c}: {kind} side {side} D {D} N {N} T {T} pad {pad} R {meta['model_params']['psf_radius']} ok", flush=True)
     return worst_ll, flips
+
+
+def run_stage_cases(be, cases, seed, max_particles=10000):
+    """The other stages of an SMC iteration on random inputs against the oracle: tempering (root bracketed to brentq's
+    tolerance, temperatures within 2e-5 of the oracle's), weights / ESS / log Z (1e-4), resampling on injected uniforms
+    (indices exact, both methods), the gather by those indices and the prune (exact).  Log-likelihood rows range from
+    nearly flat to spreads of 1e4, with -inf and nan entries as the reference produces them for impossible catalogs."""
+    from goldenlib import A
+
+    rng = np.random.default_rng(seed)
+    for c in range(cases):
+        T = int(rng.choice([1, 2, 5]))
+        N = int(rng.choice([n for n in (1, 2, 31, 256, 257, 1000, 4099, 10000) if n <= max_particles]))
+        D = int(rng.choice([1, 3, 10]))
+        spread = float(rng.choice([1e-3, 1.0, 30.0, 1e3, 1e4]))
+        ll = (-500.0 + spread * rng.standard_normal((T, N))).astype(np.float32)
+        if N > 2 and rng.random() < 0.5:
+            ll[0, rng.integers(0, N, max(1, N // 50))] = -np.inf
+        if N > 2 and rng.random() < 0.2:
+            ll[-1, rng.integers(0, N)] = np.nan
+        tin = rng.uniform(0.0, 0.999, T).astype(np.float32)
+        thr = 0.5 * N
+        logz0 = rng.standard_normal(T).astype(np.float32)
+        r = be.temper_update(ll, tin, tin, thr, logz0)
+        otau, _, _ = O.temper(ll, tin, thr)
+        fin_rows = np.isfinite(np.where(np.isnan(ll), 0.0, np.where(np.isinf(ll), 0.0, ll))).all(-1)
+        assert np.all(r["tau"] >= tin) and np.all(r["tau"] <= 1.0 + 1e-6), ("tau range", c)
+        # Every temperature step below 1 is a root of ESS(delta) = threshold, bracketed to brentq's tolerance in the
+        # float64 objective; it equals the oracle's root unless ESS(delta) is not monotone (few particles, wide spread:
+        # several roots, and which one Brent's iteration reaches then hangs on the last bit of an objective value)
+        delta = r["tau"].astype(np.float64) - tin
+        for ti in range(T):
+            clean = not np.isnan(ll[ti]).any()
+            if r["tau"][ti] < 1.0 and clean:
+                lo = O.ess_objective(ll[ti], max(delta[ti] - 3e-6, 0.0), thr, dtype=np.float64)
+                hi = O.ess_objective(ll[ti], delta[ti] + 3e-6, thr, dtype=np.float64)
+                assert lo > 0 > hi, ("bracket", c, ti, N, spread, lo, hi)
+            same = abs(float(r["tau"][ti]) - float(otau[ti])) < 2e-5
+            if not same:
+                assert clean and r["tau"][ti] < 1.0 and otau[ti] < 1.0, ("tau", c, ti, N, spread, r["tau"][ti], otau[ti])
+                grid = np.linspace(0.0, 1.0 - float(tin[ti]), 4001)
+                f = np.array([O.ess_objective(ll[ti], d, thr, dtype=np.float64) for d in grid])
+                assert (np.diff(np.sign(f)) != 0).sum() > 1, ("tau: a single root, yet another one found", c, ti, N, spread)
+        # weights, ESS, log Z at the temperatures the kernel chose
+        r2 = be.temper_update(ll, r["tau"], tin, thr, logz0, do_temper=False)
+        wlog, w, ess, logz = O.update_weights(ll, r["tau"], tin, logz0)
+        assert rel_err(r2["wlog"], wlog) < 1e-4, ("wlog", c)
+        ok = np.isfinite(w).all(-1)
+        assert np.array_equal(np.isfinite(r2["weights"]).all(-1), ok), ("weights finite", c)
+        if ok.any():
+            assert np.max(np.abs(r2["weights"][ok] - w[ok])) < 1e-4 * w[ok].max(), ("weights", c)
+            assert rel_err(r2["ess"][ok], ess[ok]) < 1e-4 and rel_err(r2["logz"][ok], logz[ok]) < 1e-4, ("ess / logz", c)
+        # resampling on injected uniforms: indices exact
+        wts = rng.random((T, N)).astype(np.float32) ** float(rng.choice([1, 4, 20])) + np.float32(1e-20)
+        if N > 3:
+            wts[0, : N // 2] = 0.0                     # zero-weight particles are never drawn
+        wts /= wts.sum(-1, keepdims=True)
+        us = rng.random(T)
+        um = rng.random((T, N))
+        idx_s, _ = be.resample(A.RESAMPLE_SYSTEMATIC, wts, us)
+        idx_m, _ = be.resample(A.RESAMPLE_MULTINOMIAL, wts, um)
+        assert np.array_equal(idx_s, O.resample(O.RESAMPLE_SYSTEMATIC, wts.astype(np.float64), us)), ("systematic", c, N)
+        assert np.array_equal(idx_m, O.resample(O.RESAMPLE_MULTINOMIAL, wts, um)), ("multinomial", c, N)
+        if N > 3:
+            assert idx_s[0].min() >= N // 2 and idx_m[0].min() >= N // 2
+        # gather and prune: exact
+        counts = rng.integers(0, D + 1, (T, N)).astype(np.float32)
+        locs = rng.uniform(-2, 10, (T, N, D, 2)).astype(np.float32)
+        fluxes = np.exp(rng.uniform(-3, 6, (T, N, D))).astype(np.float32) * (np.arange(D)[None, None] < counts[..., None])
+        got = be.gather(idx_m, counts, locs, fluxes)
+        want = O.gather(idx_m, counts, locs, fluxes)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), ("gather", c)
+        gp = be.prune(locs, fluxes, 8.0, 8.0, 0.25)
+        wp = O.prune(locs, fluxes, 8.0, 8.0, 0.25)
+        assert all(np.array_equal(a, b) for a, b in zip(gp, wp)), ("prune", c)

@@ -503,6 +503,16 @@ def test_randomised_shapes_against_the_oracle(backend, request):
     assert worst < RTOL
 
 
+def test_randomised_smc_stages_against_the_oracle(backend, request):
+    """Tempering, weights / ESS / log Z, resampling on injected uniforms, gather and prune on random inputs (flat to
+    1e4-wide log-likelihood rows with -inf / nan entries, zero-weight particles, ragged particle counts) against the
+    oracle (tests/fuzzlib.py)."""
+    from fuzzlib import run_stage_cases
+
+    on_gpu = request.node.callspec.params["backend"] == "gpu"
+    run_stage_cases(backend, 40 if on_gpu else 8, seed=3, max_particles=10000 if on_gpu else 257)
+
+
 def test_match_catalogs_equals_the_reference(backend):
     """smcdet_match_catalogs against metrics.match_catalogs of the reference (scipy's linear_sum_assignment on
     every (tile, catalog) problem) on the catalogs the reference drew: per-bin totals and matches identical."""

@@ -493,19 +493,24 @@ __global__ void __launch_bounds__(kTB) temper_update_kernel(const float* __restr
 
     float tau_old, tau_new;
     if (do_temper) {
+        // A nan or +inf log-likelihood makes the reference's objective nan at every delta, and `nan < 0` is False
+        // (sampler.py:111): such a tile jumps to temperature 1.  +inf is the sentinel of that case in the maximum
+        // (only finite values enter it otherwise; -inf entries simply carry no weight).
         float mx = -INFINITY;
         for (int i = threadIdx.x; i < N; i += kTB) {
             const float l = ll[i];
             if (fabsf(l) <= 3.4028234663852886e38f) mx = fmaxf(mx, l);
+            else if (!(l == -INFINITY)) mx = INFINITY;
         }
         mx = block_max(mx, s_redf);
-        if (mx == -INFINITY) mx = 0.0f;
+        const bool poisoned = (mx == INFINITY);
+        if (mx == -INFINITY || poisoned) mx = 0.0f;
         tau_old = tau[t];
         const double thr = (double)ess_threshold;
         const double hi = 1.0 - (double)tau_old;
         int calls = 1;
         double delta = hi;
-        const double f_hi = ess_objective(ll, N, mx, hi, thr, s_red);
+        const double f_hi = poisoned ? 0.0 : ess_objective(ll, N, mx, hi, thr, s_red);  // (uniform over the block)
         if (f_hi < 0.0) {
             // scipy evaluates both ends again before iterating
             const double f_lo = ess_objective(ll, N, mx, 0.0, thr, s_red);

@@ -146,6 +146,12 @@ def run_stage_cases(be, cases, seed, max_particles=10000):
                 hi = O.ess_objective(ll[ti], delta[ti] + 3e-6, thr, dtype=np.float64)
                 assert lo > 0 > hi, ("bracket", c, ti, N, spread, lo, hi)
             same = abs(float(r["tau"][ti]) - float(otau[ti])) < 2e-5
+            if np.isneginf(ll[ti]).any():
+                # With a -inf entry the reference's objective is nan at delta = 0 (0 * -inf), brentq's first end point,
+                # and what scipy returns then hangs on the sign bit of that nan (0 if it is set: the C oracle's case).
+                # The kernel gives -inf particles no weight at every delta and brackets the root of the others --
+                # checked above; no comparison with the oracle here.
+                continue
             if not same:
                 assert clean and r["tau"][ti] < 1.0 and otau[ti] < 1.0, ("tau", c, ti, N, spread, r["tau"][ti], otau[ti])
                 grid = np.linspace(0.0, 1.0 - float(tin[ti]), 4001)

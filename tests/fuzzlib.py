@@ -145,7 +145,9 @@ def run_stage_cases(be, cases, seed, max_particles=10000):
                 lo = O.ess_objective(ll[ti], max(delta[ti] - 3e-6, 0.0), thr, dtype=np.float64)
                 hi = O.ess_objective(ll[ti], delta[ti] + 3e-6, thr, dtype=np.float64)
                 assert lo > 0 > hi, ("bracket", c, ti, N, spread, lo, hi)
-            same = abs(float(r["tau"][ti]) - float(otau[ti])) < 2e-5
+            # (2e-5 on the golden stages; the reference's float32 objective carries rounding noise of ~1e-7 |delta * loglik|
+            # relative, which at |loglik| ~ 500 moves ITS root by a few 1e-5 -- the kernel's root is the bracketed one)
+            same = abs(float(r["tau"][ti]) - float(otau[ti])) < 1e-4
             if np.isneginf(ll[ti]).any():
                 # With a -inf entry the reference's objective is nan at delta = 0 (0 * -inf), brentq's first end point,
                 # and what scipy returns then hangs on the sign bit of that nan (0 if it is set: the C oracle's case).

@@ -191,3 +191,55 @@ def run_stage_cases(be, cases, seed, max_particles=10000):
         gp = be.prune(locs, fluxes, 8.0, 8.0, 0.25)
         wp = O.prune(locs, fluxes, 8.0, 8.0, 0.25)
         assert all(np.array_equal(a, b) for a, b in zip(gp, wp)), ("prune", c)
+
+
+def run_prior_and_render_cases(be, cases, seed, max_particles=2000):
+    """PSF stack, rate image, log-prior (stars inside and outside the prior's support, partly empty catalogs) and
+    stratified prior draws on injected uniforms (min_objects < max_objects: several count strata), on random shapes
+    against the oracle."""
+    rng = np.random.default_rng(seed)
+    base = {"m71": Golden("loglik_m71_t8_d10").meta, "gauss": Golden("loglik_gauss_t8_d8").meta}
+    for c in range(cases):
+        kind = "m71" if rng.random() < 0.6 else "gauss"
+        meta = {k: (dict(v) if isinstance(v, dict) else v) for k, v in base[kind].items()}
+        side = int(rng.choice([8, 16, 32]))
+        D = int(rng.choice([1, 2, 5, 10, 17]))
+        N = int(rng.choice([n for n in (1, 3, 64, 257, 2000) if n <= max_particles]))
+        T = int(rng.choice([1, 2, 4]))
+        pad = int(rng.choice([0, 2, 4]))
+        dmin = int(rng.integers(0, D + 1))
+        meta.update(tile=side, D=D, min_objects=dmin, pad=pad)
+        meta["model_params"]["psf_radius"] = int(rng.choice([1, 3, 8, 12]))
+        if kind == "m71":
+            meta.pop("psf_norm", None)
+        om = oracle_model(meta, psf_norm=None) if kind == "m71" else oracle_model(meta)
+        am = abi_model(dict(meta, psf_norm=float(om.psf_norm))) if kind == "m71" else abi_model(meta)
+        lo, hi = (0.07, 800.0) if kind == "m71" else (400.0, 20000.0)
+        counts = rng.integers(dmin, D + 1, (T, N)).astype(np.float32)
+        live = np.arange(D)[None, None, :] < counts[..., None]
+        locs = (rng.uniform(-pad - 1.0, side + pad + 1.0, (T, N, D, 2)) * live[..., None]).astype(np.float32)  # some outside
+        fluxes = (np.exp(rng.uniform(np.log(lo * 0.8), np.log(hi), (T, N, D))) * live).astype(np.float32)
+        # PSF stack and rate image (small N: the dense stack is [T, h, w, N, D])
+        ns = min(N, 8)
+        psf = be.psf(am, locs[:, :ns], side, side)
+        ref = O.psf(om, locs[:, :ns], side, side)
+        assert np.array_equal(psf == 0, ref == 0), ("psf truncation mask", c, kind, side, D)
+        assert np.max(np.abs(psf - ref)) < 2e-6 * max(1.0, float(ref.max())), ("psf", c, kind, side, D)
+        assert rel_err(be.render(am, locs[:, :ns], fluxes[:, :ns], side, side),
+                       O.render(om, locs[:, :ns], fluxes[:, :ns], side, side)) < 1e-4, ("rate", c, kind, side, D)
+        # log-prior, including -inf for live stars outside the support and fluxes below the lower bound
+        ap, op = abi_prior(meta), oracle_prior(meta)
+        lp = be.prior_logprob(ap, counts, locs, fluxes)
+        assert rel_err(lp, O.prior_logprob(op, counts, locs, fluxes)) < 1e-4, ("log prior", c, kind, side, D, dmin)
+        # stratified prior draws on injected uniforms: counts exact, locations 1e-5, fluxes 1e-4
+        npc = int(rng.choice([1, 5, 33]))
+        M = (D - dmin + 1) * npc
+        ul, uf = rng.random((T, M, D, 2), dtype=np.float32), rng.random((T, M, D), dtype=np.float32)
+        cs, ls_, fs_ = be.prior_sample(ap, T, npc, D, ul, uf)
+        co, lo_, fo = O.prior_sample(op, ul, uf, npc)
+        assert np.array_equal(cs, co), ("prior sample counts", c)
+        assert np.max(np.abs(ls_ - lo_)) < 1e-5 * max(1.0, side + 2 * pad), ("prior sample locs", c)
+        assert np.array_equal(fs_ == 0, fo == 0), ("prior sample empty slots", c)
+        nz = fo > 0
+        if nz.any():
+            assert np.max(np.abs(fs_[nz] / fo[nz] - 1)) < 1e-4, ("prior sample fluxes", c, kind)

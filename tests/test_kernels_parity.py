@@ -513,6 +513,15 @@ def test_randomised_smc_stages_against_the_oracle(backend, request):
     run_stage_cases(backend, 40 if on_gpu else 8, seed=3, max_particles=10000 if on_gpu else 257)
 
 
+def test_randomised_prior_and_render_against_the_oracle(backend, request):
+    """PSF stack, rate image, log-prior and stratified prior draws on random shapes against the oracle
+    (tests/fuzzlib.py): truncation masks equal, -inf log-priors equal, counts of the draws exact."""
+    from fuzzlib import run_prior_and_render_cases
+
+    on_gpu = request.node.callspec.params["backend"] == "gpu"
+    run_prior_and_render_cases(backend, 60 if on_gpu else 12, seed=9, max_particles=2000 if on_gpu else 64)
+
+
 def test_match_catalogs_equals_the_reference(backend):
     """smcdet_match_catalogs against metrics.match_catalogs of the reference (scipy's linear_sum_assignment on
     every (tile, catalog) problem) on the catalogs the reference drew: per-bin totals and matches identical."""

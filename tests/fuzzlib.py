@@ -223,7 +223,9 @@ def run_prior_and_render_cases(be, cases, seed, max_particles=2000):
         ns = min(N, 8)
         psf = be.psf(am, locs[:, :ns], side, side)
         ref = O.psf(om, locs[:, :ns], side, side)
-        assert np.array_equal(psf == 0, ref == 0), ("psf truncation mask", c, kind, side, D)
+        # the patch truncation: exact zeros outside |i - floor(l)| <= R.  (Inside the patch a narrow Gaussian falls below
+        # 1e-38 a dozen pixels out; the device's ex2.approx.ftz flushes those denormals to zero, the CPU keeps them.)
+        assert np.array_equal(psf > 1e-30, ref > 1e-30) and np.all(psf[ref == 0] == 0), ("psf truncation mask", c, kind, side, D)
         assert np.max(np.abs(psf - ref)) < 2e-6 * max(1.0, float(ref.max())), ("psf", c, kind, side, D)
         assert rel_err(be.render(am, locs[:, :ns], fluxes[:, :ns], side, side),
                        O.render(om, locs[:, :ns], fluxes[:, :ns], side, side)) < 1e-4, ("rate", c, kind, side, D)

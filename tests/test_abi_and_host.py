@@ -259,3 +259,48 @@ def test_committed_bench_line_carries_the_contract():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["also"][0]["kind"] == "reference"
     s = d["strong"]
     assert len(s["checksum"]["sha256_16"]) == 16 and s["e2e"]["d2h_bytes_per_step"] > 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/smcdet"), reason="the reference tree only exists in the build container")
+def test_public_surface_matches_the_reference():
+    """Drop-in check against the unmodified reference (build container only): every class and function the reference's
+    library modules define exists here under the same name, constructors and methods take the reference's positional
+    arguments in the reference's order (extensions are keyword-only or trail them), and no public method is missing."""
+    import importlib
+    import inspect
+
+    sys.path.insert(0, "/root/reference")
+    try:
+        problems = []
+        for mod in ("sampler", "prior", "images", "kernel", "aggregate", "metrics", "distributions"):
+            ref, own = importlib.import_module("smcdet." + mod), importlib.import_module("smcdet_b200." + mod)
+            for name, rv in vars(ref).items():
+                if not (inspect.isclass(rv) or inspect.isfunction(rv)) or getattr(rv, "__module__", "") != ref.__name__:
+                    continue
+                if not hasattr(own, name):
+                    problems.append(f"missing {mod}.{name}")
+                    continue
+                ov = getattr(own, name)
+
+                def positional(fn):
+                    return [p.name for p in inspect.signature(fn).parameters.values()
+                            if p.name != "self" and p.kind == p.POSITIONAL_OR_KEYWORD]
+
+                if inspect.isfunction(rv):
+                    if positional(ov)[:len(positional(rv))] != positional(rv):
+                        problems.append(f"signature {mod}.{name}")
+                    continue
+                for m, member in vars(rv).items():
+                    if m.startswith("_") and m != "__init__":
+                        continue
+                    if not hasattr(ov, m):
+                        problems.append(f"missing {mod}.{name}.{m}")
+                    elif inspect.isfunction(member) and inspect.isfunction(getattr(ov, m)):
+                        a, b = positional(member), positional(getattr(ov, m))
+                        if b[:len(a)] != a:
+                            problems.append(f"signature {mod}.{name}.{m}: {a} vs {b}")
+        assert not problems, problems
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "smcdet" or k.startswith("smcdet.")]:
+            del sys.modules[k]

@@ -20,8 +20,10 @@ Scaling (--scaling):
   strong  ONE field of --field-tiles tiles (BASELINE.json configs[3]) sharded round-robin over the ranks
   both    (default) the line's `value` is the weak-scaling number; the object `strong` carries the fixed-field number
           and a checksum of the field's per-tile summaries, which must not depend on the number of GPUs
-In every mode the end-to-end region gathers the posterior catalogs with NCCL onto rank 0 and runs the reference's
-`Aggregate` finish there (aggregate.py:583-589), then reads the pruned catalogs back to the host.
+End-to-end region: pinned host tiles -> H2D -> samplers -> the reference's `Aggregate` finish (aggregate.py:583-589)
+-> pruned catalogs and summaries D2H.  For ONE field (strong scaling, and any 1-GPU run) the weighted catalogs of all
+tiles are first gathered with NCCL onto rank 0, which runs the finish; in weak scaling with several GPUs every rank owns
+its own field and finishes it itself (no catalog collective).  The last warm-up step goes through this path as well.
 
 A "step" is one complete run to temperature 1 over the rank's tiles.  `value` = particle-likelihood evaluations per
 second over the whole job, counted as the reference evaluates them: per SMC iteration and live tile N*(num_iters + 2)

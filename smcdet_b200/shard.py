@@ -235,8 +235,10 @@ class ShardedSMC(object):
 
         if self.block is None:
             raise ValueError("merge_blocks needs ShardedSMC(..., grid=, block=)")
-        s, b = self.sampler, self.block
-        B = len(self.local_blocks)
+        b, B = self.block, len(self.local_blocks)
+        if B == 0:  # fewer blocks than ranks: nothing to merge here (gather_blocks still takes part in the collective)
+            return None
+        s = self.sampler
         n, d = s.counts.shape[-1], s.fluxes.shape[-1]
         local = self._tiles[self.local_ids].to(self._device)
         shape = (B * b, b)
@@ -253,11 +255,13 @@ class ShardedSMC(object):
         """All-gather per-parent summaries of ``merge_blocks`` in global block order: [num_blocks, 4] =
         (log normalising constant, mean catalog size, mean detected count, mean detected flux)."""
         dev = self._device
+        nb = (self.grid[0] // self.block) * (self.grid[1] // self.block)
+        if agg is None:
+            return gather_tiles(torch.zeros(0, 4, device=dev), nb, self.group)
         summ = torch.stack([
             torch.tensor([z[0][0] if isinstance(z[0], list) else z[0] for z in agg.log_normalizing_constant], device=dev),
             agg.counts.float().mean(-1).reshape(-1), agg.pruned_counts.float().mean(-1).reshape(-1),
             agg.pruned_fluxes.sum(-1).mean(-1).reshape(-1)], -1)
-        nb = (self.grid[0] // self.block) * (self.grid[1] // self.block)
         return gather_tiles(summ.contiguous(), nb, self.group)
 
     def aggregate(self, grid, MutationKernel, *, resample_method=None, ess_threshold_prop=0.5, print_every=10**6,

@@ -148,6 +148,9 @@ class CountStratifiedSMC(object):
         S = mine.numel()
         if self._base_seed is None:
             self._base_seed = L.fresh_seed()
+        if S == 0:  # more ranks than strata: this rank only takes part in the all-gather of the evidences
+            self.local_sampler_iters, self.live_strata = 0, []
+            return mine, torch.zeros(0, device=dev), None
         counts, locs, fluxes = self._draw_segments(seg_tile, seg_cidx, pseudo_ids, self._base_seed)
         tiles = self.tiled_image.reshape(T, 1, self.tile_dim, self.tile_dim).contiguous()
         mh = deepcopy(self.MutationKernel)
@@ -172,7 +175,7 @@ class CountStratifiedSMC(object):
         T = nh * nw
         mine, logz_local, smp = self.run_local_strata()
         S = mine.numel()
-        self.iters = torch.full((ns,), int(smp.iter), dtype=torch.int64)
+        self.iters = torch.full((ns,), int(smp.iter) if smp is not None else 0, dtype=torch.int64)
         if self.world == 1:
             self.log_normalizing_constant = logz_local.reshape(nh, nw, ns)
             self.counts = smp.counts.reshape(nh, nw, ns * n)
@@ -192,7 +195,11 @@ class CountStratifiedSMC(object):
         for r in range(self.world):
             table[parts[r][: sizes[r], 0].long()] = parts[r][: sizes[r], 1].to(torch.float32)
         self.log_normalizing_constant = table.reshape(nh, nw, ns)
-        self.counts, self.locs, self.fluxes = smp.counts.reshape(S, n), smp.locs.reshape(S, n, d, 2), smp.fluxes.reshape(S, n, d)
+        if smp is None:
+            self.counts, self.locs, self.fluxes = (torch.zeros(0, n, device=dev), torch.zeros(0, n, d, 2, device=dev),
+                                                   torch.zeros(0, n, d, device=dev))
+        else:
+            self.counts, self.locs, self.fluxes = smp.counts.reshape(S, n), smp.locs.reshape(S, n, d, 2), smp.fluxes.reshape(S, n, d)
 
     def run(self):
         if self.batched:

@@ -580,20 +580,29 @@ __global__ void __launch_bounds__(kTB) temper_update_kernel(const float* __restr
 // Kernel 3: resampling -- float64 inclusive CDF (per-thread chunks + warp-shuffle scan of the chunk
 // totals) and one binary search per draw; one block per tile
 // ---------------------------------------------------------------------------------------------
+// SMEM: the CDF lives in shared memory (N doubles; the searches are dependent loads, 14 per draw at N = 10 000, so
+// their latency is the kernel -- 57 us per tile from global memory, a third of that from shared) and the draws of a
+// tile may be split over `slices` blocks, each of which builds the same CDF (bit-identical: same chunks, same scan) and
+// searches its share; block 0 of a tile also writes the CDF to cdf_all.  Without SMEM (N too large for shared memory)
+// one block per tile works on cdf_all directly.
+template <bool SMEM>
 __global__ void __launch_bounds__(kTB) resample_kernel(int method, const float* __restrict__ weights,
                                                        const double* __restrict__ u, uint64_t seed,
                                                        const int64_t* __restrict__ tile_ids,
                                                        const int32_t* __restrict__ active,
                                                        int64_t* __restrict__ index, double* __restrict__ cdf_all,
-                                                       int N) {
-    SMC_SHARED double s_warp[kTB / 32];
-    const int t = blockIdx.x;
+                                                       int N, int slices) {
+    SMC_DYN_SHARED(double, s_dyn);       // [kTB / 32] warp totals, then (SMEM) the CDF
+    double* s_warp = s_dyn;
+    const int t = blockIdx.x / slices, slice = blockIdx.x - t * slices;
+    const int first = slice * kTB + (int)threadIdx.x, stride = slices * kTB;
     if (active != nullptr && active[t] == 0) {
-        for (int i = threadIdx.x; i < N; i += kTB) index[(size_t)t * N + i] = i;
+        for (int i = first; i < N; i += stride) index[(size_t)t * N + i] = i;
         return;
     }
     const float* w = weights + (size_t)t * N;
-    double* cdf = cdf_all + (size_t)t * N;
+    double* cdf_out = cdf_all + (size_t)t * N;
+    double* cdf = SMEM ? (s_dyn + kTB / 32) : cdf_out;
     const int chunk = (N + kTB - 1) / kTB;
     const int lo = min(N, (int)threadIdx.x * chunk), hi = min(N, lo + chunk);
     double local = 0.0;
@@ -614,6 +623,7 @@ __global__ void __launch_bounds__(kTB) resample_kernel(int method, const float* 
     for (int i = lo; i < hi; ++i) {
         run += (double)w[i];
         cdf[i] = run;
+        if (SMEM && slice == 0) cdf_out[i] = run;
     }
     __syncthreads();
     const double total = cdf[N - 1];
@@ -627,7 +637,7 @@ __global__ void __launch_bounds__(kTB) resample_kernel(int method, const float* 
             u_sys = u01_d(r.v[0], r.v[1]);
         }
     }
-    for (int i = threadIdx.x; i < N; i += kTB) {
+    for (int i = first; i < N; i += stride) {
         double ui;
         if (method == SMCDET_RESAMPLE_SYSTEMATIC) {
             ui = ((double)i + u_sys) / (double)N;
@@ -1869,7 +1879,24 @@ int smcdet_resample(int method, const float* weights, const double* u, uint64_t 
                 "smcdet_resample: unknown method");
     SMC_REQUIRE(weights && index && cdf_scratch, SMCDET_E_INVALID, "smcdet_resample: null pointer");
     SMC_REQUIRE(T > 0 && N > 0, SMCDET_E_INVALID, "smcdet_resample: non-positive size");
-    SMC_LAUNCH(resample_kernel, T, kTB, 0, (cudaStream_t)stream, method, weights, u, seed, tile_ids, active, index, cdf_scratch, N);
+    const size_t warp_bytes = sizeof(double) * (kTB / 32);
+    const size_t smem = warp_bytes + sizeof(double) * (size_t)N;
+    if (smem <= 200 * 1024) {
+        // the CDF in shared memory; few tiles: the draws of a tile split over several blocks (about two blocks per SM)
+        const int slices = (int)std::min<long long>(16, std::max<long long>(1, (2LL * num_sms()) / T));
+        SMC_REQUIRE((long long)T * slices < (1LL << 31), SMCDET_E_TOO_LARGE, "smcdet_resample: grid too large");
+#ifndef SMC_HOSTSIM
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(resample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(resample_kernel)");
+        }
+#endif
+        SMC_LAUNCH(resample_kernel<true>, (unsigned)(T * slices), kTB, smem, (cudaStream_t)stream, method, weights, u, seed,
+                   tile_ids, active, index, cdf_scratch, N, slices);
+    } else {
+        SMC_LAUNCH(resample_kernel<false>, T, kTB, warp_bytes, (cudaStream_t)stream, method, weights, u, seed, tile_ids, active,
+                   index, cdf_scratch, N, 1);
+    }
     return launch_status("resample_kernel");
 }
 

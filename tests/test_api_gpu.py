@@ -636,6 +636,7 @@ def test_checkpoint_resume_is_bit_identical(freeze, tmp_path):
     whole = make()
     whole.record_history = True
     whole.stage_timing = True
+    whole.nvtx_ranges = True   # every stage inside an NVTX range smcdet/<stage>/iter<k> (pushes and pops balance)
     whole.run()
     ms = whole.stage_report()
     assert set(ms) == {"resample", "mutate", "temper+update_weights"} and all(v > 0 for v in ms.values())

@@ -1315,3 +1315,34 @@ def test_merged_evidence_against_the_exact_parent_evidence():
     assert float(one) > 0.9
     loc = agg.locs[0, 0][agg.counts[0, 0] >= 1][:, 0]
     assert abs(float(loc[:, 0].median()) - 5.3) < 1.0 and abs(float(loc[:, 1].median()) - 3.4) < 1.0
+
+
+def test_the_ctypes_stub_of_integration_md_runs_as_printed():
+    """INTEGRATION.md section 2 shows the binding a maintainer of the reference would add (a ctypes stub that replaces
+    the body of M71ImageModel.loglikelihood, images.py:159-175).  The code block is executed here exactly as printed
+    (only the library path is made absolute) and must give this package's own log-likelihoods."""
+    import os
+    import re
+    import types
+
+    from smcdet_b200 import _lib as L
+    from smcdet_b200.images import M71ImageModel
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# smcdet/_b200.py.*?)```", text, re.S).group(1)
+    assert 'C.CDLL("libsmcdet_b200.so")' in block
+    block = block.replace('C.CDLL("libsmcdet_b200.so")', f'C.CDLL("{L.LIB_PATH}")')
+    mod = types.ModuleType("integration_stub")
+    exec(compile(block, "INTEGRATION.md", "exec"), mod.__dict__)
+
+    g = Golden("loglik_m71_t8_d10")
+    mp = g.meta["model_params"]
+    own = M71ImageModel(8, 8, background=mp["background"], psf_radius=mp["psf_radius"], adu_per_nmgy=mp["adu_per_nmgy"],
+                        psf_params=mp["psf_params"], noise_additive=mp["noise_additive"],
+                        noise_multiplicative=mp["noise_multiplicative"])
+    tiles, locs, fluxes = cu(g["tiles"]), cu(g["locs"]), cu(g["fluxes"])
+    got = mod.m71_loglikelihood(own, tiles, locs, fluxes)          # bound as a method in the reference
+    want = own.loglikelihood(tiles, locs, fluxes)
+    assert got.shape == want.shape and torch.equal(got, want)
+    assert rel_err(got.cpu().numpy(), g["loglik"]) < RTOL

@@ -667,7 +667,9 @@ def run_own(a):
     traffic = None
     try:  # DRAM bytes per particle-launch from the committed ncu --set full capture of this kernel
         prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_mh_kernel.json")))
-        traffic = prof["dram_bytes_per_particle"] * live_particles / max(1, n_launch)
+        # (captured at D = 10: 248 algorithmic bytes per particle; other catalog sizes are scaled by their own figure)
+        traffic = (prof["dram_bytes_per_particle"] * bytes_per_launch_particle / prof["algorithmic_bytes_per_particle"]
+                   * live_particles / max(1, n_launch))
     except Exception:  # noqa: BLE001
         pass
     kname = "mh_kernel<M71,8,8,TPP=1>" if is_m71(a) else "mh_kernel<GAUSS,8,8,TPP=1>"
@@ -686,7 +688,12 @@ def run_own(a):
                 "launches": n_launch, "avg_launch_ms": mh_ms / max(1, n_launch),
                 "share_of_step": mh_ms / main["ms"], "traffic": traffic,
                 "traffic_source": "dram__bytes_read+write per particle of the committed ncu --set full capture "
-                                  "(profiles/r02_ncu_mh_kernel.json) x the live particles of this run",
+                                  "(profiles/r02_ncu_mh_kernel.json: M71 model, D = 10; scaled by 24 D + 8 bytes for other "
+                                  "catalog sizes) x the live particles of this run",
+                "bound_note": None if is_m71(a) else "the Gaussian-PSF kernel issues ~110 MUFU against ~1500 other "
+                              "instructions per sweep: it is bound by instruction issue / latency (ncu: XU 40 %, issue "
+                              "62 %, profiles/r02_ncu_mh_gauss.txt), so frac is not its pipe utilisation; "
+                              "fp32_achieved_tinstr / fp32_peak_tinstr is the figure that applies (DESIGN.md 3.7)",
                 "algorithmic_bytes_per_launch": live_particles * bytes_per_launch_particle / max(1, n_launch),
                 "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "frac": hbm_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}}

@@ -662,7 +662,8 @@ def run_own(a):
     sfu_peak = 148 * 16 * sm_max * 1e6 / 1e12          # TOP/s (MUFU results per second)
     fp32_peak = 148 * 128 * sm_max * 1e6 / 1e12        # T instr/s (FMA = 1 instr)
     achieved = live_particles * mufu_per_particle / (mh_ms * 1e-3) / 1e12
-    bytes_per_launch_particle = 2 * (12 * D) + 4 + 4   # read + write catalog, count, loglik out
+    # read the catalog and its count through the 8-byte resampling index, write catalog + count, loglik out
+    bytes_per_launch_particle = 2 * (12 * D + 4) + 8 + 4
     hbm_gbs = live_particles * bytes_per_launch_particle / (mh_ms * 1e-3) / 1e9
     traffic = None
     try:  # DRAM bytes per particle-launch from the committed ncu --set full capture of this kernel
@@ -672,8 +673,9 @@ def run_own(a):
                    * live_particles / max(1, n_launch))
     except Exception:  # noqa: BLE001
         pass
-    kname = "mh_kernel<M71,8,8,TPP=1>" if is_m71(a) else "mh_kernel<GAUSS,8,8,TPP=1>"
-    roofline = {"kernel": f"{kname} (smcdet_mh_mutate)", "bound": "sfu",
+    kname = "mh_kernel<M71,8,8,TPP=1,GATHER>" if is_m71(a) else "mh_kernel<GAUSS,8,8,TPP=1,GATHER>"
+    roofline = {"kernel": f"{kname} (smcdet_mh_mutate_resampled: the MH sweeps with the resampling step's gather fused in)",
+                "bound": "sfu",
                 "achieved": achieved, "peak": sfu_peak, "unit": "TOP/s (MUFU)", "frac": achieved / sfu_peak,
                 "peak_source": f"derived: 148 SMs x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); "
                                "the path is SFU/FP32-bound, not HBM- or tensor-bound (SURVEY.md 8d)",

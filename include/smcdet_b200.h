@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMCDET_ABI_VERSION 6
+#define SMCDET_ABI_VERSION 7
 
 enum {
     SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
@@ -235,6 +235,31 @@ int smcdet_mh_mutate(const smcdet_model_params *model, const smcdet_prior_params
                      uint64_t seed, uint64_t offset, const int64_t *tile_ids,
                      const int32_t *active, int32_t *status, int T, int N, int D, int h, int w,
                      void *stream);
+
+/* SMCsampler.resample's gather (sampler.py:150-169) fused into the mutation launch that follows it
+ * (sampler.py:244-245): particle n of tile t enters the sweeps as particle index[t,n] of the SOURCE
+ * arrays and leaves in locs / fluxes / counts_out, so an SMC iteration is smcdet_resample,
+ * smcdet_mh_mutate_resampled, smcdet_temper_update -- the copy smcdet_gather would write and the
+ * mutation read again is never made.  copy_mask [T] (nullable): tiles with active == 0 whose particles
+ * still have to reach the destination arrays (their index is the identity).  Results are bit-identical
+ * to smcdet_gather followed by smcdet_mh_mutate.  Source and destination arrays must not overlap. */
+typedef struct smcdet_resampled_source {
+    const int64_t *index;    /* [T,N] from smcdet_resample                         */
+    const float *counts;     /* [T,N]     source catalogs                           */
+    const float *locs;       /* [T,N,D,2]                                           */
+    const float *fluxes;     /* [T,N,D]                                             */
+    float *counts_out;       /* [T,N] destination of the gathered counts            */
+    const int32_t *copy_mask; /* [T] nullable                                       */
+} smcdet_resampled_source;
+
+int smcdet_mh_mutate_resampled(const smcdet_model_params *model, const smcdet_prior_params *prior,
+                               const smcdet_mh_params *mh, const float *tiles,
+                               const smcdet_resampled_source *source, float *locs, float *fluxes,
+                               const float *tau, float *loglik_out, float *acc_rate,
+                               const smcdet_draw_tape *tape, const smcdet_mh_trace *trace,
+                               uint64_t seed, uint64_t offset, const int64_t *tile_ids,
+                               const int32_t *active, int32_t *status, int T, int N, int D, int h,
+                               int w, void *stream);
 
 /* SingleComponentMALA.run with log_target = SMCsampler.log_target (smcdet/kernel.py:133-275): as
  * smcdet_mh_mutate, but each sweep proposes from a truncated normal centred at

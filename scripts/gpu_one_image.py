@@ -21,6 +21,7 @@ for rep in range(reps):
     mh = SingleComponentMH(100, 0.1, 2.5, PRIOR["flux_lower"], PRIOR["flux_upper"])
     s = SMCsampler(tiles, 8, prior, model, mh, 10000, 0.5, "multinomial", DETECTION, 200, verbose=False)
     s.stage_timing = rep == reps - 1
+    s.fused_gather = os.environ.get("FUSED_GATHER", "1") != "0"   # 0: separate smcdet_gather launch (four per iteration)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     s.run()
     torch.cuda.synchronize(); dt = time.perf_counter() - t0

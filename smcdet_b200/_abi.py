@@ -2,7 +2,7 @@
 
 import ctypes as C
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 MODEL_GAUSS_POISSON, MODEL_M71_NORMAL = 0, 1
 COUNT_DISCRETE_UNIFORM, COUNT_POISSON, COUNT_NONE = 0, 1, 2
@@ -67,6 +67,11 @@ class MHTrace(C.Structure):
                 ("chain_locs", C.c_void_p), ("chain_fluxes", C.c_void_p)]
 
 
+class ResampledSource(C.Structure):
+    _fields_ = [("index", C.c_void_p), ("counts", C.c_void_p), ("locs", C.c_void_p), ("fluxes", C.c_void_p),
+                ("counts_out", C.c_void_p), ("copy_mask", C.c_void_p)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 
@@ -86,6 +91,9 @@ PROTOTYPES = {
     "smcdet_mh_mutate": (C.c_int, [C.POINTER(ModelParams), C.POINTER(PriorParams), C.POINTER(MHParams),
                                    _P, _P, _P, _P, _P, _P, _P, C.POINTER(DrawTape), C.POINTER(MHTrace),
                                    C.c_uint64, C.c_uint64, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "smcdet_mh_mutate_resampled": (C.c_int, [C.POINTER(ModelParams), C.POINTER(PriorParams), C.POINTER(MHParams),
+                                             _P, C.POINTER(ResampledSource), _P, _P, _P, _P, _P, C.POINTER(DrawTape),
+                                             C.POINTER(MHTrace), C.c_uint64, C.c_uint64, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "smcdet_mala_mutate": (C.c_int, [C.POINTER(ModelParams), C.POINTER(PriorParams), C.POINTER(MHParams),
                                      _P, _P, _P, _P, _P, _P, _P, C.POINTER(DrawTape), C.POINTER(MHTrace),
                                      C.c_uint64, C.c_uint64, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

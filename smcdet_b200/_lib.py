@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
 # kernels launched by one call of each entry point (smcdet_mh_mutate: zero + mh + divide)
 KERNELS_PER_CALL = {
     "smcdet_loglik": 1, "smcdet_loglik_segments": 1, "smcdet_psf": 1, "smcdet_psf_radial": 1, "smcdet_render": 1, "smcdet_prior_logprob": 1, "smcdet_prior_sample": 1,
-    "smcdet_temper_update": 1, "smcdet_resample": 1, "smcdet_gather": 1, "smcdet_mh_mutate": 3, "smcdet_mala_mutate": 3, "smcdet_prune": 1,
+    "smcdet_temper_update": 1, "smcdet_resample": 1, "smcdet_gather": 1, "smcdet_mh_mutate": 3, "smcdet_mh_mutate_resampled": 3, "smcdet_mala_mutate": 3, "smcdet_prune": 1,
     "smcdet_match_catalogs": 1, "smcdet_agg_join": 1, "smcdet_agg_unjoin": 1, "smcdet_agg_mutate": 3,
 }
 

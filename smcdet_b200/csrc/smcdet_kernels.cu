@@ -159,6 +159,27 @@ __device__ __forceinline__ void stage_stars(const float* __restrict__ locs, cons
     }
 }
 
+// the same through the resampling indices: particle pi of the block is the source tile's particle idx[pi]
+// (the gather fused into the mutation launch; a record is 12 D contiguous bytes, so reads stay sector-sized)
+template <int PB>
+__device__ __forceinline__ void stage_stars_gather(const float* __restrict__ locs_tile, const float* __restrict__ fluxes_tile,
+                                                   const int64_t* __restrict__ idx, int n_here, int D, float* s_star) {
+    const int nl = n_here * 2 * D;
+    for (int i = threadIdx.x; i < nl; i += kBT) {
+        const int pi = i / (2 * D), r = i - pi * 2 * D;
+        s_star[((r >> 1) * 3 + (r & 1)) * PB + pi] = locs_tile[(size_t)idx[pi] * 2 * D + r];
+    }
+    const int nf = n_here * D;
+    for (int i = threadIdx.x; i < nf; i += kBT) {
+        const int pi = i / D, d = i - pi * D;
+        s_star[(d * 3 + 2) * PB + pi] = fluxes_tile[(size_t)idx[pi] * D + d];
+    }
+    for (int i = threadIdx.x; i < (PB - n_here) * 3 * D; i += kBT) {
+        const int pi = n_here + i / (3 * D), r = i % (3 * D);
+        s_star[r * PB + pi] = 0.0f;
+    }
+}
+
 template <int MODEL, int HW, int PB, int PPT>
 __device__ __forceinline__ void stage_block(const float* __restrict__ tile, const float* __restrict__ locs,
                                             const float* __restrict__ fluxes, int n_here, int D,
@@ -827,12 +848,20 @@ struct MHArgs {
     const int32_t* tile_map;
     int32_t* status;
     int T, N, D, blocks_per_tile;
+    // gather fused into the launch (mh_kernel<..., GATHER = true>): particle n of tile t is read from the source arrays at
+    // gather_index[t, n] (the resampling step's indices) and written, with its count, to locs / fluxes / counts_out
+    const int64_t* gather_index;
+    const float* counts_src;
+    const float* locs_src;
+    const float* fluxes_src;
+    float* counts_out;
+    const int32_t* copy_mask;
 };
 
 #ifndef SMC_MH_MINB
 #define SMC_MH_MINB 3
 #endif
-template <int MODEL, int H, int W, int TPP, bool MALA>
+template <int MODEL, int H, int W, int TPP, bool MALA, bool GATHER = false>
 // Resident blocks per SM: 3 for 64 pixels per lane (168 registers); 5 for 8 pixels per lane, the decomposition of
 // a single 8x8 tile -- 10 000 particles x 8 lanes are 625 blocks, which 5 x 148 slots take in ONE wave (4 x 148 do not)
 __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_MH_MINB : (((H / TPP) * W <= 8) ? 5 : 4)))
@@ -846,14 +875,34 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     float* s_rate = s_star + 3 * a.D * PB;    // [PPT][kBT]
 
     const int t = blockIdx.x / a.blocks_per_tile;
-    if (a.active != nullptr && a.active[t] == 0) return;
     const int N = a.N, D = a.D;
     const int n0 = (blockIdx.x - t * a.blocks_per_tile) * PB;
     const int n_here = min(PB, N - n0);
     const size_t pbase = (size_t)t * N + n0;
+    if (a.active != nullptr && a.active[t] == 0) {
+        if constexpr (GATHER) {
+            // a tile that is not mutated but whose particles have to reach the destination buffers (it finished in
+            // the previous iteration: both buffer sets then hold its final particles) is copied through its indices
+            if (a.copy_mask != nullptr && a.copy_mask[t] != 0) {
+                stage_stars_gather<PB>(a.locs_src + (size_t)t * N * 2 * D, a.fluxes_src + (size_t)t * N * D,
+                                       a.gather_index + pbase, n_here, D, s_star);
+                __syncthreads();
+                unstage_block<PB>(a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D, s_star);
+                for (int i = threadIdx.x; i < n_here; i += kBT)
+                    a.counts_out[pbase + i] = a.counts_src[(size_t)t * N + a.gather_index[pbase + i]];
+            }
+        }
+        return;
+    }
     const int ti = a.tile_map != nullptr ? a.tile_map[t] : t;  // the segment's image (count strata share their tile's)
-    stage_block<MODEL, HW, PB, PPT>(a.tiles + (size_t)ti * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
-                               s_tile, s_lgam, s_star);
+    if constexpr (GATHER) {
+        stage_tile<MODEL, HW, PPT>(a.tiles + (size_t)ti * HW, s_tile, s_lgam);
+        stage_stars_gather<PB>(a.locs_src + (size_t)t * N * 2 * D, a.fluxes_src + (size_t)t * N * D, a.gather_index + pbase,
+                               n_here, D, s_star);
+    } else {
+        stage_block<MODEL, HW, PB, PPT>(a.tiles + (size_t)ti * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
+                                        s_tile, s_lgam, s_star);
+    }
     __syncthreads();
 
     const ModelK& m = a.m;
@@ -866,7 +915,8 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     const float* my_star = s_star + pi;
 
     // ---- per-particle constants
-    const float count = valid ? a.counts[pn] : (float)D;
+    float count = (float)D;
+    if (valid) count = GATHER ? a.counts_src[(size_t)t * N + a.gather_index[pn]] : a.counts[pn];
     const float tau = a.tau[t];
     // log prior (prior.py:67-75, :220-226) kept as: count term + sum of finite star terms, and the number
     // of live stars outside the location prior's support (each contributes -inf); a single-star move
@@ -1136,6 +1186,9 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         }
     }
     if (a.loglik_out != nullptr && valid && sub == 0) a.loglik_out[pn] = ll;
+    if constexpr (GATHER) {
+        if (valid && sub == 0) a.counts_out[pn] = count;
+    }
     const unsigned votes = __ballot_sync(0xffffffffu, valid && sub == 0 && last_acc);
     if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(a.acc_count + t, (float)__popc(votes));
     __syncthreads();
@@ -1670,13 +1723,13 @@ int launch_loglik_t(const ModelK& m, const float* tiles, const float* locs, cons
     }
 }
 
-template <int MODEL, int H, int TPP, bool MALA>
+template <int MODEL, int H, int TPP, bool MALA, bool GATHER = false>
 int launch_mh_t(MHArgs& a, cudaStream_t st) {
     constexpr int PB = kBT / TPP, PPT = (H / TPP) * H;
     a.blocks_per_tile = (a.N + PB - 1) / PB;
     const size_t smem = sizeof(float) * (2 * TileLayout<PPT, H * H>::kSize + 3 * (size_t)a.D * PB + (size_t)PPT * kBT);
     if ((long long)a.T * a.blocks_per_tile >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_mh_mutate: grid too large");
-    auto kern = mh_kernel<MODEL, H, H, TPP, MALA>;
+    auto kern = mh_kernel<MODEL, H, H, TPP, MALA, GATHER>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mh)");
@@ -1707,10 +1760,13 @@ template <int MODEL, int H, int TPP>
 int launch_mh_plain(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, false>(a, st); }
 template <int MODEL, int H, int TPP>
 int launch_mh_mala(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, true>(a, st); }
+template <int MODEL, int H, int TPP>
+int launch_mh_gather(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, false, true>(a, st); }
 
 template <int MODEL, int H>
 int dispatch_mh_tpp(int tpp, bool mala, MHArgs& a, cudaStream_t st) {
     if (mala) { SMC_DISPATCH_TPP(launch_mh_mala, MODEL, H, tpp, a, st) }
+    if (a.gather_index != nullptr) { SMC_DISPATCH_TPP(launch_mh_gather, MODEL, H, tpp, a, st) }
     SMC_DISPATCH_TPP(launch_mh_plain, MODEL, H, tpp, a, st)
 }
 
@@ -1924,14 +1980,22 @@ int smcdet_gather(const int64_t* index, const float* counts_in, const float* loc
 }
 
 static int mutate_impl(bool mala, const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
-                     const float* tiles, const float* counts, float* locs, float* fluxes, const float* tau,
+                     const float* tiles, const smcdet_resampled_source* source, const float* counts, float* locs, float* fluxes,
+                     const float* tau,
                      float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
                      uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
                      int T, int N, int D, int h, int w, void* stream) {
     DeviceGuard guard(locs);
     SMC_REQUIRE(model_ok(model) && prior && mh, SMCDET_E_INVALID, "smcdet_mh_mutate: bad parameters");
-    SMC_REQUIRE(tiles && counts && locs && fluxes && tau && acc_rate, SMCDET_E_INVALID,
+    SMC_REQUIRE(tiles && (counts || source) && locs && fluxes && tau && acc_rate, SMCDET_E_INVALID,
                 "smcdet_mh_mutate: null pointer");
+    if (source != nullptr) {
+        SMC_REQUIRE(!mala, SMCDET_E_UNSUPPORTED, "smcdet_mh_mutate_resampled: not available for the MALA kernel");
+        SMC_REQUIRE(source->index && source->counts && source->locs && source->fluxes && source->counts_out, SMCDET_E_INVALID,
+                    "smcdet_mh_mutate_resampled: null pointer in the source");
+        SMC_REQUIRE(source->locs != locs && source->fluxes != fluxes && source->counts != source->counts_out, SMCDET_E_INVALID,
+                    "smcdet_mh_mutate_resampled: source and destination arrays must differ");
+    }
     SMC_REQUIRE(T > 0 && N > 0 && D > 0 && mh->num_iters >= 0, SMCDET_E_INVALID, "smcdet_mh_mutate: bad sizes");
     SMC_REQUIRE(h == w && (h == 8 || h == 16 || h == 32), SMCDET_E_UNSUPPORTED,
                 "smcdet_mh_mutate: tile must be 8x8, 16x16 or 32x32");
@@ -1955,6 +2019,10 @@ static int mutate_impl(bool mala, const smcdet_model_params* model, const smcdet
     a.seed = seed; a.offset = offset; a.tile_ids = tile_ids; a.active = active; a.status = status;
     a.tile_map = mh->tile_of_segment;
     a.T = T; a.N = N; a.D = D;
+    if (source != nullptr) {
+        a.gather_index = source->index; a.counts_src = source->counts; a.locs_src = source->locs;
+        a.fluxes_src = source->fluxes; a.counts_out = source->counts_out; a.copy_mask = source->copy_mask;
+    }
     // acc_as_count: the caller keeps acc_rate zero-filled between launches and divides by N itself
     // (smcdet_temper_update does both through smcdet_loop_state), which saves two small launches per call
     if (!mh->acc_as_count) SMC_LAUNCH(zero_active_kernel, (T + 255) / 256, 256, 0, st, acc_rate, active, T);
@@ -1974,8 +2042,18 @@ int smcdet_mh_mutate(const smcdet_model_params* model, const smcdet_prior_params
                      float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
                      uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
                      int T, int N, int D, int h, int w, void* stream) {
-    return mutate_impl(false, model, prior, mh, tiles, counts, locs, fluxes, tau, loglik_out, acc_rate, tape, trace, seed,
-                       offset, tile_ids, active, status, T, N, D, h, w, stream);
+    return mutate_impl(false, model, prior, mh, tiles, nullptr, counts, locs, fluxes, tau, loglik_out, acc_rate, tape, trace,
+                       seed, offset, tile_ids, active, status, T, N, D, h, w, stream);
+}
+
+int smcdet_mh_mutate_resampled(const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
+                               const float* tiles, const smcdet_resampled_source* source, float* locs, float* fluxes,
+                               const float* tau, float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape,
+                               const smcdet_mh_trace* trace, uint64_t seed, uint64_t offset, const int64_t* tile_ids,
+                               const int32_t* active, int32_t* status, int T, int N, int D, int h, int w, void* stream) {
+    if (source == nullptr) return fail(SMCDET_E_INVALID, "smcdet_mh_mutate_resampled: null source");
+    return mutate_impl(false, model, prior, mh, tiles, source, nullptr, locs, fluxes, tau, loglik_out, acc_rate, tape, trace,
+                       seed, offset, tile_ids, active, status, T, N, D, h, w, stream);
 }
 
 int smcdet_mala_mutate(const smcdet_model_params* model, const smcdet_prior_params* prior, const smcdet_mh_params* mh,
@@ -1983,8 +2061,8 @@ int smcdet_mala_mutate(const smcdet_model_params* model, const smcdet_prior_para
                        float* loglik_out, float* acc_rate, const smcdet_draw_tape* tape, const smcdet_mh_trace* trace,
                        uint64_t seed, uint64_t offset, const int64_t* tile_ids, const int32_t* active, int32_t* status,
                        int T, int N, int D, int h, int w, void* stream) {
-    return mutate_impl(true, model, prior, mh, tiles, counts, locs, fluxes, tau, loglik_out, acc_rate, tape, trace, seed,
-                       offset, tile_ids, active, status, T, N, D, h, w, stream);
+    return mutate_impl(true, model, prior, mh, tiles, nullptr, counts, locs, fluxes, tau, loglik_out, acc_rate, tape, trace,
+                       seed, offset, tile_ids, active, status, T, N, D, h, w, stream);
 }
 
 int smcdet_prune(const float* locs, const float* fluxes, float tile_h, float tile_w, float flux_threshold,

@@ -52,10 +52,13 @@ class SingleComponentMH(object):
 
     def launch(self, prior, model, tiles, counts, locs, fluxes, tau, loglik_out, acc, status, *, seed, offset=0,
                tile_ids=None, active=None, tile_of_segment=None, live_tiles_hint=0, acc_as_count=False, tape=None,
-               trace=None):
+               trace=None, resampled=None):
         """One call of the fused kernel on caller-owned, already flattened device buffers ([T, ...]; nothing is
         allocated or copied here).  ``run`` goes through it; ``SMCsampler`` calls it directly with its persistent
-        state.  ``acc_as_count``: accept counts are ADDED to ``acc`` (see ``smcdet_mh_params`` in the header)."""
+        state.  ``acc_as_count``: accept counts are ADDED to ``acc`` (see ``smcdet_mh_params`` in the header).
+        ``resampled`` = (index, counts_src, locs_src, fluxes_src, copy_mask): the gather of the resampling step is done
+        by the launch itself (``smcdet_mh_mutate_resampled``) -- particles are read from the source arrays through
+        ``index`` and ``counts`` / ``locs`` / ``fluxes`` are pure outputs."""
         T, n, d = fluxes.shape
         mp, pp, kp = model._params(), prior._params(), self._params()
         kp.acc_as_count = 1 if acc_as_count else 0
@@ -65,12 +68,21 @@ class SingleComponentMH(object):
         if self.event_log is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(dev))
-        L.check(getattr(L.lib(), self._entry)(
-            C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), L.ptr(counts), L.ptr(locs), L.ptr(fluxes), L.ptr(tau),
-            L.ptr(loglik_out), L.ptr(acc), C.byref(tape) if tape is not None else None,
-            C.byref(trace) if trace is not None else None, int(seed), int(offset), L.ptr(tile_ids, torch.int64),
-            L.ptr(active, torch.int32), L.ptr(status, torch.int32), T, n, d, model.image_height, model.image_width,
-            L.stream_for(locs)))
+        tail = (L.ptr(locs), L.ptr(fluxes), L.ptr(tau), L.ptr(loglik_out), L.ptr(acc),
+                C.byref(tape) if tape is not None else None, C.byref(trace) if trace is not None else None, int(seed),
+                int(offset), L.ptr(tile_ids, torch.int64), L.ptr(active, torch.int32), L.ptr(status, torch.int32), T, n, d,
+                model.image_height, model.image_width, L.stream_for(locs))
+        if resampled is None:
+            L.check(getattr(L.lib(), self._entry)(C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), L.ptr(counts), *tail))
+        else:
+            if self._entry != "smcdet_mh_mutate":
+                raise NotImplementedError("the fused gather exists for the MH kernel only")
+            index, counts_src, locs_src, fluxes_src, copy_mask = resampled
+            v = lambda p: None if p is None else p.value  # noqa: E731  (c_void_p fields take plain integers)
+            src = A.ResampledSource(v(L.ptr(index, torch.int64)), v(L.ptr(counts_src)), v(L.ptr(locs_src)),
+                                    v(L.ptr(fluxes_src)), v(L.ptr(counts)), v(L.ptr(copy_mask, torch.int32)))
+            L.check(L.lib().smcdet_mh_mutate_resampled(C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), C.byref(src),
+                                                       *tail))
         if acc_as_count:
             L.lib().adjust(-2)  # no zero-fill and no divide launch
         if self.event_log is not None:

@@ -3,7 +3,7 @@
 One iteration is ``resample -> mutate (MH) -> temper -> update_weights`` (reference sampler.py:244-247);
 every stage is a launch of the CUDA library on the whole [numH, numW] grid of tiles:
 
-  resample        smcdet_resample (float64 CDF + search) + smcdet_gather
+  resample        smcdet_resample (float64 CDF + search) + smcdet_gather (run(): the gather is fused into the mutation launch)
   mutate          smcdet_mh_mutate (all MH sweeps fused; also yields the new log-likelihood)
   temper          smcdet_temper_update(do_temper=1): on-device Brent solve of ESS(delta) = rho N
   update_weights  smcdet_temper_update(do_temper=0): softmax weights, ESS, log normalising constant
@@ -411,9 +411,10 @@ class SMCsampler(object):
             prev, cur = cur, post_flag()
 
     def _iterate_fused(self):
-        """The SMC loop on persistent device state (the ``freeze_finished`` case first): per iteration exactly four launches --
-        ``smcdet_resample``, ``smcdet_gather``, ``smcdet_mh_mutate``, ``smcdet_temper_update`` -- and one 4-byte
-        device-to-host copy.  Everything the plain loop does between the stages with small tensor operations
+        """The SMC loop on persistent device state (the ``freeze_finished`` case first): per iteration exactly three launches --
+        ``smcdet_resample``, ``smcdet_mh_mutate_resampled`` (the MH sweeps read the resampled particles through the indices
+        themselves; with ``fused_gather = False`` or another kernel: ``smcdet_gather`` + the kernel's own launch, four),
+        ``smcdet_temper_update`` -- and one 4-byte device-to-host copy.  Everything the plain loop does between the stages with small tensor operations
         (the mask of live tiles, keeping finished tiles' results, the loop test ``torch.any(temperature < 1)`` of
         reference sampler.py:230, acceptance counts -> rates) happens inside those kernels (``active`` masks,
         ``smcdet_loop_state``, ``acc_as_count``); particles ping-pong between two buffer sets and a finished tile is
@@ -454,6 +455,9 @@ class SMCsampler(object):
         base = self.iter
         ring = [torch.empty(1, dtype=torch.int32, pin_memory=True) for _ in range(3)]
         stream = torch.cuda.current_stream(dev)
+        # the MH kernel gathers the resampled particles itself (smcdet_mh_mutate_resampled): three launches per iteration
+        fused_gather = bool(getattr(self, "fused_gather", True)) and getattr(mk, "_entry", "") == "smcdet_mh_mutate"
+        everything = torch.ones(T, device=dev, dtype=torch.int32)
 
         def post(k):  # asynchronous read-back of live[k]
             host = ring[k % len(ring)]
@@ -469,18 +473,27 @@ class SMCsampler(object):
         def iteration(k, a_cur, a_prev, hint):
             nonlocal cur, oth
             seed_r, seed_m = self._seed(1, k), self._seed(2, k)
+            # With a handful of live tiles the separate gather launch is the faster form (measured on B200, one tile: the
+            # indirect staging costs the latency-bound single-tile launch more than the gather launch it saves); the two
+            # forms give the same bits, so the choice may change from one iteration to the next.
+            fused = fused_gather and (hint if frozen else T) >= 8
 
             def resample():
                 L.check(lib.smcdet_resample(method, L.ptr(weights), None, seed_r, L.ptr(tids, torch.int64),
                                             L.ptr(a_cur, torch.int32), L.ptr(idx, torch.int64), L.ptr(cdf, torch.float64),
                                             T, n, L.stream_for(weights)))
-                L.check(lib.smcdet_gather(L.ptr(idx, torch.int64), L.ptr(cur[0]), L.ptr(cur[1]), L.ptr(cur[2]),
-                                          L.ptr(oth[0]), L.ptr(oth[1]), L.ptr(oth[2]), L.ptr(a_prev, torch.int32), T, n, d,
-                                          L.stream_for(weights)))
+                if not fused:
+                    L.check(lib.smcdet_gather(L.ptr(idx, torch.int64), L.ptr(cur[0]), L.ptr(cur[1]), L.ptr(cur[2]),
+                                              L.ptr(oth[0]), L.ptr(oth[1]), L.ptr(oth[2]), L.ptr(a_prev, torch.int32), T, n,
+                                              d, L.stream_for(weights)))
 
             def mutate():
+                # (fused gather: the launch reads the particles through the resampling indices itself and copies the
+                # tiles that finished in the previous iteration; a_prev = None means "every tile", as for smcdet_gather)
+                src = (idx, cur[0], cur[1], cur[2], a_prev if a_prev is not None else everything) if fused else None
                 mk.launch(prior, model, tiles, oth[0], oth[1], oth[2], tau, loglik, acc_count, status, seed=seed_m,
-                          offset=k, tile_ids=tids, active=a_cur, tile_of_segment=tmap, live_tiles_hint=hint, acc_as_count=True)
+                          offset=k, tile_ids=tids, active=a_cur, tile_of_segment=tmap, live_tiles_hint=hint, acc_as_count=True,
+                          resampled=src)
 
             def temper():
                 a_next = active[(k - base) % 2]  # (lock-step: written, never read)

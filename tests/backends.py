@@ -161,9 +161,11 @@ class GpuBackend:
         return co.cpu().numpy(), lo.cpu().numpy(), fo.cpu().numpy()
 
     def mh_mutate(self, model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-                  active=None, chain=False, mala=False, tile_of_segment=None, acc_init=-1.0):
+                  active=None, chain=False, mala=False, tile_of_segment=None, acc_init=-1.0, resampled=None):
         """``tile_of_segment`` [T] int: segment -> image map (uploaded and installed in a copy of ``mh``);
-        ``acc_init``: initial content of the acceptance output (0 for mh.acc_as_count = 1)."""
+        ``acc_init``: initial content of the acceptance output (0 for mh.acc_as_count = 1); ``resampled`` =
+        dict(index [T,N] int64, copy_mask [T] int32 or None): smcdet_mh_mutate_resampled -- counts / locs / fluxes are the
+        SOURCE arrays, the results (and ``counts``) come back in fresh arrays pre-filled with -7."""
         t = self.torch
         tiles, counts, locs, fluxes = self._d(tiles), self._d(counts), self._d(locs), self._d(fluxes)
         tau = self._d(np.reshape(tau, -1))
@@ -197,12 +199,26 @@ class GpuBackend:
             tr = A.MHTrace(la.data_ptr(), tg.data_ptr(), ac.data_ptr(), cl.data_ptr() if chain else None,
                            cf.data_ptr() if chain else None)
         act = self._d(active, np.int32)
-        fn = self.lib.smcdet_mala_mutate if mala else self.lib.smcdet_mh_mutate
-        self._check(fn(
-            C.byref(model), C.byref(prior), C.byref(mh), self._p(tiles), self._p(counts), self._p(locs), self._p(fluxes),
-            self._p(tau), self._p(ll), self._p(acc), C.byref(tp) if tp is not None else None,
-            C.byref(tr) if tr is not None else None, seed, offset, None, self._p(act), self._p(status), T, N, D, h, w,
-            self._stream()))
+        if resampled is not None:
+            idx = self._d(resampled["index"], np.int64)
+            cm = self._d(resampled.get("copy_mask"), np.int32)
+            src_locs, src_fluxes = locs, fluxes
+            locs, fluxes, counts_out = t.full_like(locs, -7.0), t.full_like(fluxes, -7.0), t.full_like(counts, -7.0)
+            v = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+            src = A.ResampledSource(v(idx), v(counts), v(src_locs), v(src_fluxes), v(counts_out), v(cm))
+            self._check(self.lib.smcdet_mh_mutate_resampled(
+                C.byref(model), C.byref(prior), C.byref(mh), self._p(tiles), C.byref(src), self._p(locs), self._p(fluxes),
+                self._p(tau), self._p(ll), self._p(acc), C.byref(tp) if tp is not None else None,
+                C.byref(tr) if tr is not None else None, seed, offset, None, self._p(act), self._p(status), T, N, D, h, w,
+                self._stream()))
+            out.update(counts=counts_out.cpu().numpy())
+        else:
+            fn = self.lib.smcdet_mala_mutate if mala else self.lib.smcdet_mh_mutate
+            self._check(fn(
+                C.byref(model), C.byref(prior), C.byref(mh), self._p(tiles), self._p(counts), self._p(locs), self._p(fluxes),
+                self._p(tau), self._p(ll), self._p(acc), C.byref(tp) if tp is not None else None,
+                C.byref(tr) if tr is not None else None, seed, offset, None, self._p(act), self._p(status), T, N, D, h, w,
+                self._stream()))
         if traces:
             out.update(log_alpha=la.cpu().numpy(), target_prop=tg.cpu().numpy(), accept=ac.cpu().numpy())
             if chain:

@@ -151,7 +151,9 @@ def gather(idx, counts, locs, fluxes):
 
 
 def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, seed=0, offset=0, traces=True,
-              active=None, chain=False, mala=False, tile_of_segment=None, acc_init=-1.0):
+              active=None, chain=False, mala=False, tile_of_segment=None, acc_init=-1.0, resampled=None):
+    """``resampled`` = dict(index [T,N] int64, copy_mask [T] int32 or None): smcdet_mh_mutate_resampled -- counts / locs /
+    fluxes are the SOURCE arrays, the results (and ``counts_out``) come back in fresh arrays pre-filled with -7."""
     tiles, counts = _f(tiles), _f(counts)
     locs, fluxes = _f(locs).copy(), _f(fluxes).copy()
     tau = _f(tau).reshape(-1)
@@ -187,11 +189,25 @@ def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, see
         if chain:
             out.update(chain_locs=cl, chain_fluxes=cf)
     act = np.ascontiguousarray(active, np.int32) if active is not None else None
-    fn = lib().smcdet_mala_mutate if mala else lib().smcdet_mh_mutate
-    check(fn(C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes),
-                                 _p(tau), _p(ll), _p(acc), C.byref(tp) if tp is not None else None,
-                                 C.byref(tr) if tr is not None else None, seed, offset, None, _p(act), _p(status),
-                                 T, N, D, h, w, None))
+    if resampled is not None:
+        idx = np.ascontiguousarray(resampled["index"], np.int64)
+        cm = resampled.get("copy_mask")
+        cm = np.ascontiguousarray(cm, np.int32) if cm is not None else None
+        src_locs, src_fluxes = locs, fluxes
+        locs, fluxes, counts_out = np.full_like(locs, -7.0), np.full_like(fluxes, -7.0), np.full_like(counts, -7.0)
+        src = A.ResampledSource(_p(idx).value, _p(counts).value, _p(src_locs).value, _p(src_fluxes).value,
+                                _p(counts_out).value, _p(cm).value if cm is not None else None)
+        check(lib().smcdet_mh_mutate_resampled(
+            C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), C.byref(src), _p(locs), _p(fluxes), _p(tau), _p(ll),
+            _p(acc), C.byref(tp) if tp is not None else None, C.byref(tr) if tr is not None else None, seed, offset, None,
+            _p(act), _p(status), T, N, D, h, w, None))
+        out.update(counts=counts_out)
+    else:
+        fn = lib().smcdet_mala_mutate if mala else lib().smcdet_mh_mutate
+        check(fn(C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes),
+                 _p(tau), _p(ll), _p(acc), C.byref(tp) if tp is not None else None,
+                 C.byref(tr) if tr is not None else None, seed, offset, None, _p(act), _p(status),
+                 T, N, D, h, w, None))
     out.update(locs=locs, fluxes=fluxes, loglik=ll, acc_rate=acc, status=int(status[0]))
     return out
 

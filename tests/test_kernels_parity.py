@@ -814,6 +814,52 @@ def test_segments_share_their_tiles_pixels(backend):
     assert np.array_equal(z["acc_rate"], z["accept"][-1].sum(-1).astype(np.float32))
 
 
+@pytest.mark.parametrize("name", ["mh_m71", "mh_gauss", "mh_m71_t16"])
+def test_gather_fused_into_the_mutation_equals_gather_then_mutate(backend, name):
+    """smcdet_mh_mutate_resampled (the resampling step's gather done by the mutation launch itself) against
+    smcdet_gather followed by smcdet_mh_mutate on the same injected draws: counts, catalogs, log-likelihoods, accept
+    decisions and acceptance rates bit-identical, for every lanes-per-particle decomposition; an inactive tile is left
+    alone or -- with its copy_mask entry set -- copied through its indices; the source arrays are not modified."""
+    g = Golden(name)
+    meta = g.meta
+    iters, T, N = min(meta["iters"], 4), meta["nside"] ** 2, meta["N"]
+    m, p = abi_model(meta), abi_prior(meta)
+    tiles, counts, locs, fluxes, tau = g.flat("tiles"), g.flat("counts"), g.flat("locs"), g.flat("fluxes"), g["tau"].reshape(-1)
+    rng = np.random.default_rng(4)
+    counts = counts.copy()
+    counts[:, ::3] -= 1.0                      # a few shorter catalogs, so the gathered counts matter
+    idx = rng.integers(0, N, (T, N)).astype(np.int64)
+    active = np.ones(T, np.int32)
+    active[-1] = 0
+    idx[-1] = np.arange(N)                     # (smcdet_resample writes the identity for inactive tiles)
+    tape = dict(comp=g["comp"][:iters], u_loc=g["u_loc"][:iters], u_flux=g["u_flux"][:iters], u_acc=g["u_acc"][:iters])
+    co, lo, fo = backend.gather(idx, counts, locs, fluxes)
+    try:
+        for tpp in TPPS[meta["tile"]]:
+            backend.force_tpp(tpp)
+            want = backend.mh_mutate(m, p, abi_mh(meta, iters), tiles, co, lo, fo, tau, tape=tape, active=active)
+            for copy_mask in (None, np.ones(T, np.int32)):
+                got = backend.mh_mutate(m, p, abi_mh(meta, iters), tiles, counts, locs, fluxes, tau, tape=tape, active=active,
+                                        resampled=dict(index=idx, copy_mask=copy_mask))
+                live = active.astype(bool)
+                for k in ("locs", "fluxes", "loglik", "accept"):
+                    a, b = got[k], want[k]
+                    if k == "accept":
+                        a, b = a[:, live], b[:, live]
+                    else:
+                        a, b = a[live], b[live]
+                    assert np.array_equal(a, b), (tpp, k)
+                assert np.array_equal(got["counts"][live], co[live]) and np.array_equal(got["acc_rate"], want["acc_rate"])
+                if copy_mask is None:          # the inactive tile's destination is untouched
+                    assert np.all(got["locs"][~live] == -7.0) and np.all(got["counts"][~live] == -7.0)
+                else:                          # ... or receives the tile's particles unchanged
+                    assert np.array_equal(got["locs"][~live], locs[~live]) and np.array_equal(got["fluxes"][~live], fluxes[~live])
+                    assert np.array_equal(got["counts"][~live], counts[~live])
+                assert got["status"] == want["status"]
+    finally:
+        backend.force_tpp(0)
+
+
 def test_loop_state_of_temper_update(backend):
     """smcdet_loop_state: the loop test of sampler.py:230 and the acceptance-rate division evaluated inside
     smcdet_temper_update -- active_next = [new temperature < 1], live_count += their number, acc_rate = acc_count / N

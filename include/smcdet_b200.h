@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMCDET_ABI_VERSION 7
+#define SMCDET_ABI_VERSION 8
 
 enum {
     SMCDET_E_INVALID = -1,     /* null pointer, non-positive size                          */
@@ -242,7 +242,16 @@ int smcdet_mh_mutate(const smcdet_model_params *model, const smcdet_prior_params
  * smcdet_mh_mutate_resampled, smcdet_temper_update -- the copy smcdet_gather would write and the
  * mutation read again is never made.  copy_mask [T] (nullable): tiles with active == 0 whose particles
  * still have to reach the destination arrays (their index is the identity).  Results are bit-identical
- * to smcdet_gather followed by smcdet_mh_mutate.  Source and destination arrays must not overlap. */
+ * to smcdet_gather followed by smcdet_mh_mutate.  Source and destination arrays must not overlap.
+ *
+ * rates / rates_out (ABI v8, both nullable, need loglik_out and mh->refresh_loglik): the expected-count image of
+ * every particle (ImageModel.loglikelihood's `rate`, smcdet/images.py:87-89, :163-167; [T,N,h*w], row-major
+ * pixels) carried from one launch of the SMC loop to the next.  rates_out receives the image of the FINAL state,
+ * which the launch renders from scratch anyway for loglik_out (sampler.py:100-102); rates, written as rates_out by
+ * the previous launch on the same tiles, is read through `index` like the catalogs and replaces the render of the
+ * ENTRY state (the log_denom_target evaluation of kernel.py:88-96).  Both renders run the same code on the same
+ * stars, so results are bit-identical with and without the carried images; a launch renders D stars per
+ * particle once instead of twice.  Tiles with active == 0 are neither read nor written. */
 typedef struct smcdet_resampled_source {
     const int64_t *index;    /* [T,N] from smcdet_resample                         */
     const float *counts;     /* [T,N]     source catalogs                           */
@@ -250,6 +259,8 @@ typedef struct smcdet_resampled_source {
     const float *fluxes;     /* [T,N,D]                                             */
     float *counts_out;       /* [T,N] destination of the gathered counts            */
     const int32_t *copy_mask; /* [T] nullable                                       */
+    const float *rates;      /* [T,N,h*w] nullable: rates_out of the previous launch */
+    float *rates_out;        /* [T,N,h*w] nullable                                  */
 } smcdet_resampled_source;
 
 int smcdet_mh_mutate_resampled(const smcdet_model_params *model, const smcdet_prior_params *prior,

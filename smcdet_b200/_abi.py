@@ -2,7 +2,7 @@
 
 import ctypes as C
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 MODEL_GAUSS_POISSON, MODEL_M71_NORMAL = 0, 1
 COUNT_DISCRETE_UNIFORM, COUNT_POISSON, COUNT_NONE = 0, 1, 2
@@ -69,7 +69,8 @@ class MHTrace(C.Structure):
 
 class ResampledSource(C.Structure):
     _fields_ = [("index", C.c_void_p), ("counts", C.c_void_p), ("locs", C.c_void_p), ("fluxes", C.c_void_p),
-                ("counts_out", C.c_void_p), ("copy_mask", C.c_void_p)]
+                ("counts_out", C.c_void_p), ("copy_mask", C.c_void_p), ("rates", C.c_void_p),
+                ("rates_out", C.c_void_p)]
 
 
 _P = C.c_void_p

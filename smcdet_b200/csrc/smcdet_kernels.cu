@@ -203,6 +203,33 @@ __device__ __forceinline__ void unstage_block(float* __restrict__ locs, float* _
     }
 }
 
+// The block's expected-count images between shared memory ([PPT/4][kBT] float4: lane `thread`, quad g at g * kBT + thread)
+// and HBM ([particle][HW] floats, row-major pixels: lane sub of a particle owns floats sub * PPT .. (sub + 1) * PPT), moved
+// by the whole block so that a warp touches 512 consecutive bytes of an image.  The HBM layout does not depend on the number
+// of lanes per particle, so consecutive launches may use different decompositions.
+template <int TPP, int PPT, int HW>
+__device__ __forceinline__ void load_rate_images(const float* __restrict__ rates_tile, const int64_t* __restrict__ idx,
+                                                 int n_here, float* s_rate) {
+    constexpr int Q = HW / 4, QL = PPT / 4;  // float4 per image / per lane
+    float4* dst = reinterpret_cast<float4*>(s_rate);
+    for (int i = threadIdx.x; i < n_here * Q; i += kBT) {
+        const int p = i / Q, q = i - p * Q;
+        const float4* src = reinterpret_cast<const float4*>(rates_tile + (size_t)idx[p] * HW);
+        dst[(q % QL) * kBT + p * TPP + q / QL] = src[q];
+    }
+}
+
+template <int TPP, int PPT, int HW>
+__device__ __forceinline__ void store_rate_images(float* __restrict__ rates_block, int n_here, const float* s_rate) {
+    constexpr int Q = HW / 4, QL = PPT / 4;
+    const float4* src = reinterpret_cast<const float4*>(s_rate);
+    float4* dst = reinterpret_cast<float4*>(rates_block);
+    for (int i = threadIdx.x; i < n_here * Q; i += kBT) {
+        const int p = i / Q, q = i - p * Q;
+        dst[i] = src[(q % QL) * kBT + p * TPP + q / QL];
+    }
+}
+
 // full render of the lane's pixels from the staged catalog (without the background)
 template <int MODEL, int RPT, int W, int PB>
 __device__ __forceinline__ void render_rows(const ModelK& m, const float* s_star, int pi, int D, int row0,
@@ -856,6 +883,10 @@ struct MHArgs {
     const float* fluxes_src;
     float* counts_out;
     const int32_t* copy_mask;
+    // expected-count images [T,N,HW] carried between the launches of the SMC loop (GATHER only, both nullable): rates_src is
+    // read through gather_index in place of the render of the entry state, rates_out receives the render of the final state
+    const float* rates_src;
+    float* rates_out;
 };
 
 #ifndef SMC_MH_MINB
@@ -899,6 +930,8 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         stage_tile<MODEL, HW, PPT>(a.tiles + (size_t)ti * HW, s_tile, s_lgam);
         stage_stars_gather<PB>(a.locs_src + (size_t)t * N * 2 * D, a.fluxes_src + (size_t)t * N * D, a.gather_index + pbase,
                                n_here, D, s_star);
+        if (a.rates_src != nullptr)
+            load_rate_images<TPP, PPT, HW>(a.rates_src + (size_t)t * N * HW, a.gather_index + pbase, n_here, s_rate);
     } else {
         stage_block<MODEL, HW, PB, PPT>(a.tiles + (size_t)ti * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
                                         s_tile, s_lgam, s_star);
@@ -964,8 +997,10 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     //   it = 0..iters-1  one MH sweep: rate' = rate - old star + new star on the lane's pixels
     //   it = iters       fresh full render of the final state -> loglik_out (what sampler.py:100-102 recomputes)
     const int it_end = a.mh.num_iters + ((a.loglik_out != nullptr && a.mh.refresh_loglik) ? 1 : 0);
+    const bool carried = GATHER && a.rates_src != nullptr;  // the entry state's rate image is in shared memory already
     for (int it = -1; it < it_end; ++it) {
         const bool full = (it < 0) || (it == a.mh.num_iters);
+        const bool render = full && !(carried && it < 0);
         int k = 0;
         bool frozen_slot = false;
         float u0 = 0.5f, u1 = 0.5f, uf = 0.5f, ua = 0.5f;
@@ -1070,7 +1105,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
                 if (pf != 0.0f) star_accumulate<MODEL, RPT, W>(m, pl0, pl1, m.c0 * pf, row0, acc);
             }
         }
-        const int ns = full ? D : ((MALA || frozen_slot) ? 0 : 2);
+        const int ns = full ? (render ? D : 0) : ((MALA || frozen_slot) ? 0 : 2);
 #pragma unroll 1
         for (int s = 0; s < ns; ++s) {
             float s0, s1, sw;
@@ -1087,7 +1122,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
             nxt = mh_draw_block(pidx, tile_key, a.offset, it + 1, a.seed);
             nxt_it = it + 1;
         }
-        if (full) {
+        if (render) {
 #pragma unroll
             for (int g = 0; g < PPT / 4; ++g) {
                 my_rate[g * kBT] = rate_plus(make_float4(m.bg, m.bg, m.bg, m.bg), acc[2 * g], acc[2 * g + 1]);
@@ -1193,6 +1228,9 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(a.acc_count + t, (float)__popc(votes));
     __syncthreads();
     unstage_block<PB>(a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D, s_star);
+    if constexpr (GATHER) {  // (the last pass was the fresh render of the final state: mutate_impl sees to that)
+        if (a.rates_out != nullptr) store_rate_images<TPP, PPT, HW>(a.rates_out + pbase * HW, n_here, s_rate);
+    }
 }
 
 __global__ void divide_kernel(float* v, const int32_t* active, float denom, int T) {
@@ -2022,6 +2060,12 @@ static int mutate_impl(bool mala, const smcdet_model_params* model, const smcdet
     if (source != nullptr) {
         a.gather_index = source->index; a.counts_src = source->counts; a.locs_src = source->locs;
         a.fluxes_src = source->fluxes; a.counts_out = source->counts_out; a.copy_mask = source->copy_mask;
+        // the carried images are those of a fresh render of the final state, which only the refresh pass makes
+        if (loglik_out != nullptr && mh->refresh_loglik) {
+            SMC_REQUIRE(source->rates == nullptr || source->rates != source->rates_out, SMCDET_E_INVALID,
+                        "smcdet_mh_mutate_resampled: rates and rates_out must differ");
+            a.rates_src = source->rates; a.rates_out = source->rates_out;
+        }
     }
     // acc_as_count: the caller keeps acc_rate zero-filled between launches and divides by N itself
     // (smcdet_temper_update does both through smcdet_loop_state), which saves two small launches per call

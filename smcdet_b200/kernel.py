@@ -56,9 +56,10 @@ class SingleComponentMH(object):
         """One call of the fused kernel on caller-owned, already flattened device buffers ([T, ...]; nothing is
         allocated or copied here).  ``run`` goes through it; ``SMCsampler`` calls it directly with its persistent
         state.  ``acc_as_count``: accept counts are ADDED to ``acc`` (see ``smcdet_mh_params`` in the header).
-        ``resampled`` = (index, counts_src, locs_src, fluxes_src, copy_mask): the gather of the resampling step is done
-        by the launch itself (``smcdet_mh_mutate_resampled``) -- particles are read from the source arrays through
-        ``index`` and ``counts`` / ``locs`` / ``fluxes`` are pure outputs."""
+        ``resampled`` = (index, counts_src, locs_src, fluxes_src, copy_mask[, rates, rates_out]): the gather of the
+        resampling step is done by the launch itself (``smcdet_mh_mutate_resampled``) -- particles are read from the
+        source arrays through ``index`` and ``counts`` / ``locs`` / ``fluxes`` are pure outputs; ``rates`` / ``rates_out``
+        [T, n, h*w] carry the particles' expected-count images from one launch to the next (see the header)."""
         T, n, d = fluxes.shape
         mp, pp, kp = model._params(), prior._params(), self._params()
         kp.acc_as_count = 1 if acc_as_count else 0
@@ -77,10 +78,11 @@ class SingleComponentMH(object):
         else:
             if self._entry != "smcdet_mh_mutate":
                 raise NotImplementedError("the fused gather exists for the MH kernel only")
-            index, counts_src, locs_src, fluxes_src, copy_mask = resampled
+            index, counts_src, locs_src, fluxes_src, copy_mask, rates, rates_out = (tuple(resampled) + (None, None))[:7]
             v = lambda p: None if p is None else p.value  # noqa: E731  (c_void_p fields take plain integers)
             src = A.ResampledSource(v(L.ptr(index, torch.int64)), v(L.ptr(counts_src)), v(L.ptr(locs_src)),
-                                    v(L.ptr(fluxes_src)), v(L.ptr(counts)), v(L.ptr(copy_mask, torch.int32)))
+                                    v(L.ptr(fluxes_src)), v(L.ptr(counts)), v(L.ptr(copy_mask, torch.int32)),
+                                    v(L.ptr(rates)), v(L.ptr(rates_out)))
             L.check(L.lib().smcdet_mh_mutate_resampled(C.byref(mp), C.byref(pp), C.byref(kp), L.ptr(tiles), C.byref(src),
                                                        *tail))
         if acc_as_count:

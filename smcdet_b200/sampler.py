@@ -458,6 +458,16 @@ class SMCsampler(object):
         # the MH kernel gathers the resampled particles itself (smcdet_mh_mutate_resampled): three launches per iteration
         fused_gather = bool(getattr(self, "fused_gather", True)) and getattr(mk, "_entry", "") == "smcdet_mh_mutate"
         everything = torch.ones(T, device=dev, dtype=torch.int32)
+        # expected-count images of all particles, carried from one mutation launch to the next (ABI v8: the launch then
+        # renders a catalog once, for the fresh log-likelihood of its final state, instead of twice); two sets, like the
+        # particles.  Same bits with and without; ``carry_rates = False`` (or more than ``carry_rates_max_bytes``) keeps
+        # the memory instead.
+        hw = int(self.tile_dim) ** 2
+        carry = (fused_gather and bool(getattr(self, "carry_rates", True)) and bool(getattr(mk, "refresh_loglik", True))
+                 and 2 * T * n * hw * 4 <= int(getattr(self, "carry_rates_max_bytes", 16 << 30)))
+        rates = [torch.empty(T, n, hw, device=dev) for _ in range(2)] if carry else None
+        rates_from = [None]  # iteration whose launch wrote rates[0]
+        self.carried_launches = 0  # mutation launches that took their entry images from the previous one
 
         def post(k):  # asynchronous read-back of live[k]
             host = ring[k % len(ring)]
@@ -491,6 +501,12 @@ class SMCsampler(object):
                 # (fused gather: the launch reads the particles through the resampling indices itself and copies the
                 # tiles that finished in the previous iteration; a_prev = None means "every tile", as for smcdet_gather)
                 src = (idx, cur[0], cur[1], cur[2], a_prev if a_prev is not None else everything) if fused else None
+                if fused and carry:
+                    # (every tile live now was live, and so written, in the previous iteration's launch)
+                    src += (rates[0] if rates_from[0] == k - 1 else None, rates[1])
+                    self.carried_launches += int(rates_from[0] == k - 1)
+                    rates.reverse()
+                    rates_from[0] = k
                 mk.launch(prior, model, tiles, oth[0], oth[1], oth[2], tau, loglik, acc_count, status, seed=seed_m,
                           offset=k, tile_ids=tids, active=a_cur, tile_of_segment=tmap, live_tiles_hint=hint, acc_as_count=True,
                           resampled=src)

@@ -205,13 +205,18 @@ class GpuBackend:
             src_locs, src_fluxes = locs, fluxes
             locs, fluxes, counts_out = t.full_like(locs, -7.0), t.full_like(fluxes, -7.0), t.full_like(counts, -7.0)
             v = lambda x: None if x is None else x.data_ptr()  # noqa: E731
-            src = A.ResampledSource(v(idx), v(counts), v(src_locs), v(src_fluxes), v(counts_out), v(cm))
+            # carried expected-count images: ``rates`` [T,N,h*w] (or None) is read, ``want_rates`` asks for rates_out
+            rin = self._d(resampled.get("rates"))
+            rout = t.full((T, N, h * w), -7.0, device=self.dev) if resampled.get("want_rates") else None
+            src = A.ResampledSource(v(idx), v(counts), v(src_locs), v(src_fluxes), v(counts_out), v(cm), v(rin), v(rout))
             self._check(self.lib.smcdet_mh_mutate_resampled(
                 C.byref(model), C.byref(prior), C.byref(mh), self._p(tiles), C.byref(src), self._p(locs), self._p(fluxes),
                 self._p(tau), self._p(ll), self._p(acc), C.byref(tp) if tp is not None else None,
                 C.byref(tr) if tr is not None else None, seed, offset, None, self._p(act), self._p(status), T, N, D, h, w,
                 self._stream()))
             out.update(counts=counts_out.cpu().numpy())
+            if rout is not None:
+                out.update(rates=rout.cpu().numpy())
         else:
             fn = self.lib.smcdet_mala_mutate if mala else self.lib.smcdet_mh_mutate
             self._check(fn(

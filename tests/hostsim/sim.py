@@ -195,13 +195,18 @@ def mh_mutate(model, prior, mh, tiles, counts, locs, fluxes, tau, tape=None, see
         cm = np.ascontiguousarray(cm, np.int32) if cm is not None else None
         src_locs, src_fluxes = locs, fluxes
         locs, fluxes, counts_out = np.full_like(locs, -7.0), np.full_like(fluxes, -7.0), np.full_like(counts, -7.0)
+        rin = _f(resampled["rates"]) if resampled.get("rates") is not None else None
+        rout = np.full((T, N, h * w), -7.0, np.float32) if resampled.get("want_rates") else None
         src = A.ResampledSource(_p(idx).value, _p(counts).value, _p(src_locs).value, _p(src_fluxes).value,
-                                _p(counts_out).value, _p(cm).value if cm is not None else None)
+                                _p(counts_out).value, _p(cm).value if cm is not None else None,
+                                _p(rin).value if rin is not None else None, _p(rout).value if rout is not None else None)
         check(lib().smcdet_mh_mutate_resampled(
             C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), C.byref(src), _p(locs), _p(fluxes), _p(tau), _p(ll),
             _p(acc), C.byref(tp) if tp is not None else None, C.byref(tr) if tr is not None else None, seed, offset, None,
             _p(act), _p(status), T, N, D, h, w, None))
         out.update(counts=counts_out)
+        if rout is not None:
+            out.update(rates=rout)
     else:
         fn = lib().smcdet_mala_mutate if mala else lib().smcdet_mh_mutate
         check(fn(C.byref(model), C.byref(prior), C.byref(mh), _p(tiles), _p(counts), _p(locs), _p(fluxes),

@@ -49,8 +49,9 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_abi.LoopState) == 4 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_abi.DrawTape) == 4 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_abi.MHTrace) == 5 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(_abi.ResampledSource) == 6 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_abi.ResampledSource) == 8 * ctypes.sizeof(ctypes.c_void_p)
     assert _abi.ResampledSource.counts_out.offset == 4 * ctypes.sizeof(ctypes.c_void_p)
+    assert _abi.ResampledSource.rates_out.offset == 7 * ctypes.sizeof(ctypes.c_void_p)
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu():

@@ -1076,6 +1076,37 @@ def test_host_ahead_loop_equals_the_plain_loop(max_iters, freeze, capsys):
         assert other is None
 
 
+@pytest.mark.parametrize("freeze", [True, False])
+def test_carried_rate_images_leave_a_run_unchanged(freeze):
+    """With ``refresh_loglik`` (the log-likelihood tempering sees is a fresh evaluation, reference sampler.py:100-102) the
+    fused loop hands every particle's expected-count image from one mutation launch to the next (ABI v8), so a launch
+    renders a catalog once instead of twice: same bits as with ``carry_rates = False``; without the refresh pass nothing
+    is carried."""
+    from smcdet_b200.sampler import SMCsampler
+
+    g = Golden("smc_stages_m71")
+    meta = g.meta
+    image = cu(g["image"]).repeat(2, 2).contiguous()  # 16 tiles: enough for the launches that gather by themselves
+
+    def run(carry, refresh):
+        torch.manual_seed(23)
+        model, prior, mh = build_objects(meta, iters=6)
+        mh.refresh_loglik = refresh
+        s = SMCsampler(image, meta["tile"], prior, model, mh, 768, 0.5, "multinomial", meta["flux_threshold"], 200,
+                       freeze_finished=freeze, verbose=False)
+        s.carry_rates = carry
+        s.run()
+        return s
+
+    for refresh in (True, False):
+        a, b = run(True, refresh), run(False, refresh)
+        assert a.iter == b.iter and b.carried_launches == 0
+        assert (a.carried_launches > 0) == refresh and a.carried_launches <= a.iter - 1
+        for k in ("locs", "fluxes", "counts", "weights", "temperature", "log_normalizing_constant", "loglik", "ess",
+                  "mutation_acc_rates", "pruned_counts", "pruned_fluxes", "weights_log_unnorm", "resampled_index"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (refresh, k)
+
+
 def test_end_to_end_posterior_within_monte_carlo_error_of_the_reference():
     """D = 10 end to end against stored runs of the unmodified reference (tests/golden/smc_stats_m71_d10.npz: 20 seeds
     of SMCsampler.run() on one 8x8 M71 tile, N = 2000, 25 MH sweeps): the mean over 20 seeds of this sampler's log

@@ -860,6 +860,73 @@ def test_gather_fused_into_the_mutation_equals_gather_then_mutate(backend, name)
         backend.force_tpp(0)
 
 
+@pytest.mark.parametrize("name", ["mh_m71", "mh_gauss", "mh_m71_t16"])
+def test_carried_rate_images_replace_the_entry_render(backend, name):
+    """smcdet_resampled_source.rates / rates_out (ABI v8): the expected-count images a launch writes for its final
+    state are the rate of ImageModel.loglikelihood for that state (smcdet_render), and a following launch that reads
+    them through its resampling indices -- whatever lanes-per-particle decomposition wrote or reads them -- returns
+    the same bits as one that renders its entry state itself; inactive tiles are neither read nor written; a launch
+    without the refresh pass ignores both pointers."""
+    g = Golden(name)
+    meta = g.meta
+    iters, T, N = min(meta["iters"], 3), meta["nside"] ** 2, meta["N"]
+    t = meta["tile"]
+    m, p = abi_model(meta), abi_prior(meta)
+    tiles, counts, locs, fluxes, tau = g.flat("tiles"), g.flat("counts"), g.flat("locs"), g.flat("fluxes"), g["tau"].reshape(-1)
+    rng = np.random.default_rng(11)
+    idx1, idx2 = (rng.integers(0, N, (T, N)).astype(np.int64) for _ in range(2))
+    active = np.ones(T, np.int32)
+    if T > 1:  # (a one-tile golden keeps its tile live)
+        active[-1] = 0
+        idx1[-1] = idx2[-1] = np.arange(N)
+    live = active.astype(bool)
+    tape = dict(comp=g["comp"][:iters], u_loc=g["u_loc"][:iters], u_flux=g["u_flux"][:iters], u_acc=g["u_acc"][:iters])
+    tpps = TPPS[t]
+    try:
+        firsts = {}
+        for tpp in tpps:
+            backend.force_tpp(tpp)
+            firsts[tpp] = backend.mh_mutate(m, p, abi_mh(meta, iters), tiles, counts, locs, fluxes, tau, tape=tape, active=active,
+                                            resampled=dict(index=idx1, want_rates=True), traces=False)
+        a = firsts[tpps[0]]
+        for tpp in tpps[1:]:  # the images do not depend on the decomposition that wrote them
+            assert np.array_equal(firsts[tpp]["rates"], a["rates"]) and np.array_equal(firsts[tpp]["locs"], a["locs"])
+        assert np.all(a["rates"][~live] == -7.0)
+        # [T,N,h*w] against the dense render [T,h,w,N] of the returned catalogs
+        dense = backend.render(m, a["locs"][live], a["fluxes"][live], t, t)
+        dense = np.moveaxis(dense.reshape(int(live.sum()), t * t, N), 1, 2)
+        assert np.allclose(a["rates"][live], dense, rtol=2e-6, atol=0)
+        poisoned = a["rates"].copy()
+        poisoned[~live] = np.nan  # never read
+        for tpp in tpps:
+            backend.force_tpp(tpp)
+            kw = dict(tape=tape, active=active, traces=True, offset=1)
+            want = backend.mh_mutate(m, p, abi_mh(meta, iters), tiles, a["counts"], a["locs"], a["fluxes"], tau,
+                                     resampled=dict(index=idx2, want_rates=True), **kw)
+            got = backend.mh_mutate(m, p, abi_mh(meta, iters), tiles, a["counts"], a["locs"], a["fluxes"], tau,
+                                    resampled=dict(index=idx2, rates=poisoned, want_rates=True), **kw)
+            for k in ("locs", "fluxes", "counts", "loglik", "rates", "accept", "log_alpha", "target_prop", "acc_rate"):
+                x, y = got[k], want[k]
+                if k in ("accept", "log_alpha", "target_prop"):
+                    x, y = x[:, live], y[:, live]
+                elif k != "acc_rate":
+                    x, y = x[live], y[live]
+                assert np.array_equal(x, y, equal_nan=True), (tpp, k)
+        # no refresh pass: the images a launch holds at its end are not fresh renders, so none are read or written
+        backend.force_tpp(0)
+        k = abi_mh(meta, iters)
+        k.refresh_loglik = 0
+        junk = np.full_like(a["rates"], 1e30)
+        plain = backend.mh_mutate(m, p, k, tiles, a["counts"], a["locs"], a["fluxes"], tau, tape=tape, active=active,
+                                  resampled=dict(index=idx2), traces=False)
+        got = backend.mh_mutate(m, p, k, tiles, a["counts"], a["locs"], a["fluxes"], tau, tape=tape, active=active,
+                                resampled=dict(index=idx2, rates=junk, want_rates=True), traces=False)
+        assert np.array_equal(got["locs"], plain["locs"]) and np.array_equal(got["loglik"], plain["loglik"])
+        assert np.all(got["rates"] == -7.0)
+    finally:
+        backend.force_tpp(0)
+
+
 def test_loop_state_of_temper_update(backend):
     """smcdet_loop_state: the loop test of sampler.py:230 and the acceptance-rate division evaluated inside
     smcdet_temper_update -- active_next = [new temperature < 1], live_count += their number, acc_rate = acc_count / N

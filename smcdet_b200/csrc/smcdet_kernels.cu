@@ -892,7 +892,9 @@ struct MHArgs {
 #ifndef SMC_MH_MINB
 #define SMC_MH_MINB 3
 #endif
-template <int MODEL, int H, int W, int TPP, bool MALA, bool GATHER = false>
+template <int MODEL, int H, int W, int TPP, bool MALA, bool GATHER = false, bool CARRY = false>
+// CARRY (with GATHER): the launches that read / write the carried expected-count images are instantiations of their own, so
+// that the sweep loop of the others is compiled as if the feature did not exist (it is that sensitive).
 // Resident blocks per SM: 3 for 64 pixels per lane (168 registers); 5 for 8 pixels per lane, the decomposition of
 // a single 8x8 tile -- 10 000 particles x 8 lanes are 625 blocks, which 5 x 148 slots take in ONE wave (4 x 148 do not)
 __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_MH_MINB : (((H / TPP) * W <= 8) ? 5 : 4)))
@@ -930,7 +932,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
         stage_tile<MODEL, HW, PPT>(a.tiles + (size_t)ti * HW, s_tile, s_lgam);
         stage_stars_gather<PB>(a.locs_src + (size_t)t * N * 2 * D, a.fluxes_src + (size_t)t * N * D, a.gather_index + pbase,
                                n_here, D, s_star);
-        if (a.rates_src != nullptr)
+        if (CARRY && a.rates_src != nullptr)
             load_rate_images<TPP, PPT, HW>(a.rates_src + (size_t)t * N * HW, a.gather_index + pbase, n_here, s_rate);
     } else {
         stage_block<MODEL, HW, PB, PPT>(a.tiles + (size_t)ti * HW, a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D,
@@ -997,7 +999,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     //   it = 0..iters-1  one MH sweep: rate' = rate - old star + new star on the lane's pixels
     //   it = iters       fresh full render of the final state -> loglik_out (what sampler.py:100-102 recomputes)
     const int it_end = a.mh.num_iters + ((a.loglik_out != nullptr && a.mh.refresh_loglik) ? 1 : 0);
-    const bool carried = GATHER && a.rates_src != nullptr;  // the entry state's rate image is in shared memory already
+    const bool carried = CARRY && a.rates_src != nullptr;  // the entry state's rate image is in shared memory already
     for (int it = -1; it < it_end; ++it) {
         const bool full = (it < 0) || (it == a.mh.num_iters);
         const bool render = full && !(carried && it < 0);
@@ -1228,7 +1230,7 @@ __global__ void __launch_bounds__(kBT, MALA ? 2 : (((H / TPP) * W >= 64) ? SMC_M
     if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(a.acc_count + t, (float)__popc(votes));
     __syncthreads();
     unstage_block<PB>(a.locs + pbase * 2 * D, a.fluxes + pbase * D, n_here, D, s_star);
-    if constexpr (GATHER) {  // (the last pass was the fresh render of the final state: mutate_impl sees to that)
+    if constexpr (CARRY) {  // (the last pass was the fresh render of the final state: mutate_impl sees to that)
         if (a.rates_out != nullptr) store_rate_images<TPP, PPT, HW>(a.rates_out + pbase * HW, n_here, s_rate);
     }
 }
@@ -1761,13 +1763,13 @@ int launch_loglik_t(const ModelK& m, const float* tiles, const float* locs, cons
     }
 }
 
-template <int MODEL, int H, int TPP, bool MALA, bool GATHER = false>
+template <int MODEL, int H, int TPP, bool MALA, bool GATHER = false, bool CARRY = false>
 int launch_mh_t(MHArgs& a, cudaStream_t st) {
     constexpr int PB = kBT / TPP, PPT = (H / TPP) * H;
     a.blocks_per_tile = (a.N + PB - 1) / PB;
     const size_t smem = sizeof(float) * (2 * TileLayout<PPT, H * H>::kSize + 3 * (size_t)a.D * PB + (size_t)PPT * kBT);
     if ((long long)a.T * a.blocks_per_tile >= (1LL << 31)) return fail(SMCDET_E_TOO_LARGE, "smcdet_mh_mutate: grid too large");
-    auto kern = mh_kernel<MODEL, H, H, TPP, MALA, GATHER>;
+    auto kern = mh_kernel<MODEL, H, H, TPP, MALA, GATHER, CARRY>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mh)");
@@ -1800,10 +1802,15 @@ template <int MODEL, int H, int TPP>
 int launch_mh_mala(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, true>(a, st); }
 template <int MODEL, int H, int TPP>
 int launch_mh_gather(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, false, true>(a, st); }
+template <int MODEL, int H, int TPP>
+int launch_mh_carry(MHArgs& a, cudaStream_t st) { return launch_mh_t<MODEL, H, TPP, false, true, true>(a, st); }
 
 template <int MODEL, int H>
 int dispatch_mh_tpp(int tpp, bool mala, MHArgs& a, cudaStream_t st) {
     if (mala) { SMC_DISPATCH_TPP(launch_mh_mala, MODEL, H, tpp, a, st) }
+    if (a.gather_index != nullptr && (a.rates_src != nullptr || a.rates_out != nullptr)) {
+        SMC_DISPATCH_TPP(launch_mh_carry, MODEL, H, tpp, a, st)
+    }
     if (a.gather_index != nullptr) { SMC_DISPATCH_TPP(launch_mh_gather, MODEL, H, tpp, a, st) }
     SMC_DISPATCH_TPP(launch_mh_plain, MODEL, H, tpp, a, st)
 }

@@ -10,10 +10,12 @@ from smcdet_b200.sampler import SMCsampler
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
 MODEL = os.environ.get("MODEL", "m71")   # m71 | gauss (BASELINE config 2 / config 1 shapes)
 GATHER = os.environ.get("GATHER", "1") != "0"
+CARRY = os.environ.get("CARRY", "0") != "0"    # refresh_loglik + expected-count images carried from the first launch to the second
 g = Golden("mh_m71" if MODEL == "m71" else "mh_gauss"); meta = dict(g.meta)
 meta["D"] = meta["min_objects"] = 10 if MODEL == "m71" else 8
 T, N, D = int(os.environ.get("T", 148)), 10000, meta["D"]
 model, prior, mh = build_objects(meta, iters=int(os.environ.get("ITERS", 100)))
+mh.refresh_loglik = CARRY
 tiles = torch.from_numpy(g["tiles"]).to(dev).reshape(-1, 8, 8)[:1].repeat(T, 1, 1).reshape(T, 1, 8, 8).contiguous()
 counts, locs, fluxes = prior._sample_grid(T, 1, None, True, N, seed=1)
 s = SMCsampler(tiles, 8, prior, model, mh, N, 0.5, "multinomial", 0.25, 100, verbose=False)
@@ -25,10 +27,14 @@ dst = [torch.empty_like(x) for x in src]
 tau = s.temperature.reshape(T).contiguous()
 loglik, acc, status = torch.empty(T, N, device=dev), torch.zeros(T, device=dev), torch.zeros(1, device=dev, dtype=torch.int32)
 tl = tiles.reshape(T, 8, 8)
-for _ in range(2):
+rates = [torch.empty(T, N, 64, device=dev) for _ in range(2)] if CARRY else None
+for rep in range(2):
     if GATHER:
+        extra = (rates[0] if rep else None, rates[1]) if CARRY else ()
         mh.launch(prior, model, tl, dst[0], dst[1], dst[2], tau, loglik, acc, status, seed=1, acc_as_count=True,
-                  resampled=(idx, src[0], src[1], src[2], None))
+                  resampled=(idx, src[0], src[1], src[2], None) + extra)
+        if CARRY:
+            rates.reverse()
     else:
         mh.run(tiles, counts, locs, fluxes, s.temperature, s.log_target, seed=1)
     model.loglikelihood(tiles, locs, fluxes)

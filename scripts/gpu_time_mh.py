@@ -37,4 +37,5 @@ for i in range(8):
         mh.run(tiles, counts, locs, fluxes, s.temperature, s.log_target, seed=1)
     e1.record()
     torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-print("mh launch ms:", [round(t, 3) for t in sorted(ts)[:5]])
+print("mh launch ms:", [round(t, 3) for t in sorted(ts)[:5]],
+      ("loglik sum %.6f acc %.1f" % (loglik.double().sum().item(), acc.sum().item() / 8)) if GATHER else "")

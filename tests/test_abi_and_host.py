@@ -67,6 +67,15 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert cdll.smcdet_loglik(ctypes.byref(m), None, None, None, None, 1, 1, 1, 8, 8, None) == _abi.E_INVALID
     assert cdll.smcdet_resample(5, None, None, 0, None, None, None, None, 1, 1, None) == _abi.E_INVALID
     assert cdll.smcdet_temper_update(None, None, None, 1.0, 1, None, None, None, None, None, None, None, 1, 1, None) == _abi.E_INVALID
+    # carried expected-count images (ABI v8): reading and writing the same buffer is refused before anything is launched
+    buf = [ctypes.create_string_buffer(64) for _ in range(12)]
+    ad = [ctypes.addressof(b) for b in buf]
+    pr, mh = _abi.PriorParams(), _abi.MHParams()
+    mh.num_iters, mh.refresh_loglik = 1, 1
+    src = _abi.ResampledSource(ad[0], ad[1], ad[2], ad[3], ad[4], None, ad[5], ad[5])
+    rc = cdll.smcdet_mh_mutate_resampled(ctypes.byref(m), ctypes.byref(pr), ctypes.byref(mh), ad[6], ctypes.byref(src), ad[7], ad[8],
+                                         ad[9], ad[10], ad[11], None, None, 0, 0, None, None, None, 1, 1, 1, 8, 8, None)
+    assert rc == _abi.E_INVALID and b"rates" in cdll.smcdet_last_error_string()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

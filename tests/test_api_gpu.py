@@ -1107,17 +1107,19 @@ def test_carried_rate_images_leave_a_run_unchanged(freeze):
             assert torch.equal(getattr(a, k), getattr(b, k)), (refresh, k)
 
 
-def test_posterior_is_calibrated_over_many_synthetic_images():
+@pytest.mark.parametrize("basic", [False, True])
+def test_posterior_is_calibrated_over_many_synthetic_images(basic):
     """The reference's own validation is statistical: coverage of posterior credible intervals over 1000 synthetic images
     (experiments/m71synthetic/results/results.ipynb cells 37-52).  Its exact form (tests/sbclib.py): 600 images drawn from
-    the very prior the sampler uses (M71 model, 3 stars), the reference's settings (10 000 catalogs, 100 MH sweeps), one
-    batched run -- the rank of the truth among the posterior draws must be uniform for every functional: mean rank and the
-    coverage of the central 50 % / 90 % intervals within 4 binomial standard errors.  (With 2 000 catalogs and 50 sweeps the
-    90 % intervals cover 82-86 %: the bands do detect an under-dispersed posterior.)"""
+    the very prior the sampler uses (3 stars; the M71 model, or the Gaussian-PSF / Poisson model of experiments/basic), the
+    reference's settings (10 000 catalogs, 100 MH sweeps), one batched run -- the rank of the truth among the posterior
+    draws must be uniform for every functional: mean rank and the coverage of the central 50 % / 90 % intervals within 4
+    binomial standard errors.  (With 2 000 catalogs and 50 sweeps the 90 % intervals of the M71 model cover 82-86 %: the bands
+    do detect an under-dispersed posterior.)"""
     from sbclib import sbc
 
     n = 600
-    res, iters = sbc(n, 10000, 3, 100, seed=0)
+    res, iters = sbc(n, 10000, 3, 100, seed=0, basic=basic)
     assert 5 < iters < 100
     for name, v in res.items():
         assert abs(v["mean_rank"] - 0.5) < 4 * 0.2887 / n ** 0.5, (name, v)

@@ -931,6 +931,39 @@ def test_carried_rate_images_replace_the_entry_render(backend, name):
         backend.force_tpp(0)
 
 
+def test_carried_rate_images_with_segments_and_live_only(backend, request):
+    """The carried images on generic segments (count strata sharing a tile's pixels through tile_of_segment, catalogs
+    shorter than the slot count, live_only sweeps, Philox draws): a launch that reads them returns the bits of one that
+    renders its entry state.  (Emulator tier only: written after the round's GPU budget was spent; the same source.)"""
+    if request.node.callspec.params["backend"] == "gpu":
+        pytest.skip("checked on the CPU emulator")
+    g = Golden("mh_m71")
+    meta = g.meta
+    m, p = abi_model(meta), abi_prior(meta)
+    tiles, tau = g.flat("tiles"), g["tau"].reshape(-1)
+    T, N = g.flat("counts").shape
+    D = meta["D"]
+    seg = np.repeat(np.arange(T), 2).astype(np.int32)[::-1].copy()
+    S = seg.size
+    rng = np.random.default_rng(8)
+    locs, fluxes = g.flat("locs")[seg].copy(), g.flat("fluxes")[seg].copy()
+    counts = rng.integers(0, D + 1, (S, N)).astype(np.float32)
+    fluxes[np.arange(D)[None, None, :] >= counts[:, :, None]] = 0.0   # empty slots (prior.py:61-62)
+    taus = np.repeat(tau, 2)[::-1].copy()
+    k = abi_mh(meta, 3)
+    k.live_only = 1
+    idx1, idx2 = (rng.integers(0, N, (S, N)).astype(np.int64) for _ in range(2))
+    a = backend.mh_mutate(m, p, k, tiles, counts, locs, fluxes, taus, seed=5, offset=1, tile_of_segment=seg, traces=False,
+                          resampled=dict(index=idx1, want_rates=True))
+    kw = dict(seed=5, offset=2, tile_of_segment=seg, traces=True)
+    want = backend.mh_mutate(m, p, k, tiles, a["counts"], a["locs"], a["fluxes"], taus, resampled=dict(index=idx2, want_rates=True), **kw)
+    got = backend.mh_mutate(m, p, k, tiles, a["counts"], a["locs"], a["fluxes"], taus,
+                            resampled=dict(index=idx2, rates=a["rates"], want_rates=True), **kw)
+    for key in ("locs", "fluxes", "counts", "loglik", "rates", "accept", "log_alpha", "acc_rate"):
+        assert np.array_equal(got[key], want[key], equal_nan=True), key
+    assert got["accept"].any() and (a["counts"] == np.take_along_axis(counts, idx1, 1)).all()
+
+
 def test_loop_state_of_temper_update(backend):
     """smcdet_loop_state: the loop test of sampler.py:230 and the acceptance-rate division evaluated inside
     smcdet_temper_update -- active_next = [new temperature < 1], live_count += their number, acc_rate = acc_count / N
